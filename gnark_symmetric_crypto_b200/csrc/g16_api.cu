@@ -1,0 +1,508 @@
+// C-ABI of libg16b200.so (include/g16b200.h). Host code only. Every entry point converts exceptions into status codes;
+// nothing propagates across the ABI. There is no CPU fallback: without a CUDA device these functions return G16_ERR_CUDA.
+#include "../../include/g16b200.h"
+#include "g16_ctx.cuh"
+#include <mutex>
+#include <random>
+
+using namespace g16;
+
+struct g16_ctx {
+    std::unique_ptr<Ctx> cx;
+    std::mutex mu;
+};
+
+struct g16_msm_plan {
+    int group, device, c;
+    uint32_t n;
+    DevBuf<G1Affine> p1;
+    DevBuf<G2Affine> p2;
+    DevBuf<Fr> scalars;
+    int scalars_mont = 0;
+    MsmWorkspace<G1> ws1;
+    MsmWorkspace<G2> ws2;
+    DevBuf<G1Affine> o1;
+    DevBuf<G2Affine> o2;
+    StageTimer tm;
+    cudaStream_t stream = nullptr;
+    ~g16_msm_plan() { if (stream) cudaStreamDestroy(stream); }
+};
+
+static thread_local std::string t_last_error;
+
+template <class F>
+static int guarded(F&& fn) {
+    try {
+        fn();
+        t_last_error.clear();
+        return G16_OK;
+    } catch (const ParseError& e) {
+        t_last_error = e.what();
+        return G16_ERR_PARSE;
+    } catch (const CudaError& e) {
+        t_last_error = e.what();
+        return G16_ERR_CUDA;
+    } catch (const std::domain_error& e) {
+        t_last_error = e.what();
+        return G16_ERR_UNSAT;
+    } catch (const std::invalid_argument& e) {
+        t_last_error = e.what();
+        return G16_ERR_ARG;
+    } catch (const std::bad_alloc&) {
+        t_last_error = "out of host memory";
+        return G16_ERR_ARG;
+    } catch (const std::exception& e) {
+        t_last_error = e.what();
+        return G16_ERR_UNSUPPORTED;
+    } catch (...) {
+        t_last_error = "unknown error";
+        return G16_ERR_UNSUPPORTED;
+    }
+}
+#define REQUIRE(cond, msg) do { if (!(cond)) throw std::invalid_argument(msg); } while (0)
+
+static void require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) throw CudaError("no CUDA device available (libg16b200 has no CPU fallback)");
+}
+
+// OS CSPRNG, rejection-sampled into [0, r)  (gnark draws r, s with fr.Element.SetRandom from crypto/rand)
+static void random_scalars_be(uint8_t* out, size_t count) {
+    static const uint8_t R_BE[32] = {0x30, 0x64, 0x4e, 0x72, 0xe1, 0x31, 0xa0, 0x29, 0xb8, 0x50, 0x45, 0xb6, 0x81, 0x81, 0x58, 0x5d,
+                                     0x28, 0x33, 0xe8, 0x48, 0x79, 0xb9, 0x70, 0x91, 0x43, 0xe1, 0xf5, 0x93, 0xf0, 0x00, 0x00, 0x01};
+    std::random_device rd("/dev/urandom");
+    for (size_t i = 0; i < count; i++) {
+        uint8_t* o = out + 32 * i;
+        for (;;) {
+            for (int k = 0; k < 32; k += 4) {
+                uint32_t v = rd();
+                memcpy(o + k, &v, 4);
+            }
+            o[0] &= 0x3F;
+            if (memcmp(o, R_BE, 32) < 0) break;
+        }
+    }
+}
+
+static void stage_rs(Ctx& c, size_t n, const uint8_t* rs) {
+    std::vector<uint8_t> tmp;
+    if (!rs) {
+        tmp.resize(64 * n);
+        random_scalars_be(tmp.data(), 2 * n);
+        rs = tmp.data();
+    }
+    c.d_rs_be.upload(rs, 64 * n, c.stream);
+    G16_CUDA(cudaStreamSynchronize(c.stream));   // tmp must outlive the copy
+}
+
+static void prove_witness_impl(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, const uint8_t* rs,
+                               uint8_t* proof_out, size_t* proof_len, uint64_t* msm_g1_out, uint64_t* msm_g2_out,
+                               uint64_t* h_out) {
+    REQUIRE(ctx && witness && proof_out, "NULL argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Ctx& c = *ctx->cx;
+    REQUIRE(n_witness == (size_t)c.n_public - 1 + c.n_secret, "witness length must be nbPublic-1+nbSecret");
+    G16_CUDA(cudaSetDevice(c.device));
+    c.d_witness.upload((const Fr*)witness, n_witness, c.stream);
+    stage_rs(c, 1, rs);
+    c.staged = 1;
+    c.staged_is_chacha = false;
+    ctx_run_batch(c, 1, false);
+    c.d_proofs.download(proof_out, c.proof_bytes(), c.stream);
+    if (proof_len) *proof_len = c.proof_bytes();
+    if (msm_g1_out) {
+        DevBuf<G1Affine> aff(4);
+        DevBuf<G1XYZZ> x(4);
+        const G1XYZZ* src[4] = {c.resA.p, c.resB1.p, c.resK.p, c.resZ.p};
+        for (int i = 0; i < 4; i++) G16_CUDA(cudaMemcpyAsync(x.p + i, src[i], sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, c.stream));
+        xyzz_to_affine_g1(x.p, 4, aff.p, c.stream);
+        aff.download((G1Affine*)msm_g1_out, 4, c.stream);
+        G16_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    if (msm_g2_out) {
+        DevBuf<G2Affine> aff(1);
+        xyzz_to_affine_g2(c.resB2.p, 1, aff.p, c.stream);
+        aff.download((G2Affine*)msm_g2_out, 1, c.stream);
+        G16_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    if (h_out) c.Aev.download((Fr*)h_out, c.n_dom, c.stream);
+    G16_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+static int log2_exact(size_t n) {
+    int k = 0;
+    while (((size_t)1 << k) < n) k++;
+    if (((size_t)1 << k) != n) throw std::invalid_argument("n must be a power of two");
+    return k;
+}
+
+extern "C" {
+
+int g16_version(void) { return 100; }
+const char* g16_last_error(void) { return t_last_error.c_str(); }
+int g16_device_count(int* n) {
+    return guarded([&] {
+        REQUIRE(n, "n is NULL");
+        G16_CUDA(cudaGetDeviceCount(n));
+    });
+}
+
+int g16_init(const uint8_t* pk, size_t pk_len, const uint8_t* r1cs, size_t r1cs_len, int device, g16_ctx** out) {
+    return guarded([&] {
+        REQUIRE(pk && r1cs && out, "NULL argument");
+        require_device();
+        std::unique_ptr<g16_ctx> h(new g16_ctx());
+        h->cx = ctx_create(pk, pk_len, r1cs, r1cs_len, device);
+        *out = h.release();
+    });
+}
+void g16_free(g16_ctx* ctx) {
+    if (!ctx) return;
+    try {
+        cudaSetDevice(ctx->cx->device);
+        delete ctx;
+    } catch (...) {
+    }
+}
+int g16_info(const g16_ctx* ctx, uint64_t info[16]) {
+    return guarded([&] {
+        REQUIRE(ctx && info, "NULL argument");
+        const Ctx& c = *ctx->cx;
+        uint64_t v[16] = {c.n_dom, c.nA, c.nB, c.nZ, c.nK, c.nB2, c.nb_wires, c.n_public, c.n_secret, c.n_constraints,
+                          c.n_instr, c.nlevels, c.n_commit, c.proof_bytes(), (uint64_t)c.device,
+                          (uint64_t)(c.solver_supported ? 1 : 0)};
+        memcpy(info, v, sizeof(v));
+    });
+}
+
+int g16_chacha_batch_stage(g16_ctx* ctx, size_t n, const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters,
+                           const uint8_t* inputs, const uint8_t* rs) {
+    return guarded([&] {
+        REQUIRE(ctx && keys && nonces && counters && inputs, "NULL argument");
+        REQUIRE(n > 0 && n <= (1u << 20), "batch size out of range");
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        Ctx& c = *ctx->cx;
+        REQUIRE(c.n_public == 1153 && c.n_secret == 256, "context does not hold the ChaCha20 circuit");
+        G16_CUDA(cudaSetDevice(c.device));
+        c.d_keys.upload(keys, 32 * n, c.stream);
+        c.d_nonces.upload(nonces, 12 * n, c.stream);
+        c.d_counters.upload(counters, n, c.stream);
+        c.d_inputs.upload(inputs, 64 * n, c.stream);
+        stage_rs(c, n, rs);
+        c.staged = n;
+        c.staged_is_chacha = true;
+    });
+}
+int g16_chacha_batch_run(g16_ctx* ctx, float* ms) {
+    return guarded([&] {
+        REQUIRE(ctx, "NULL argument");
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        Ctx& c = *ctx->cx;
+        REQUIRE(c.staged > 0 && c.staged_is_chacha, "no staged ChaCha batch");
+        G16_CUDA(cudaSetDevice(c.device));
+        float t = ctx_run_batch(c, c.staged, true);
+        if (ms) *ms = t;
+    });
+}
+int g16_chacha_batch_fetch(g16_ctx* ctx, uint8_t* proofs_out, uint8_t* ct_out) {
+    return guarded([&] {
+        REQUIRE(ctx && proofs_out, "NULL argument");
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        Ctx& c = *ctx->cx;
+        REQUIRE(c.staged > 0, "no staged batch");
+        G16_CUDA(cudaSetDevice(c.device));
+        c.d_proofs.download(proofs_out, c.staged * c.proof_bytes(), c.stream);
+        if (ct_out) c.d_ct.download(ct_out, c.staged * 64, c.stream);
+        G16_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+int g16_prove_chacha_batch(g16_ctx* ctx, size_t n, const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters,
+                           const uint8_t* inputs, const uint8_t* rs, uint8_t* proofs_out, uint8_t* ct_out) {
+    int rc = g16_chacha_batch_stage(ctx, n, keys, nonces, counters, inputs, rs);
+    if (rc) return rc;
+    rc = g16_chacha_batch_run(ctx, nullptr);
+    if (rc) return rc;
+    return g16_chacha_batch_fetch(ctx, proofs_out, ct_out);
+}
+int g16_last_stage_ms(const g16_ctx* ctx, float ms[8]) {
+    return guarded([&] {
+        REQUIRE(ctx && ms, "NULL argument");
+        memcpy(ms, ctx->cx->stage_ms, sizeof(float) * 8);
+    });
+}
+
+int g16_prove_witness(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, const uint8_t* rs, uint8_t* proof_out,
+                      size_t* proof_len) {
+    return guarded([&] { prove_witness_impl(ctx, witness, n_witness, rs, proof_out, proof_len, nullptr, nullptr, nullptr); });
+}
+int g16_prove_witness_detail(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, const uint8_t* rs, uint8_t* proof_out,
+                             size_t* proof_len, uint64_t* msm_g1_out, uint64_t* msm_g2_out, uint64_t* h_out) {
+    return guarded([&] { prove_witness_impl(ctx, witness, n_witness, rs, proof_out, proof_len, msm_g1_out, msm_g2_out, h_out); });
+}
+
+int g16_solve(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, size_t batch, uint64_t* W, uint64_t* A, uint64_t* B,
+              uint64_t* C) {
+    return guarded([&] {
+        REQUIRE(ctx && witness && batch > 0, "bad argument");
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        Ctx& c = *ctx->cx;
+        REQUIRE(n_witness == (size_t)c.n_public - 1 + c.n_secret, "witness length must be nbPublic-1+nbSecret");
+        if (!c.solver_supported) throw std::runtime_error("unsupported circuit: " + c.solver_unsupported_reason);
+        G16_CUDA(cudaSetDevice(c.device));
+        cudaStream_t st = c.stream;
+        ctx_ensure_batch(c, batch);
+        c.d_witness.upload((const Fr*)witness, n_witness * batch, st);
+        G16_CUDA(cudaMemsetAsync(c.d_status.p, 0, 4, st));
+        G16_CUDA(cudaMemsetAsync(c.Aev.p, 0, batch * c.n_dom * sizeof(Fr), st));
+        G16_CUDA(cudaMemsetAsync(c.Bev.p, 0, batch * c.n_dom * sizeof(Fr), st));
+        G16_CUDA(cudaMemsetAsync(c.Cev.p, 0, batch * c.n_dom * sizeof(Fr), st));
+        launch_witness_copy(c.d_witness.p, (uint32_t)n_witness, (uint32_t)batch, c.W.p, (size_t)c.nb_wires, st);
+        launch_solver(c.sp, (uint32_t)batch, c.W.p, (size_t)c.nb_wires, c.Aev.p, c.Bev.p, c.Cev.p, c.d_status.p, st);
+        uint32_t status = 0;
+        c.d_status.download(&status, 1, st);
+        if (W) c.W.download((Fr*)W, batch * c.nb_wires, st);
+        for (size_t i = 0; i < batch; i++) {
+            if (A) G16_CUDA(cudaMemcpyAsync(A + i * 4 * c.n_constraints, c.Aev.p + i * c.n_dom, (size_t)c.n_constraints * 32, cudaMemcpyDeviceToHost, st));
+            if (B) G16_CUDA(cudaMemcpyAsync(B + i * 4 * c.n_constraints, c.Bev.p + i * c.n_dom, (size_t)c.n_constraints * 32, cudaMemcpyDeviceToHost, st));
+            if (C) G16_CUDA(cudaMemcpyAsync(C + i * 4 * c.n_constraints, c.Cev.p + i * c.n_dom, (size_t)c.n_constraints * 32, cudaMemcpyDeviceToHost, st));
+        }
+        G16_CUDA(cudaStreamSynchronize(st));
+        if (status & 4u) throw std::runtime_error("solver: unsupported hint");
+        if (status & 3u) throw std::domain_error("witness does not satisfy the constraint system");
+    });
+}
+
+int g16_compute_h(g16_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c_in, uint64_t* h_out) {
+    return guarded([&] {
+        REQUIRE(ctx && a && b && c_in && h_out, "NULL argument");
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        Ctx& c = *ctx->cx;
+        G16_CUDA(cudaSetDevice(c.device));
+        cudaStream_t st = c.stream;
+        ctx_ensure_batch(c, 1);
+        const uint64_t* src[3] = {a, b, c_in};
+        Fr* dst[3] = {c.Aev.p, c.Bev.p, c.Cev.p};
+        for (int i = 0; i < 3; i++) {
+            G16_CUDA(cudaMemsetAsync(dst[i], 0, c.n_dom * sizeof(Fr), st));
+            G16_CUDA(cudaMemcpyAsync(dst[i], src[i], (size_t)c.n_constraints * 32, cudaMemcpyHostToDevice, st));
+        }
+        compute_h_run(c.dom, c.Aev.p, c.Bev.p, c.Cev.p, c.n_dom, 1, st);
+        c.Aev.download((Fr*)h_out, c.n_dom, st);
+        G16_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ stage-level: fields, groups
+int g16_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    return guarded([&] {
+        REQUIRE(a && out && (field == 0 || field == 1) && op >= 0 && op <= 7, "bad argument");
+        REQUIRE(b || op >= 3, "binary op needs b");
+        require_device();
+        DevBuf<uint64_t> da, db, dout(4 * n);
+        da.upload(a, 4 * n);
+        if (b) db.upload(b, 4 * n);
+        launch_field_op(field, op, da.p, b ? db.p : nullptr, dout.p, n, 0);
+        dout.download(out, 4 * n);
+        G16_CUDA(cudaDeviceSynchronize());
+    });
+}
+int g16_group_op(int group, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    return guarded([&] {
+        REQUIRE(a && out && (group == 1 || group == 2) && op >= 0 && op <= 3, "bad argument");
+        REQUIRE(b || op == 2, "op needs b");
+        require_device();
+        size_t pw = group == 1 ? 8 : 16;
+        size_t bw = (op == 0 || op == 3) ? pw : 4;
+        DevBuf<uint64_t> da, db, dout(pw * n);
+        da.upload(a, pw * n);
+        if (b) db.upload(b, bw * n);
+        launch_group_op(group, op, da.p, b ? db.p : nullptr, dout.p, n, 0);
+        dout.download(out, pw * n);
+        G16_CUDA(cudaDeviceSynchronize());
+    });
+}
+int g16_decompress(int group, const uint8_t* in, uint64_t* out, size_t n) {
+    return guarded([&] {
+        REQUIRE(in && out && (group == 1 || group == 2), "bad argument");
+        require_device();
+        DevBuf<uint8_t> din;
+        DevBuf<uint32_t> err(1);
+        err.zero();
+        din.upload(in, n * (group == 1 ? 32 : 64));
+        if (group == 1) {
+            DevBuf<G1Affine> o(n);
+            launch_decompress_g1(din.p, (uint32_t)n, o.p, err.p, 0);
+            o.download((G1Affine*)out, n);
+            G16_CUDA(cudaDeviceSynchronize());
+        } else {
+            DevBuf<G2Affine> o(n);
+            launch_decompress_g2(din.p, (uint32_t)n, o.p, err.p, 0);
+            o.download((G2Affine*)out, n);
+            G16_CUDA(cudaDeviceSynchronize());
+        }
+        uint32_t e = 0;
+        err.download(&e, 1);
+        G16_CUDA(cudaDeviceSynchronize());
+        if (e) throw ParseError("point decompression failed (flags=" + std::to_string(e) + ")");
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ stage-level: MSM
+int g16_msm_plan_create(int group, const uint64_t* points, size_t n, int window, int device, g16_msm_plan** out) {
+    return guarded([&] {
+        REQUIRE(points && out && (group == 1 || group == 2), "bad argument");
+        REQUIRE(n > 0 && n <= (1u << 26), "n out of range");
+        require_device();
+        G16_CUDA(cudaSetDevice(device));
+        std::unique_ptr<g16_msm_plan> p(new g16_msm_plan());
+        p->group = group; p->device = device; p->n = (uint32_t)n;
+        p->c = window > 0 ? window : msm_pick_window(n);
+        REQUIRE(p->c >= 2 && p->c <= 24, "window out of range");
+        G16_CUDA(cudaStreamCreate(&p->stream));
+        if (group == 1) { p->p1.upload((const G1Affine*)points, n, p->stream); p->o1.alloc(1); }
+        else { p->p2.upload((const G2Affine*)points, n, p->stream); p->o2.alloc(1); }
+        p->scalars.alloc(n);
+        G16_CUDA(cudaStreamSynchronize(p->stream));
+        *out = p.release();
+    });
+}
+int g16_msm_plan_set_scalars(g16_msm_plan* plan, const uint64_t* scalars, int scalars_mont) {
+    return guarded([&] {
+        REQUIRE(plan && scalars, "NULL argument");
+        G16_CUDA(cudaSetDevice(plan->device));
+        plan->scalars.upload((const Fr*)scalars, plan->n, plan->stream);
+        plan->scalars_mont = scalars_mont;
+        G16_CUDA(cudaStreamSynchronize(plan->stream));
+    });
+}
+int g16_msm_plan_run(g16_msm_plan* plan, uint64_t* out, float ms[4]) {
+    return guarded([&] {
+        REQUIRE(plan && out, "NULL argument");
+        G16_CUDA(cudaSetDevice(plan->device));
+        cudaStream_t st = plan->stream;
+        MsmShape sh = msm_make_shape(plan->n, 1, plan->c, 0);
+        plan->tm.reset();
+        if (plan->group == 1) {
+            msm_run_g1(plan->ws1, sh, plan->p1.p, plan->scalars.p, plan->n, nullptr, plan->scalars_mont, st, &plan->tm);
+            xyzz_to_affine_g1(plan->ws1.result.p, 1, plan->o1.p, st);
+            plan->o1.download((G1Affine*)out, 1, st);
+        } else {
+            msm_run_g2(plan->ws2, sh, plan->p2.p, plan->scalars.p, plan->n, nullptr, plan->scalars_mont, st, &plan->tm);
+            xyzz_to_affine_g2(plan->ws2.result.p, 1, plan->o2.p, st);
+            plan->o2.download((G2Affine*)out, 1, st);
+        }
+        G16_CUDA(cudaStreamSynchronize(st));
+        if (ms) {
+            float per[ST_COUNT];
+            ms[0] = plan->tm.finish(per);
+            ms[1] = per[ST_MSM_ACC];
+            ms[2] = per[ST_MSM_SORT];
+            ms[3] = per[ST_MSM_REDUCE];
+        }
+    });
+}
+void g16_msm_plan_free(g16_msm_plan* plan) {
+    if (!plan) return;
+    try {
+        cudaSetDevice(plan->device);
+        delete plan;
+    } catch (...) {
+    }
+}
+int g16_msm(int group, const uint64_t* points, const uint64_t* scalars, int scalars_mont, size_t n, int window, uint64_t* out,
+            float ms[4]) {
+    g16_msm_plan* p = nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int rc = g16_msm_plan_create(group, points, n, window, dev, &p);
+    if (rc) return rc;
+    rc = g16_msm_plan_set_scalars(p, scalars, scalars_mont);
+    if (!rc) rc = g16_msm_plan_run(p, out, ms);
+    std::string keep = t_last_error;
+    g16_msm_plan_free(p);
+    t_last_error = keep;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ stage-level: NTT
+int g16_ntt(uint64_t* data, size_t n, int inverse, int coset, float* ms) {
+    return guarded([&] {
+        REQUIRE(data && n >= 2 && n <= (1u << 26), "bad argument");
+        require_device();
+        int k = log2_exact(n);
+        NttDomain d;
+        ntt_standalone_domain(d, k, 0);
+        DevBuf<Fr> a, t(n);
+        a.upload((const Fr*)data, n);
+        cudaEvent_t e0, e1;
+        G16_CUDA(cudaEventCreate(&e0));
+        G16_CUDA(cudaEventCreate(&e1));
+        G16_CUDA(cudaEventRecord(e0, 0));
+        if (!inverse) {
+            // natural -> (bit reversal) -> DIT with optional coset pre-scaling on the bit-reversed side
+            ntt_bitrev(a.p, t.p, k, 0);
+            ntt_run(d, t.p, n, 1, false, false, coset ? d.scale_coset_only.p : nullptr, 0);
+        } else {
+            // DIF with the inverse root, scaled on the bit-reversed side, then back to natural order
+            ntt_run(d, a.p, n, 1, true, true, coset ? d.scale_coset_inv.p : d.scale_ninv.p, 0);
+            ntt_bitrev(a.p, t.p, k, 0);
+        }
+        G16_CUDA(cudaEventRecord(e1, 0));
+        t.download((Fr*)data, n);
+        G16_CUDA(cudaDeviceSynchronize());
+        if (ms) cudaEventElapsedTime(ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    });
+}
+
+// forward DIF then inverse DIT (bit-reversed in between): a round trip that must reproduce the input exactly.
+// checksum = number of mismatching elements after the last round trip (0 = exact).
+int g16_ntt_bench(size_t n, size_t batch, int iters, float* ms_per_iter, uint64_t* checksum) {
+    return guarded([&] {
+        REQUIRE(n >= 2 && n <= (1u << 26) && batch >= 1 && iters >= 1 && ms_per_iter, "bad argument");
+        require_device();
+        int k = log2_exact(n);
+        NttDomain d;
+        ntt_standalone_domain(d, k, 0);
+        size_t total = n * batch;
+        DevBuf<Fr> a(total), ref(total);
+        DevBuf<uint32_t> mism(1);
+        mism.zero();
+        ntt_fill_pattern(ref.p, total, 0);
+        G16_CUDA(cudaMemcpy(a.p, ref.p, total * sizeof(Fr), cudaMemcpyDeviceToDevice));
+        cudaEvent_t e0, e1;
+        G16_CUDA(cudaEventCreate(&e0));
+        G16_CUDA(cudaEventCreate(&e1));
+        // warm-up round trip
+        ntt_run(d, a.p, n, (uint32_t)batch, true, false, nullptr, 0);
+        ntt_run(d, a.p, n, (uint32_t)batch, false, true, d.scale_ninv.p, 0);
+        G16_CUDA(cudaEventRecord(e0, 0));
+        for (int it = 0; it < iters; it++) {
+            ntt_run(d, a.p, n, (uint32_t)batch, true, false, nullptr, 0);
+            ntt_run(d, a.p, n, (uint32_t)batch, false, true, d.scale_ninv.p, 0);
+        }
+        G16_CUDA(cudaEventRecord(e1, 0));
+        ntt_count_mismatches(a.p, ref.p, total, mism.p, 0);
+        uint32_t m = 0;
+        mism.download(&m, 1);
+        G16_CUDA(cudaDeviceSynchronize());
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_per_iter = ms / (float)(2 * iters);   // per transform
+        if (checksum) *checksum = m;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    });
+}
+
+int g16_imad_peak(double* imad_per_s, double* imad_wide_per_s, double* modmul_per_s) {
+    return guarded([&] {
+        REQUIRE(imad_per_s && imad_wide_per_s && modmul_per_s, "NULL argument");
+        require_device();
+        imad_peak_measure(imad_per_s, imad_wide_per_s, modmul_per_s);
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,377 @@
+// Prover context: one (proving key, constraint system) pair resident on one GPU, and the batched prove pipeline.
+// Host code only — every kernel is launched through the wrappers of msm_types.hpp / ntt_api.hpp / prover_api.hpp.
+// Replaces gnark v0.11.0 backend/groth16/bn254/prove.go:64-295 (Prove) and marshal.go:311-348 (ProvingKey.ReadFrom),
+// as driven by libraries/prover/impl/prove_impl.go:65-114 (InitAlgorithm) and provers.go:79-158 (proveChaCha).
+#pragma once
+#include "common.cuh"
+#include "host_parse.hpp"
+#include "msm_types.hpp"
+#include "ntt_api.hpp"
+#include "prover_api.hpp"
+#include <memory>
+
+namespace g16 {
+
+struct PrecompQuery {
+    DevBuf<G1Affine> table;
+    DevBuf<uint32_t> map;   // scalar index (wire id) of point i ; empty = identity
+    uint32_t n = 0;
+    int c = 0;
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // sizes
+    uint64_t n_dom = 0;
+    int k_dom = 0;
+    uint32_t nA = 0, nB = 0, nZ = 0, nK = 0, nB2 = 0;
+    uint32_t nb_wires = 0, n_public = 0, n_secret = 0, n_constraints = 0, n_instr = 0, nlevels = 0, n_commit = 0;
+    // key material
+    DevBuf<G1Affine> A, B, Z, K;
+    DevBuf<G2Affine> B2;
+    PrecompQuery qA, qB, qZ, qK;
+    DevBuf<G2Affine> tabB2;
+    int cB2 = 0;
+    AssemblyKeys keys;
+    NttDomain dom;
+    // solver program
+    DevBuf<uint32_t> d_calldata, d_level_instr, d_level_off;
+    DevBuf<InsMeta> d_meta;
+    DevBuf<Fr> d_coeffs, d_ucoef_inv, d_lookup_tabs;
+    SolverProgram sp;
+    bool solver_supported = true;
+    std::string solver_unsupported_reason;
+    // batch state
+    size_t staged = 0;
+    bool staged_is_chacha = false;
+    DevBuf<uint8_t> d_keys, d_nonces, d_inputs, d_rs_be, d_ct, d_proofs;
+    DevBuf<uint32_t> d_counters, d_status;
+    DevBuf<Fr> d_rs, d_witness, W, Aev, Bev, Cev;
+    MsmWorkspace<G1> ws1;
+    MsmWorkspace<G2> ws2;
+    DevBuf<G1XYZZ> resA, resB1, resK, resZ;
+    DevBuf<G2XYZZ> resB2;
+    StageTimer timer;
+    float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    size_t launches = 0;
+    uint32_t sub_batch = 64;
+
+    ~Ctx() {
+        if (stream) cudaStreamDestroy(stream);
+    }
+    size_t proof_bytes() const { return 164; }
+};
+
+static inline int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return atoi(v);
+}
+
+static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, const uint8_t* r1cs_bytes, size_t r1cs_len,
+                                       int device) {
+    std::unique_ptr<Ctx> cx(new Ctx());
+    cx->device = device;
+    G16_CUDA(cudaSetDevice(device));
+    G16_CUDA(cudaStreamCreate(&cx->stream));
+    cudaStream_t st = cx->stream;
+    cx->sub_batch = (uint32_t)env_int("G16_SUBBATCH", 64);
+    if (cx->sub_batch == 0) cx->sub_batch = 1;
+
+    PkFile pk = parse_pk(pk_bytes, pk_len);
+    R1csFile cs = parse_r1cs(r1cs_bytes, r1cs_len);
+    if (pk.nb_wires != cs.n_wires()) throw ParseError("pk and r1cs disagree on the number of wires");
+    if (pk.n_commit_keys != cs.commitments.size()) throw ParseError("pk and r1cs disagree on the number of commitments");
+    uint64_t need = 1;
+    while (need < cs.n_constraints) need <<= 1;
+    if (need != pk.n) throw ParseError("pk domain size does not match the constraint count");
+    cx->n_dom = pk.n;
+    while ((1ull << cx->k_dom) < pk.n) cx->k_dom++;
+    cx->nA = pk.nA; cx->nB = pk.nB; cx->nZ = pk.nZ; cx->nK = pk.nK; cx->nB2 = pk.nB2;
+    cx->nb_wires = (uint32_t)pk.nb_wires;
+    cx->n_public = (uint32_t)cs.n_public; cx->n_secret = (uint32_t)cs.n_secret;
+    cx->n_constraints = (uint32_t)cs.n_constraints;
+    cx->n_instr = (uint32_t)cs.n_instr(); cx->nlevels = (uint32_t)cs.levels.size();
+    cx->n_commit = (uint32_t)cs.commitments.size();
+
+    // ---- decompress the key on the GPU (~89k Fp + 12.5k Fp2 square roots)
+    DevBuf<uint32_t> err(1);
+    err.zero(st);
+    auto decompress1 = [&](const uint8_t* raw, uint32_t n, DevBuf<G1Affine>& out) {
+        DevBuf<uint8_t> d;
+        d.upload(raw, (size_t)n * 32, st);
+        out.alloc(n);
+        launch_decompress_g1(d.p, n, out.p, err.p, st);
+        G16_CUDA(cudaStreamSynchronize(st));
+    };
+    auto decompress2 = [&](const uint8_t* raw, uint32_t n, DevBuf<G2Affine>& out) {
+        DevBuf<uint8_t> d;
+        d.upload(raw, (size_t)n * 64, st);
+        out.alloc(n);
+        launch_decompress_g2(d.p, n, out.p, err.p, st);
+        G16_CUDA(cudaStreamSynchronize(st));
+    };
+    DevBuf<G1Affine> abd;
+    DevBuf<G2Affine> bd2;
+    decompress1(pk.g1_abd, 3, abd);
+    decompress1(pk.A, pk.nA, cx->A);
+    decompress1(pk.B, pk.nB, cx->B);
+    decompress1(pk.Z, pk.nZ, cx->Z);
+    decompress1(pk.K, pk.nK, cx->K);
+    decompress2(pk.g2_bd, 2, bd2);
+    decompress2(pk.B2, pk.nB2, cx->B2);
+    uint32_t herr = 0;
+    err.download(&herr, 1, st);
+    G16_CUDA(cudaStreamSynchronize(st));
+    if (herr) throw ParseError("pk: point decompression failed (flags=" + std::to_string(herr) + ")");
+    {
+        G1Affine h1[3];
+        G2Affine h2[2];
+        abd.download(h1, 3, st);
+        bd2.download(h2, 2, st);
+        G16_CUDA(cudaStreamSynchronize(st));
+        cx->keys.alpha = h1[0]; cx->keys.beta = h1[1]; cx->keys.delta = h1[2];
+        cx->keys.beta2 = h2[0]; cx->keys.delta2 = h2[1];
+    }
+
+    // ---- wire maps of the four G1 queries (the G2 query shares B's)
+    std::vector<uint32_t> mapA, mapB, mapK;
+    for (uint32_t w = 0; w < cx->nb_wires; w++) {
+        if (!pk.inf_a[w]) mapA.push_back(w);
+        if (!pk.inf_b[w]) mapB.push_back(w);
+    }
+    {
+        std::vector<uint8_t> skip(cx->nb_wires, 0);
+        for (auto& ci : cs.commitments) {
+            for (uint32_t w : ci.private_committed) if (w < cx->nb_wires) skip[w] = 1;
+            if (ci.commitment_index < cx->nb_wires) skip[ci.commitment_index] = 1;
+        }
+        for (uint32_t w = cx->n_public; w < cx->nb_wires; w++) if (!skip[w]) mapK.push_back(w);
+    }
+    if (mapA.size() != pk.nA || mapB.size() != pk.nB) throw ParseError("pk: infinity masks do not match the query sizes");
+    if (mapK.size() != pk.nK) throw ParseError("pk: len(G1.K) does not match the private wires of the r1cs");
+    cx->qA.map.upload(mapA.data(), mapA.size(), st);
+    cx->qB.map.upload(mapB.data(), mapB.size(), st);
+    cx->qK.map.upload(mapK.data(), mapK.size(), st);
+    G16_CUDA(cudaStreamSynchronize(st));
+
+    // ---- fixed-base tables: table[w][i] = 2^(c w) * P_i, so each MSM needs a single bucket set per proof
+    cx->qZ.c = env_int("G16_C_Z", 16);
+    cx->qA.c = env_int("G16_C_A", 13);
+    cx->qB.c = env_int("G16_C_B", 13);
+    cx->qK.c = env_int("G16_C_K", 13);
+    cx->cB2 = env_int("G16_C_B2", 13);
+    cx->qA.n = pk.nA; cx->qB.n = pk.nB; cx->qZ.n = pk.nZ; cx->qK.n = pk.nK;
+    auto nwin = [](int c) { return (254 + c - 1) / c; };
+    cx->qA.table.alloc((size_t)pk.nA * nwin(cx->qA.c));
+    cx->qB.table.alloc((size_t)pk.nB * nwin(cx->qB.c));
+    cx->qZ.table.alloc((size_t)pk.nZ * nwin(cx->qZ.c));
+    cx->qK.table.alloc((size_t)pk.nK * nwin(cx->qK.c));
+    cx->tabB2.alloc((size_t)pk.nB2 * nwin(cx->cB2));
+    msm_precompute_g1(cx->A.p, pk.nA, nwin(cx->qA.c), cx->qA.c, cx->qA.table.p, st);
+    msm_precompute_g1(cx->B.p, pk.nB, nwin(cx->qB.c), cx->qB.c, cx->qB.table.p, st);
+    msm_precompute_g1(cx->Z.p, pk.nZ, nwin(cx->qZ.c), cx->qZ.c, cx->qZ.table.p, st);
+    msm_precompute_g1(cx->K.p, pk.nK, nwin(cx->qK.c), cx->qK.c, cx->qK.table.p, st);
+    msm_precompute_g2(cx->B2.p, pk.nB2, nwin(cx->cB2), cx->cB2, cx->tabB2.p, st);
+    G16_CUDA(cudaStreamSynchronize(st));
+
+    // ---- FFT domain from the pk header (w, g big-endian canonical -> Montgomery on the device)
+    {
+        DevBuf<uint8_t> hb;
+        hb.upload(&pk.fr_hdr[0][0], 160, st);
+        DevBuf<Fr> hm(5);
+        fr_be_to_mont(hb.p, 5, hm.p, st);
+        Fr h[5];
+        hm.download(h, 5, st);
+        G16_CUDA(cudaStreamSynchronize(st));
+        ntt_domain_init(cx->dom, cx->k_dom, h[1], h[3], st);
+    }
+
+    // ---- solver program: static analysis of which wire every R1C defines (instruction order is a valid schedule,
+    //      SURVEY.md Appendix E), then upload
+    {
+        std::vector<uint8_t> solved(cx->nb_wires, 0);
+        for (uint32_t w = 0; w < cx->n_public + cx->n_secret; w++) solved[w] = 1;
+        std::vector<InsMeta> meta(cs.n_instr());
+        std::vector<uint32_t> lk_index(cs.bp_kind.size(), 0);
+        uint32_t ntab = 0;
+        for (size_t b = 0; b < cs.bp_kind.size(); b++) if (cs.bp_kind[b] == INS_LOOKUP) lk_index[b] = ntab++;
+        const std::vector<uint32_t>& cd = cs.calldata;
+        for (size_t i = 0; i < cs.n_instr(); i++) {
+            InsMeta& m = meta[i];
+            uint64_t s0 = cs.start[i];
+            if (s0 >= cd.size() || s0 + cd[s0] > cd.size()) throw ParseError("r1cs: instruction calldata out of range");
+            m.cd_start = (uint32_t)s0;
+            uint8_t kind = cs.bp_kind[cs.bp_id[i]];
+            m.kind = kind;
+            m.solve_wire = SOLVE_WIRE_NONE;
+            m.cons_off = cs.cons_off[i];
+            m.wire_off = cs.wire_off[i];
+            m.lookup_tab = lk_index[cs.bp_id[i]];
+            if (kind == INS_R1C) {
+                uint32_t n[3] = {cd[s0 + 1], cd[s0 + 2], cd[s0 + 3]};
+                size_t pos = s0 + 4;
+                int uside = -1;
+                uint32_t uw = SOLVE_WIRE_NONE;
+                for (int side = 0; side < 3; side++)
+                    for (uint32_t t = 0; t < n[side]; t++) {
+                        uint32_t wid = cd[pos + 1];
+                        pos += 2;
+                        if (wid == WIRE_CONST) continue;
+                        if (wid >= cx->nb_wires) throw ParseError("r1cs: wire id out of range");
+                        if (!solved[wid]) {
+                            if (uside >= 0 && (uside != side || uw != wid)) throw ParseError("r1cs: constraint with two unknown wires");
+                            uside = side; uw = wid;
+                        }
+                    }
+                if (m.cons_off >= cx->n_constraints) throw ParseError("r1cs: constraint offset out of range");
+                if (uside >= 0) { m.solve_wire = uw; m.kind |= (uint32_t)uside << 8; solved[uw] = 1; }
+            } else if (kind == INS_HINT) {
+                uint32_t hid = cd[s0 + 1], nin = cd[s0 + 2];
+                size_t pos = s0 + 3;
+                for (uint32_t k = 0; k < nin; k++) { uint32_t nt = cd[pos]; pos += 1 + 2 * (size_t)nt; }
+                uint32_t o0 = cd[pos], o1 = cd[pos + 1];
+                if (o1 < o0 || o1 > cx->nb_wires) throw ParseError("r1cs: hint output range out of bounds");
+                for (uint32_t w = o0; w < o1; w++) solved[w] = 1;
+                if (hid != HINT_NBITS) {
+                    cx->solver_supported = false;
+                    cx->solver_unsupported_reason = "hint id " + std::to_string(hid) + " (commitment / log-derivative hints) is not implemented on the device yet";
+                }
+            } else {
+                uint32_t nin = cd[s0 + 2];
+                if (m.wire_off + nin > cx->nb_wires) throw ParseError("r1cs: lookup output range out of bounds");
+                for (uint32_t k = 0; k < nin; k++) solved[m.wire_off + k] = 1;
+            }
+        }
+        for (uint32_t w = 0; w < cx->nb_wires; w++) if (!solved[w]) throw ParseError("r1cs: wire " + std::to_string(w) + " is never defined");
+        std::vector<uint32_t> lvl_instr, lvl_off(1, 0);
+        for (auto& lv : cs.levels) {
+            for (uint32_t id : lv) {
+                if (id >= cs.n_instr()) throw ParseError("r1cs: level references unknown instruction");
+                lvl_instr.push_back(id);
+            }
+            lvl_off.push_back((uint32_t)lvl_instr.size());
+        }
+        if (lvl_instr.size() != cs.n_instr()) throw ParseError("r1cs: levels do not cover every instruction exactly once");
+        // lookup tables: entry k of table t = coeffs[cid] of the single constant term of that entry (pure gather)
+        std::vector<uint64_t> tabs((size_t)(ntab ? ntab : 1) * 256 * 4, 0);
+        for (size_t b = 0; b < cs.bp_kind.size(); b++) {
+            if (cs.bp_kind[b] != INS_LOOKUP) continue;
+            const auto& ec = cs.bp_lookup_entries[b];
+            size_t q = 0, ent = 0;
+            while (q < ec.size() && ent < 256) {
+                uint32_t nt = ec[q++];
+                if (nt != 1 || q + 2 > ec.size() || ec[q + 1] != WIRE_CONST || ec[q] * 4ull + 4 > cs.coeffs.size())
+                    throw ParseError("r1cs: unsupported lookup table entry");
+                memcpy(&tabs[((size_t)lk_index[b] * 256 + ent) * 4], &cs.coeffs[(size_t)ec[q] * 4], 32);
+                q += 2;
+                ent++;
+            }
+        }
+        cx->d_calldata.upload(cd.data(), cd.size(), st);
+        cx->d_meta.upload(meta.data(), meta.size(), st);
+        cx->d_level_instr.upload(lvl_instr.data(), lvl_instr.size(), st);
+        cx->d_level_off.upload(lvl_off.data(), lvl_off.size(), st);
+        cx->d_coeffs.upload((const Fr*)cs.coeffs.data(), cs.coeffs.size() / 4, st);
+        cx->d_lookup_tabs.upload((const Fr*)tabs.data(), tabs.size() / 4, st);
+        cx->d_ucoef_inv.alloc(cs.n_instr());
+        SolverProgram& sp = cx->sp;
+        sp.calldata = cx->d_calldata.p; sp.meta = cx->d_meta.p; sp.level_instr = cx->d_level_instr.p;
+        sp.level_off = cx->d_level_off.p; sp.coeffs = cx->d_coeffs.p; sp.ucoef_inv = cx->d_ucoef_inv.p;
+        sp.lookup_tabs = cx->d_lookup_tabs.p; sp.nlevels = cx->nlevels; sp.n_wires = cx->nb_wires;
+        sp.n_dom = (uint32_t)cx->n_dom; sp.fast_coeffs = 0;
+        G16_CUDA(cudaStreamSynchronize(st));   // host vectors above must outlive the copies
+        sp.fast_coeffs = launch_solver_init(sp, (uint32_t)cs.n_instr(), (uint32_t)(cs.coeffs.size() / 4), cx->d_ucoef_inv.p, st);
+    }
+    if (cx->n_commit) {
+        cx->solver_supported = false;
+        if (cx->solver_unsupported_reason.empty()) cx->solver_unsupported_reason = "circuits with BSB22 commitments are not supported yet";
+    }
+    cx->d_status.alloc(1);
+    return cx;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// batch pipeline. Inputs must already be on the device: either the ChaCha request arrays (d_keys, ...) or d_witness.
+// ---------------------------------------------------------------------------------------------------------------------
+static void ctx_ensure_batch(Ctx& cx, size_t n) {
+    cx.W.ensure(n * cx.nb_wires);
+    cx.Aev.ensure(n * cx.n_dom);
+    cx.Bev.ensure(n * cx.n_dom);
+    cx.Cev.ensure(n * cx.n_dom);
+    cx.resA.ensure(n); cx.resB1.ensure(n); cx.resK.ensure(n); cx.resZ.ensure(n); cx.resB2.ensure(n);
+    cx.d_proofs.ensure(n * cx.proof_bytes());
+    cx.d_ct.ensure(n * 64);
+    cx.d_rs.ensure(2 * n);
+}
+
+static void run_query_g1(Ctx& cx, const PrecompQuery& q, const Fr* scalars, size_t row_stride, bool use_map, uint32_t rows,
+                         G1XYZZ* out, StageTimer* tm) {
+    MsmShape sh = msm_make_shape(q.n, rows, q.c, 1);
+    msm_run_g1(cx.ws1, sh, q.table.p, scalars, row_stride, use_map ? q.map.p : nullptr, 1, cx.stream, tm);
+    G16_CUDA(cudaMemcpyAsync(out, cx.ws1.result.p, (size_t)rows * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, cx.stream));
+}
+
+// returns device ms (sum over stages). Leaves proofs in d_proofs. Throws on unsatisfied witness.
+static float ctx_run_batch(Ctx& cx, size_t n, bool chacha) {
+    if (!cx.solver_supported) throw std::runtime_error("unsupported circuit: " + cx.solver_unsupported_reason);
+    cudaStream_t st = cx.stream;
+    ctx_ensure_batch(cx, n);
+    StageTimer& tm = cx.timer;
+    tm.reset();
+    size_t l0 = cx.ws1.launches + cx.ws2.launches + cx.dom.launches;
+    size_t own = 0;
+    tm.mark(ST_SOLVE, st);
+    G16_CUDA(cudaMemsetAsync(cx.d_status.p, 0, 4, st));
+    G16_CUDA(cudaMemsetAsync(cx.Aev.p, 0, n * cx.n_dom * sizeof(Fr), st));
+    G16_CUDA(cudaMemsetAsync(cx.Bev.p, 0, n * cx.n_dom * sizeof(Fr), st));
+    G16_CUDA(cudaMemsetAsync(cx.Cev.p, 0, n * cx.n_dom * sizeof(Fr), st));
+    if (chacha) {
+        launch_chacha_witness(cx.d_keys.p, cx.d_nonces.p, cx.d_counters.p, cx.d_inputs.p, (uint32_t)n, cx.W.p,
+                              (size_t)cx.nb_wires, cx.d_ct.p, st);
+    } else {
+        launch_witness_copy(cx.d_witness.p, cx.n_public - 1 + cx.n_secret, (uint32_t)n, cx.W.p, (size_t)cx.nb_wires, st);
+    }
+    launch_scalars_from_be(cx.d_rs_be.p, (uint32_t)(2 * n), cx.d_rs.p, st);
+    launch_solver(cx.sp, (uint32_t)n, cx.W.p, (size_t)cx.nb_wires, cx.Aev.p, cx.Bev.p, cx.Cev.p, cx.d_status.p, st);
+    own += 3;
+    for (size_t sb = 0; sb < n; sb += cx.sub_batch) {
+        uint32_t rows = (uint32_t)((n - sb) < cx.sub_batch ? (n - sb) : cx.sub_batch);
+        Fr* a = cx.Aev.p + sb * cx.n_dom;
+        Fr* b = cx.Bev.p + sb * cx.n_dom;
+        Fr* c = cx.Cev.p + sb * cx.n_dom;
+        const Fr* w = cx.W.p + sb * cx.nb_wires;
+        tm.mark(ST_H, st);
+        compute_h_run(cx.dom, a, b, c, cx.n_dom, rows, st);
+        // h (gnark order) pairs index-for-index with G1.Z; the other queries read wire values through their maps
+        run_query_g1(cx, cx.qZ, a, cx.n_dom, false, rows, cx.resZ.p + sb, &tm);
+        run_query_g1(cx, cx.qA, w, cx.nb_wires, true, rows, cx.resA.p + sb, &tm);
+        run_query_g1(cx, cx.qB, w, cx.nb_wires, true, rows, cx.resB1.p + sb, &tm);
+        run_query_g1(cx, cx.qK, w, cx.nb_wires, true, rows, cx.resK.p + sb, &tm);
+        {
+            MsmShape sh = msm_make_shape(cx.nB2, rows, cx.cB2, 1);
+            msm_run_g2(cx.ws2, sh, cx.tabB2.p, w, cx.nb_wires, cx.qB.map.p, 1, st, &tm);
+            G16_CUDA(cudaMemcpyAsync(cx.resB2.p + sb, cx.ws2.result.p, (size_t)rows * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    tm.mark(ST_ASSEMBLE, st);
+    launch_assemble(cx.keys, (uint32_t)n, cx.resA.p, cx.resB1.p, cx.resK.p, cx.resZ.p, cx.resB2.p, cx.d_rs.p, cx.d_proofs.p,
+                    cx.proof_bytes(), st);
+    own += 1;
+    tm.mark(-1, st);
+    uint32_t status = 0;
+    cx.d_status.download(&status, 1, st);
+    G16_CUDA(cudaStreamSynchronize(st));
+    float per[ST_COUNT];
+    float total = tm.finish(per);
+    for (int i = 0; i < ST_COUNT; i++) cx.stage_ms[i] = per[i];
+    cx.stage_ms[6] = total;
+    cx.launches = own + (cx.ws1.launches + cx.ws2.launches + cx.dom.launches - l0);
+    cx.stage_ms[7] = (float)cx.launches;
+    if (status & 4u) throw std::runtime_error("solver: unsupported hint");
+    if (status & 3u) throw std::domain_error("witness does not satisfy the constraint system");
+    return total;
+}
+
+}  // namespace g16

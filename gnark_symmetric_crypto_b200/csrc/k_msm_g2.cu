@@ -1,0 +1,21 @@
+// G2 instantiation of the MSM pipeline (msm.cuh). Cold TU (built with -DG16_COLD): G2 is 6k additions per ChaCha proof, so code size wins over inlining.
+#include "msm.cuh"
+
+namespace g16 {
+
+void msm_run_g2(MsmWorkspace<G2>& ws, const MsmShape& sh, const G2Affine* bases, const Fr* scalars, size_t row_stride,
+                const uint32_t* map, int is_mont, cudaStream_t stream, StageTimer* tm, int chunk_len) {
+    msm_run<G2>(ws, sh, bases, scalars, row_stride, map, is_mont, stream, tm, chunk_len);
+}
+void msm_precompute_g2(const G2Affine* pts, uint32_t n, int nwin, int c, G2Affine* table, cudaStream_t stream) {
+    auto k = msm_precompute_kernel<G2>;
+    G16_LAUNCH(k, div_up(n, 64), 64, 0, stream, false, pts, n, nwin, c, table);
+    G16_CHECK_LAUNCH();
+}
+void xyzz_to_affine_g2(const G2XYZZ* in, uint32_t n, G2Affine* out, cudaStream_t stream) {
+    auto k = xyzz_to_affine_kernel<G2>;
+    G16_LAUNCH(k, div_up(n, 32), 32, 0, stream, false, in, n, out);
+    G16_CHECK_LAUNCH();
+}
+
+}  // namespace g16

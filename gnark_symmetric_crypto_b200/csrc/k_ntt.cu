@@ -1,0 +1,231 @@
+// Hot translation unit: NTT passes, compute_h, and the integer-multiply microbenchmarks (field product inlined).
+#include "ntt.cuh"
+
+namespace g16 {
+
+static std::vector<NttPass> ntt_plan(int k, bool dif) {
+    std::vector<NttPass> ps;
+    int m0 = k < NTT_MAX_TILE_LG ? k : NTT_MAX_TILE_LG;
+    NttPass c;
+    c.k = k; c.b_lo = 0; c.m = m0; c.q = 0; c.lg_tile = m0; c.dif = dif;
+    int rem = k - m0;
+    const int npass = (rem + 7) / 8;
+    std::vector<NttPass> strided;
+    int b = m0;
+    for (int i = 0; i < npass; i++) {
+        int m = rem / npass + (i < rem % npass ? 1 : 0);   // even split
+        NttPass s;
+        s.k = k; s.b_lo = b; s.m = m; s.q = NTT_MAX_TILE_LG - m; s.lg_tile = NTT_MAX_TILE_LG; s.dif = dif;
+        if (s.q > b) { s.q = b; s.lg_tile = s.m + s.q; }
+        strided.push_back(s);
+        b += m;
+    }
+    if (dif) {
+        for (int i = (int)strided.size() - 1; i >= 0; i--) ps.push_back(strided[i]);
+        ps.push_back(c);
+    } else {
+        ps.push_back(c);
+        for (auto& s : strided) ps.push_back(s);
+    }
+    return ps;
+}
+
+void ntt_domain_init(NttDomain& d, int k, const Fr& w, const Fr& g, cudaStream_t stream) {
+    d.k = k;
+    d.n = 1u << k;
+    DevBuf<Fr> consts(4);
+    G16_LAUNCH(ntt_domain_consts_kernel, 1, 1, 0, stream, false, w, g, d.n, consts.p);
+    G16_CHECK_LAUNCH();
+    Fr h[4];
+    consts.download(h, 4, stream);
+    G16_CUDA(cudaStreamSynchronize(stream));
+    Fr winv = h[0], ninv = h[1], ginv = h[2];
+    d.den = h[3];
+    uint32_t half = d.n > 1 ? d.n / 2 : 1;
+    d.tw_fwd.alloc(half);
+    d.tw_inv.alloc(half);
+    G16_LAUNCH(ntt_powers_kernel, div_up(half, 128), 128, 0, stream, false, w, half, d.tw_fwd.p);
+    G16_LAUNCH(ntt_powers_kernel, div_up(half, 128), 128, 0, stream, false, winv, half, d.tw_inv.p);
+    d.scale_ninv.alloc(d.n);
+    d.scale_coset_fwd.alloc(d.n);
+    d.scale_coset_inv.alloc(d.n);
+    d.scale_coset_only.alloc(d.n);
+    G16_LAUNCH(ntt_coset_table_kernel, div_up(d.n, 128), 128, 0, stream, false, Fr::one(), ninv, k, d.scale_ninv.p);
+    G16_LAUNCH(ntt_coset_table_kernel, div_up(d.n, 128), 128, 0, stream, false, g, ninv, k, d.scale_coset_fwd.p);
+    G16_LAUNCH(ntt_coset_table_kernel, div_up(d.n, 128), 128, 0, stream, false, ginv, ninv, k, d.scale_coset_inv.p);
+    G16_LAUNCH(ntt_coset_table_kernel, div_up(d.n, 128), 128, 0, stream, false, g, Fr::one(), k, d.scale_coset_only.p);
+    G16_CHECK_LAUNCH();
+    d.dif_passes = ntt_plan(k, true);
+    d.dit_passes = ntt_plan(k, false);
+    G16_CUDA(cudaStreamSynchronize(stream));
+}
+
+// 2^28-th root of unity of Fr, big-endian canonical
+static const uint8_t ROOT28_BE[32] = {0x2a, 0x3c, 0x09, 0xf0, 0xa5, 0x8a, 0x7e, 0x85, 0x00, 0xe0, 0xa7, 0xeb, 0x8e, 0xf6, 0x2a, 0xbc,
+                                      0x40, 0x2d, 0x11, 0x1e, 0x41, 0x11, 0x2e, 0xd4, 0x9b, 0xd6, 0x1b, 0x6e, 0x72, 0x5b, 0x19, 0xf0};
+
+void ntt_standalone_domain(NttDomain& d, int k, cudaStream_t st) {
+    DevBuf<uint8_t> rb;
+    rb.upload(ROOT28_BE, 32, st);
+    DevBuf<Fr> wg(2);
+    G16_LAUNCH(ntt_root_kernel, 1, 1, 0, st, false, rb.p, k, wg.p);
+    G16_CHECK_LAUNCH();
+    Fr h[2];
+    wg.download(h, 2, st);
+    G16_CUDA(cudaStreamSynchronize(st));
+    ntt_domain_init(d, k, h[0], h[1], st);
+}
+
+static void ntt_set_smem_attr() {
+#if !defined(G16_EMU)
+    // per device: the attribute belongs to the function in the current context
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !done[dev]) {
+        G16_CUDA(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)((size_t)32 << NTT_MAX_TILE_LG)));
+        done[dev] = true;
+    }
+#endif
+}
+
+void ntt_run(NttDomain& d, Fr* data, size_t vec_stride, uint32_t batch, bool dif, bool inverse_root, const Fr* scale,
+             cudaStream_t stream) {
+    ntt_set_smem_attr();
+    const std::vector<NttPass>& ps = dif ? d.dif_passes : d.dit_passes;
+    const Fr* tw = inverse_root ? d.tw_inv.p : d.tw_fwd.p;
+    for (const NttPass& p : ps) {
+        if (p.m == 0) continue;
+        dim3 grid(d.n >> p.lg_tile, batch);
+        size_t smem = (size_t)32 << p.lg_tile;
+        const Fr* sc = (p.b_lo == 0) ? scale : nullptr;
+        G16_LAUNCH(ntt_pass_kernel, grid, NTT_THREADS, smem, stream, true, data, vec_stride, p, tw, sc);
+        d.launches++;
+    }
+    G16_CHECK_LAUNCH();
+}
+
+void compute_h_run(NttDomain& d, Fr* a, Fr* b, Fr* c, size_t vec_stride, uint32_t batch, cudaStream_t stream) {
+    if (vec_stride != d.n) throw std::invalid_argument("compute_h: vectors must be contiguous (stride == n)");
+    Fr* v[3] = {a, b, c};
+    for (int i = 0; i < 3; i++) {
+        ntt_run(d, v[i], vec_stride, batch, true, true, d.scale_coset_fwd.p, stream);    // iNTT, then * g^i / n
+        ntt_run(d, v[i], vec_stride, batch, false, false, nullptr, stream);              // evaluate on the coset
+    }
+    size_t total = (size_t)batch * vec_stride;
+    G16_LAUNCH(h_pointwise_kernel, div_up(total, 256), 256, 0, stream, false, a, b, c, d.den, total);
+    d.launches++;
+    ntt_run(d, a, vec_stride, batch, true, true, d.scale_coset_inv.p, stream);           // coset iNTT
+}
+
+void ntt_bitrev(const Fr* in, Fr* out, int k, cudaStream_t stream) {
+    G16_LAUNCH(ntt_bitrev_kernel, div_up((size_t)1 << k, 256), 256, 0, stream, false, in, out, k);
+    G16_CHECK_LAUNCH();
+}
+void fr_be_to_mont(const uint8_t* d_in, uint32_t n, Fr* d_out, cudaStream_t stream) {
+    G16_LAUNCH(fr_be_to_mont_kernel, div_up(n, 64), 64, 0, stream, false, d_in, n, d_out);
+    G16_CHECK_LAUNCH();
+}
+void ntt_fill_pattern(Fr* out, size_t total, cudaStream_t stream) {
+    G16_LAUNCH(fill_pattern_kernel, div_up(total, 256), 256, 0, stream, false, out, total);
+    G16_CHECK_LAUNCH();
+}
+void ntt_count_mismatches(const Fr* a, const Fr* b, size_t total, uint32_t* d_count, cudaStream_t stream) {
+    G16_LAUNCH(count_mismatch_kernel, div_up(total, 256), 256, 0, stream, false, a, b, total, d_count);
+    G16_CHECK_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------------ integer-multiply peak
+#if !defined(G16_EMU)
+template <int WIDE>
+__global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, int iters) {
+    uint32_t a = threadIdx.x * 2654435761u + 1, b = blockIdx.x * 40503u + 7;
+    if (WIDE) {
+        uint64_t c0 = a, c1 = b, c2 = a ^ b, c3 = a + b, c4 = a * 3, c5 = b * 5, c6 = a * 7, c7 = b * 9;
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\t"
+                             "mad.wide.u32 %2, %8, %9, %2;\n\tmad.wide.u32 %3, %8, %9, %3;\n\t"
+                             "mad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\t"
+                             "mad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
+                             : "+l"(c0), "+l"(c1), "+l"(c2), "+l"(c3), "+l"(c4), "+l"(c5), "+l"(c6), "+l"(c7)
+                             : "r"(a), "r"(b));
+            }
+        }
+        uint64_t s = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+        if (s == 0x1234567ull) out[0] = (uint32_t)s;
+    } else {
+        uint32_t c0 = a, c1 = b, c2 = a ^ b, c3 = a + b, c4 = a * 3, c5 = b * 5, c6 = a * 7, c7 = b * 9;
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                asm volatile("mad.lo.u32 %0, %8, %9, %0;\n\tmad.lo.u32 %1, %8, %9, %1;\n\t"
+                             "mad.lo.u32 %2, %8, %9, %2;\n\tmad.lo.u32 %3, %8, %9, %3;\n\t"
+                             "mad.lo.u32 %4, %8, %9, %4;\n\tmad.lo.u32 %5, %8, %9, %5;\n\t"
+                             "mad.lo.u32 %6, %8, %9, %6;\n\tmad.lo.u32 %7, %8, %9, %7;"
+                             : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7)
+                             : "r"(a), "r"(b));
+            }
+        }
+        uint32_t s = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+        if (s == 0x1234567u) out[0] = s;
+    }
+}
+// two independent dependent-chains of Fp products per thread
+__global__ void __launch_bounds__(256) modmul_peak_kernel(Fp* out, int iters) {
+    Fp a = Fp::one(), b = Fp::r2(), c = Fp::one(), d = Fp::r2();
+    a.l[0] += threadIdx.x;
+    b.l[0] += blockIdx.x;
+    c.l[1] += threadIdx.x;
+    d.l[1] += blockIdx.x;
+    for (int i = 0; i < iters; i++) {
+        a = a * b;
+        c = c * d;
+        b = b * a;
+        d = d * c;
+    }
+    if (a.l[0] == 0x12345u && b.l[3] == 77u && c.l[1] == d.l[2]) out[0] = a;
+}
+#endif
+
+void imad_peak_measure(double* imad_per_s, double* imad_wide_per_s, double* modmul_per_s) {
+#if defined(G16_EMU)
+    throw std::runtime_error("imad peak needs a GPU");
+#else
+    DevBuf<uint32_t> out(64);
+    cudaEvent_t e0, e1;
+    G16_CUDA(cudaEventCreate(&e0));
+    G16_CUDA(cudaEventCreate(&e1));
+    const int blocks = 148 * 8, threads = 256, iters = 2000;
+    auto time_it = [&](auto launch) {
+        launch();   // warm-up
+        G16_CUDA(cudaDeviceSynchronize());
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {
+            G16_CUDA(cudaEventRecord(e0, 0));
+            launch();
+            G16_CUDA(cudaEventRecord(e1, 0));
+            G16_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (ms < best) best = ms;
+        }
+        return (double)best * 1e-3;
+    };
+    double ops = (double)blocks * threads * iters * 16.0 * 8.0;
+    double t0 = time_it([&] { imad_peak_kernel<0><<<blocks, threads>>>(out.p, iters); });
+    double t1 = time_it([&] { imad_peak_kernel<1><<<blocks, threads>>>(out.p, iters); });
+    const int mm_iters = 400;
+    double t2 = time_it([&] { modmul_peak_kernel<<<blocks, threads>>>((Fp*)out.p, mm_iters); });
+    G16_CHECK_LAUNCH();
+    *imad_per_s = ops / t0;
+    *imad_wide_per_s = ops / t1;
+    *modmul_per_s = (double)blocks * threads * mm_iters * 4.0 / t2;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+#endif
+}
+
+}  // namespace g16

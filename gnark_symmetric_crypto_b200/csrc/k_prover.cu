@@ -1,0 +1,114 @@
+// Cold translation unit (built with -DG16_COLD): key decompression, witness assignment, R1CS solver, proof assembly and
+// the stage-level field / group test kernels. The Montgomery product stays out of line here (see field.cuh FD_MUL).
+#include "prover_kernels.cuh"
+#include "msm_types.hpp"
+
+namespace g16 {
+
+__global__ void field_op_kernel(int field, int op, const uint64_t* __restrict__ a, const uint64_t* __restrict__ b,
+                                uint64_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (field == 0) {
+        Fp x = ((const Fp*)a)[i], y = b ? ((const Fp*)b)[i] : Fp::zero(), r;
+        switch (op) {
+            case 0: r = x + y; break; case 1: r = x - y; break; case 2: r = x * y; break; case 3: r = x.inv(); break;
+            case 4: r = x.sqr(); break; case 5: r = x.neg(); break; case 6: r = x.to_mont(); break; default: r = x.from_mont();
+        }
+        ((Fp*)out)[i] = r;
+    } else {
+        Fr x = ((const Fr*)a)[i], y = b ? ((const Fr*)b)[i] : Fr::zero(), r;
+        switch (op) {
+            case 0: r = x + y; break; case 1: r = x - y; break; case 2: r = x * y; break; case 3: r = x.inv(); break;
+            case 4: r = x.sqr(); break; case 5: r = x.neg(); break; case 6: r = x.to_mont(); break; default: r = x.from_mont();
+        }
+        ((Fr*)out)[i] = r;
+    }
+}
+// op 0: a + b via madd ; 1: k*a (k = 8 x u32 canonical limbs in b) ; 2: 2a ; 3: a + b via the general XYZZ addition
+template <class C>
+__global__ void group_op_kernel(int op, const typename C::A* __restrict__ a, const uint64_t* __restrict__ b,
+                                typename C::A* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    typedef typename C::X X;
+    X acc = X::from_affine(a[i]);
+    if (op == 0) {
+        acc.madd(((const typename C::A*)b)[i], false);
+    } else if (op == 1) {
+        uint32_t k[8];
+        for (int j = 0; j < 8; j++) k[j] = ((const uint32_t*)b)[8 * i + j];
+        acc = scalar_mul(acc, k, 256);
+    } else if (op == 2) {
+        acc = acc.dbl();
+    } else {
+        X o = X::from_affine(((const typename C::A*)b)[i]);
+        // make the second operand non-trivially projective: (x,y,1,1) -> (4x, 8y, 4, 8)
+        if (!o.is_inf()) {
+            typename C::F two = C::F::one().dbl(), four = two.dbl(), eight = four.dbl();
+            o.X = o.X * four; o.Y = o.Y * eight; o.ZZ = four; o.ZZZ = eight;
+        }
+        acc.add(o);
+    }
+    out[i] = acc.to_affine();
+}
+
+void launch_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, cudaStream_t st) {
+    G16_LAUNCH(field_op_kernel, div_up(n, 128), 128, 0, st, false, field, op, a, b, out, n);
+    G16_CHECK_LAUNCH();
+}
+void launch_group_op(int group, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, cudaStream_t st) {
+    if (group == 1) {
+        auto k = group_op_kernel<G1>;
+        G16_LAUNCH(k, div_up(n, 64), 64, 0, st, false, op, (const G1Affine*)a, b, (G1Affine*)out, n);
+    } else {
+        auto k = group_op_kernel<G2>;
+        G16_LAUNCH(k, div_up(n, 64), 64, 0, st, false, op, (const G2Affine*)a, b, (G2Affine*)out, n);
+    }
+    G16_CHECK_LAUNCH();
+}
+
+void launch_decompress_g1(const uint8_t* in, uint32_t n, G1Affine* out, uint32_t* err, cudaStream_t st) {
+    G16_LAUNCH(decompress_g1_kernel, div_up(n, 128), 128, 0, st, false, in, n, out, err);
+    G16_CHECK_LAUNCH();
+}
+void launch_decompress_g2(const uint8_t* in, uint32_t n, G2Affine* out, uint32_t* err, cudaStream_t st) {
+    G16_LAUNCH(decompress_g2_kernel, div_up(n, 64), 64, 0, st, false, in, n, out, err);
+    G16_CHECK_LAUNCH();
+}
+void launch_scalars_from_be(const uint8_t* in, uint32_t n, Fr* out, cudaStream_t st) {
+    G16_LAUNCH(scalars_from_be_kernel, div_up(n, 128), 128, 0, st, false, in, n, out);
+    G16_CHECK_LAUNCH();
+}
+void launch_chacha_witness(const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters, const uint8_t* inputs,
+                           uint32_t n, Fr* W, size_t w_stride, uint8_t* ct_out, cudaStream_t st) {
+    G16_LAUNCH(chacha_witness_kernel, div_up(n, 64), 64, 0, st, false, keys, nonces, counters, inputs, n, W, w_stride, ct_out);
+    G16_CHECK_LAUNCH();
+}
+void launch_witness_copy(const Fr* witness, uint32_t n_witness, uint32_t batch, Fr* W, size_t w_stride, cudaStream_t st) {
+    G16_LAUNCH(witness_copy_kernel, div_up((size_t)batch * (n_witness + 1), 256), 256, 0, st, false, witness, n_witness,
+               batch, W, w_stride);
+    G16_CHECK_LAUNCH();
+}
+void launch_solver(const SolverProgram& sp, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C, uint32_t* status,
+                   cudaStream_t st) {
+    G16_LAUNCH(solver_kernel, div_up(batch, 32), dim3(32, SOLVER_WARPS), 0, st, true, sp, batch, W, w_stride, A, B, C, status);
+    G16_CHECK_LAUNCH();
+}
+int launch_solver_init(const SolverProgram& sp, uint32_t n_instr, uint32_t n_coeffs, Fr* ucoef_inv, cudaStream_t st) {
+    DevBuf<uint32_t> flag(1);
+    G16_LAUNCH(solver_check_coeffs_kernel, 1, 1, 0, st, false, sp.coeffs, n_coeffs, flag.p);
+    G16_LAUNCH(solver_ucoef_kernel, div_up(n_instr, 128), 128, 0, st, false, sp, n_instr, ucoef_inv);
+    G16_CHECK_LAUNCH();
+    uint32_t hf = 0;
+    flag.download(&hf, 1, st);
+    G16_CUDA(cudaStreamSynchronize(st));
+    return (int)hf;
+}
+void launch_assemble(const AssemblyKeys& keys, uint32_t n, const G1XYZZ* mA, const G1XYZZ* mB1, const G1XYZZ* mK,
+                     const G1XYZZ* mZ, const G2XYZZ* mB2, const Fr* rs, uint8_t* out, size_t out_stride, cudaStream_t st) {
+    G16_LAUNCH(assemble_kernel, div_up(n, 64), 64, 0, st, false, keys, n, mA, mB1, mK, mZ, mB2, rs, out, out_stride);
+    G16_CHECK_LAUNCH();
+}
+
+}  // namespace g16

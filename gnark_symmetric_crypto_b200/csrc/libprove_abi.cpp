@@ -1,0 +1,256 @@
+// Outer ABI: the four cgo exports of the reference's c-shared library libraries/prover/libprove.go
+// (enforce_binding :17-18, InitAlgorithm :20-23, Free :25-28, Prove :30-47) and the JSON layer of
+// libraries/prover/impl/prove_impl.go:116-143 / provers.go:53-59,79-89 restated in C++ (no Go toolchain on this box),
+// on top of the g16_* inner seam. Same names, argument meaning and error behaviour:
+//   * InitAlgorithm returns 0 and prints the reason for unknown ids / unparsable keys (prove_impl.go:65-114)
+//   * Prove has no status channel: failures ("panics" in the reference) come back AS the payload, JSON-encoded
+//     (libprove.go:33-43); success is {"proof":{"proofJson":<base64>},"publicSignals":<base64>} (prove_impl.go:129-134)
+//   * the result buffer is malloc'd and must be released with Free (libprove.go:25-28,40,46)
+#include "../../include/g16b200.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace {
+
+const char* const ALG_NAMES[3] = {"chacha20", "aes-128-ctr", "aes-256-ctr"};   // prove_impl.go:15-25
+g16_ctx* g_provers[3] = {nullptr, nullptr, nullptr};
+std::mutex g_mu;
+
+struct Panic : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// ---- minimal JSON reader for InputParams (provers.go:53-59). []uint8 fields accept an array of numbers or a base64
+//      string, as Go's encoding/json does.
+struct Json {
+    const char* p;
+    const char* end;
+    void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++; }
+    bool eat(char c) { ws(); if (p < end && *p == c) { p++; return true; } return false; }
+    void expect(char c) { if (!eat(c)) throw Panic(std::string("invalid character in JSON input, expected '") + c + "'"); }
+    std::string str() {
+        ws();
+        if (p >= end || *p != '"') throw Panic("json: expected string");
+        p++;
+        std::string s;
+        while (p < end && *p != '"') {
+            if (*p == '\\' && p + 1 < end) {
+                p++;
+                switch (*p) {
+                    case 'n': s += '\n'; break; case 't': s += '\t'; break; case 'r': s += '\r'; break;
+                    case 'b': s += '\b'; break; case 'f': s += '\f'; break;
+                    case 'u': { if (p + 4 < end) { unsigned v = (unsigned)strtoul(std::string(p + 1, 4).c_str(), nullptr, 16); s += (char)v; p += 4; } break; }
+                    default: s += *p;
+                }
+                p++;
+            } else {
+                s += *p++;
+            }
+        }
+        if (p >= end) throw Panic("unexpected end of JSON input");
+        p++;
+        return s;
+    }
+    double num() {
+        ws();
+        char* e = nullptr;
+        double v = strtod(p, &e);
+        if (e == p) throw Panic("json: expected number");
+        p = e;
+        return v;
+    }
+    void skip_value() {
+        ws();
+        if (p >= end) throw Panic("unexpected end of JSON input");
+        if (*p == '"') { str(); return; }
+        if (*p == '{') { p++; if (eat('}')) return; do { str(); expect(':'); skip_value(); } while (eat(',')); expect('}'); return; }
+        if (*p == '[') { p++; if (eat(']')) return; do { skip_value(); } while (eat(',')); expect(']'); return; }
+        if (!strncmp(p, "true", 4)) { p += 4; return; }
+        if (!strncmp(p, "false", 5)) { p += 5; return; }
+        if (!strncmp(p, "null", 4)) { p += 4; return; }
+        num();
+    }
+};
+
+int b64val(char c) {
+    if (c >= 'A' && c <= 'Z') return c - 'A';
+    if (c >= 'a' && c <= 'z') return c - 'a' + 26;
+    if (c >= '0' && c <= '9') return c - '0' + 52;
+    if (c == '+') return 62;
+    if (c == '/') return 63;
+    return -1;
+}
+std::vector<uint8_t> b64decode(const std::string& s) {
+    std::vector<uint8_t> out;
+    uint32_t acc = 0;
+    int bits = 0;
+    for (char c : s) {
+        if (c == '=') break;
+        int v = b64val(c);
+        if (v < 0) throw Panic("illegal base64 data");
+        acc = (acc << 6) | (uint32_t)v;
+        bits += 6;
+        if (bits >= 8) { bits -= 8; out.push_back((uint8_t)(acc >> bits)); }
+    }
+    return out;
+}
+std::string b64encode(const uint8_t* d, size_t n) {
+    static const char T[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+    std::string s;
+    for (size_t i = 0; i < n; i += 3) {
+        uint32_t v = (uint32_t)d[i] << 16;
+        if (i + 1 < n) v |= (uint32_t)d[i + 1] << 8;
+        if (i + 2 < n) v |= d[i + 2];
+        s += T[(v >> 18) & 63];
+        s += T[(v >> 12) & 63];
+        s += i + 1 < n ? T[(v >> 6) & 63] : '=';
+        s += i + 2 < n ? T[v & 63] : '=';
+    }
+    return s;
+}
+std::vector<uint8_t> read_bytes(Json& j) {
+    j.ws();
+    if (j.p < j.end && *j.p == '"') return b64decode(j.str());
+    if (j.p + 4 <= j.end && !strncmp(j.p, "null", 4)) { j.p += 4; return {}; }
+    std::vector<uint8_t> out;
+    j.expect('[');
+    if (j.eat(']')) return out;
+    do {
+        double v = j.num();
+        if (v < 0 || v > 255 || v != (double)(int)v) throw Panic("json: cannot unmarshal number into Go value of type uint8");
+        out.push_back((uint8_t)v);
+    } while (j.eat(','));
+    j.expect(']');
+    return out;
+}
+
+struct InputParams {
+    std::string cipher;
+    std::vector<uint8_t> key, nonce, input;
+    uint32_t counter = 0;
+};
+InputParams parse_params(const uint8_t* data, size_t len) {
+    Json j{(const char*)data, (const char*)data + len};
+    InputParams ip;
+    j.expect('{');
+    if (!j.eat('}')) {
+        do {
+            std::string k = j.str();
+            j.expect(':');
+            if (k == "cipher") ip.cipher = j.str();
+            else if (k == "key") ip.key = read_bytes(j);
+            else if (k == "nonce") ip.nonce = read_bytes(j);
+            else if (k == "input") ip.input = read_bytes(j);
+            else if (k == "counter") {
+                j.ws();
+                if (j.p < j.end && (*j.p == '[' || *j.p == '"' || *j.p == '{'))
+                    throw Panic("json: cannot unmarshal into Go struct field InputParams.counter of type uint32");
+                double v = j.num();
+                if (v < 0 || v > 4294967295.0 || v != (double)(uint64_t)v) throw Panic("json: cannot unmarshal number into Go struct field InputParams.counter of type uint32");
+                ip.counter = (uint32_t)v;
+            } else j.skip_value();
+        } while (j.eat(','));
+        j.expect('}');
+    }
+    return ip;
+}
+
+std::string json_string(const std::string& s) {
+    std::string o = "\"";
+    for (char c : s) {
+        if (c == '"' || c == '\\') { o += '\\'; o += c; }
+        else if (c == '\n') o += "\\n";
+        else if ((unsigned char)c < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", c); o += b; }
+        else o += c;
+    }
+    return o + "\"";
+}
+
+std::string prove_impl(const uint8_t* params, size_t len) {
+    InputParams ip = parse_params(params, len);
+    int alg = -1;
+    for (int i = 0; i < 3; i++) if (ip.cipher == ALG_NAMES[i]) alg = i;
+    if (alg < 0) throw Panic("could not find prover for" + ip.cipher);   // prove_impl.go:140-142 (sic, no space)
+    g16_ctx* ctx;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        ctx = g_provers[alg];
+    }
+    if (!ctx) throw Panic("proving params are not initialized for cipher: " + ip.cipher);   // prove_impl.go:124-126
+    std::vector<uint8_t> proof(256), ct(64);
+    if (alg == 0) {
+        if (ip.key.size() != 32) throw Panic("key length must be 32: " + std::to_string(ip.key.size()));         // provers.go:81-83
+        if (ip.nonce.size() != 12) throw Panic("nonce length must be 12: " + std::to_string(ip.nonce.size()));   // :84-86
+        if (ip.input.size() != 64) throw Panic("plaintext length must be 64: " + std::to_string(ip.input.size()));   // :87-89
+        int rc = g16_prove_chacha_batch(ctx, 1, ip.key.data(), ip.nonce.data(), &ip.counter, ip.input.data(), nullptr,
+                                        proof.data(), ct.data());
+        if (rc) throw Panic(std::string("groth16 prove failed: ") + g16_last_error());
+        proof.resize(164);
+    } else {
+        if (ip.key.size() != 32 && ip.key.size() != 16) throw Panic("key length must be 16 or 32: " + std::to_string(ip.key.size()));   // provers.go:174-176
+        if (ip.nonce.size() != 12) throw Panic("nonce length must be 12: " + std::to_string(ip.nonce.size()));
+        if (ip.input.size() != 64) throw Panic("plaintext length must be 64: " + std::to_string(ip.input.size()));
+        throw Panic("AES-CTR proving (BSB22 commitment path) is not implemented in this build of libg16b200");
+    }
+    return "{\"proof\":{\"proofJson\":\"" + b64encode(proof.data(), proof.size()) + "\"},\"publicSignals\":\"" +
+           b64encode(ct.data(), ct.size()) + "\"}";
+}
+
+}  // namespace
+
+extern "C" {
+
+void enforce_binding(void) {}
+
+unsigned char InitAlgorithm(unsigned char algorithmID, GoSlice_g16 provingKey, GoSlice_g16 r1cs) {
+    if (algorithmID > 2) return 0;   // prove_impl.go:72,113
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_provers[algorithmID]) return 1;   // initDone, prove_impl.go:74-76
+    if (!provingKey.data || !r1cs.data || provingKey.len < 0 || r1cs.len < 0) {
+        printf("error reading proving key: empty input\n");
+        return 0;
+    }
+    int device = 0;
+    if (const char* d = getenv("G16_DEVICE")) device = atoi(d);
+    g16_ctx* ctx = nullptr;
+    int rc = g16_init((const uint8_t*)provingKey.data, (size_t)provingKey.len, (const uint8_t*)r1cs.data, (size_t)r1cs.len,
+                      device, &ctx);
+    if (rc) {
+        printf("error reading proving key: %s\n", g16_last_error());   // prove_impl.go:88-91,104-107
+        return 0;
+    }
+    g_provers[algorithmID] = ctx;
+    return 1;
+}
+
+void Free(void* pointer) { free(pointer); }
+
+Prove_return_g16 Prove(GoSlice_g16 params) {
+    std::string res;
+    try {
+        if (!params.data || params.len <= 0) throw Panic("unexpected end of JSON input");
+        res = prove_impl((const uint8_t*)params.data, (size_t)params.len);
+    } catch (const std::exception& e) {
+        printf("%s\n", e.what());          // libprove.go:35
+        res = json_string(e.what());       // libprove.go:36-41: json.Marshal(err) returned as the payload
+    }
+    Prove_return_g16 r;
+    r.r1 = (long long)res.size();
+    r.r0 = malloc(res.size() ? res.size() : 1);   // C.CBytes, libprove.go:40,46
+    if (r.r0) memcpy(r.r0, res.data(), res.size());
+    else r.r1 = 0;
+    return r;
+}
+
+// test hook: drop the cached provers (the reference has no such call; its map lives for the process lifetime)
+void g16_libprove_reset(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& p : g_provers) { if (p) g16_free(p); p = nullptr; }
+}
+
+}  // extern "C"

@@ -1,0 +1,409 @@
+// Pippenger multi-scalar multiplication for BN254 G1 / G2 on sm_100a.
+//
+// Replaces: gnark-crypto v0.14.0 ecc/bn254/multiexp.go:106-325 ((*G1Jac).MultiExp, _innerMsmG1,
+// partitionScalars :670-792, msmReduceChunkG1Affine), multiexp_affine.go:35-176, :363-500 (G2) — the five MSMs of
+// groth16 Prove (gnark backend/groth16/bn254/prove.go:197-295) reached from libraries/prover/impl/provers.go:148,216.
+//
+// Pipeline (all rows of a batch share the bases; row = one independent scalar vector, i.e. one proof):
+//   1 digits+count   signed c-bit windows of sign-normalised scalars (s > r/2 -> r-s with the point negated, so the
+//                    {0,1,-1} wires of the ChaCha circuit cost one addition each); histogram of bucket ids
+//   2 scan           exclusive prefix sum of the histogram
+//   3 scatter        counting sort of (bucket id, point ref) pairs = single-pass radix sort on the full key
+//   4 accumulate     every thread owns L consecutive SORTED entries: perfectly balanced, no atomics; complete buckets
+//                    are written directly, the two open runs at the chunk edges go to head/tail partials
+//   5 merge          partials of a bucket that spans several chunks are summed
+//   6 reduce         sum_k k*B_k per (row, window) as a 32-ary tree of running sums
+//   7 combine        Horner over windows (not needed with precomputed 2^(cw) P tables: one bucket set per row)
+// Points are read with 128-bit loads (64 B / 128 B affine points are 16-byte aligned).
+#pragma once
+#include "msm_types.hpp"
+
+namespace g16 {
+
+// ------------------------------------------------------------------------------------------------ scalar recoding
+// canonical, sign-normalised scalar -> signed digits. Returns the digit of window w in [-2^(c-1), 2^(c-1)].
+struct Recoded {
+    uint32_t s[9];
+    uint32_t neg;
+};
+
+FD Recoded recode_load(const Fr* scalars, size_t idx, int is_mont) {
+    Fr v = scalars[idx];
+    if (is_mont) v = v.from_mont();
+    // s > (r-1)/2  ->  s = r - s, negate the point
+    uint32_t h[8], t[8];
+    for (int i = 0; i < 8; i++) h[i] = (FrParams::mod(i) >> 1) | (i < 7 ? (FrParams::mod(i + 1) << 31) : 0u);
+    uint32_t big = sub8(t, h, v.l);   // borrow <=> v > h
+    Recoded r;
+    r.neg = big ? 1u : 0u;
+    if (big) v = Fr::modulus_minus(v);
+    for (int i = 0; i < 8; i++) r.s[i] = v.l[i];
+    r.s[8] = 0;
+    return r;
+}
+
+// iterate the windows in order; carry must start at 0
+FD int recode_digit(const Recoded& r, int w, int c, int& carry) {
+    int bit = w * c;
+    int limb = bit >> 5, sh = bit & 31;
+    uint64_t v = r.s[limb];
+    if (limb < 8) v |= (uint64_t)r.s[limb + 1] << 32;
+    int d = (int)((v >> sh) & ((1u << c) - 1u)) + carry;
+    if (d > (1 << (c - 1))) { d -= (1 << c); carry = 1; } else carry = 0;
+    return d;
+}
+
+// One thread per (row, point). pass 0: histogram ; pass 1: scatter into the sorted entry array.
+// scalars: row-major, row r at scalars + r*row_stride ; map (optional): scalar of point i is scalars[map[i]].
+static __global__ void msm_digits_kernel(MsmShape sh, const Fr* __restrict__ scalars, size_t row_stride,
+                                  const uint32_t* __restrict__ map, int is_mont, int pass, uint32_t* __restrict__ counts,
+                                  uint2* __restrict__ entries) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)sh.n * sh.rows) return;
+    uint32_t row = (uint32_t)(gid / sh.n), i = (uint32_t)(gid % sh.n);
+    size_t sidx = (size_t)row * row_stride + (map ? map[i] : i);
+    Fr raw = scalars[sidx];
+    if (raw.is_zero()) return;
+    Recoded r = recode_load(scalars, sidx, is_mont);
+    int carry = 0;
+    uint32_t base = row * sh.buckets_per_row();
+    for (int w = 0; w < sh.nwin; w++) {
+        int d = recode_digit(r, w, sh.c, carry);
+        if (d == 0) continue;
+        uint32_t neg = r.neg ^ (d < 0 ? 1u : 0u);
+        uint32_t mag = (uint32_t)(d < 0 ? -d : d);
+        uint32_t b = base + (sh.precomp ? 0u : (uint32_t)w * sh.nbk) + (mag - 1u);
+        if (pass == 0) {
+            atomicAdd(&counts[b], 1u);
+        } else {
+            uint32_t pos = atomicAdd(&counts[b], 1u);   // counts holds the running write cursor (= exclusive scan)
+            uint32_t ref = sh.precomp ? (uint32_t)w * sh.n + i : i;
+            entries[pos] = make_uint2(b, (ref << 1) | neg);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ exclusive scan (u32)
+// three-kernel scan: tile sums -> scan of tile sums (single block) -> rescan tiles. Tile = 256 threads x 8 items.
+#define SCAN_T 256
+#define SCAN_I 8
+static __global__ void scan_tile_sums(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ tile_sums) {
+    __shared__ uint32_t sm[SCAN_T];
+    size_t base = (size_t)blockIdx.x * SCAN_T * SCAN_I;
+    uint32_t s = 0;
+    for (int k = 0; k < SCAN_I; k++) {
+        size_t idx = base + (size_t)k * SCAN_T + threadIdx.x;
+        if (idx < n) s += in[idx];
+    }
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = SCAN_T / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sm[threadIdx.x] += sm[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = sm[0];
+}
+// single block: in-place exclusive scan of `m` tile sums; writes the grand total to *total
+static __global__ void scan_of_sums(uint32_t* __restrict__ tile_sums, size_t m, uint32_t* __restrict__ total) {
+    __shared__ uint32_t sm[SCAN_T];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (size_t base = 0; base < m; base += SCAN_T) {
+        size_t idx = base + threadIdx.x;
+        uint32_t v = idx < m ? tile_sums[idx] : 0;
+        sm[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < SCAN_T; off <<= 1) {   // Hillis-Steele inclusive
+            uint32_t add = (int)threadIdx.x >= off ? sm[threadIdx.x - off] : 0;
+            __syncthreads();
+            sm[threadIdx.x] += add;
+            __syncthreads();
+        }
+        uint32_t incl = sm[threadIdx.x];
+        uint32_t c0 = carry;
+        if (idx < m) tile_sums[idx] = c0 + incl - v;
+        __syncthreads();
+        if (threadIdx.x == SCAN_T - 1) carry = c0 + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+// each tile: exclusive scan of its SCAN_T*SCAN_I items (thread-contiguous layout) + tile offset ; out may alias in
+static __global__ void scan_tiles(const uint32_t* __restrict__ in, size_t n, const uint32_t* __restrict__ tile_offs,
+                           uint32_t* __restrict__ out) {
+    __shared__ uint32_t sm[SCAN_T];
+    size_t base = (size_t)blockIdx.x * SCAN_T * SCAN_I + (size_t)threadIdx.x * SCAN_I;
+    uint32_t v[SCAN_I];
+    uint32_t s = 0;
+    for (int k = 0; k < SCAN_I; k++) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 1; off < SCAN_T; off <<= 1) {
+        uint32_t add = (int)threadIdx.x >= off ? sm[threadIdx.x - off] : 0;
+        __syncthreads();
+        sm[threadIdx.x] += add;
+        __syncthreads();
+    }
+    uint32_t run = tile_offs[blockIdx.x] + sm[threadIdx.x] - s;
+    for (int k = 0; k < SCAN_I; k++) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+}
+// NOTE scan_tile_sums reads items tile-strided while scan_tiles reads thread-contiguous: both cover the same tile
+// [blockIdx*2048, +2048), so the tile sums agree.
+
+// ------------------------------------------------------------------------------------------------ bucket accumulation
+template <class C>
+FD typename C::A load_point(const typename C::A* __restrict__ bases, uint32_t ref) {
+#if G16_ASM
+    // 128-bit loads through the read-only path
+    typename C::A p;
+    const uint4* src = reinterpret_cast<const uint4*>(bases + ref);
+    uint4* dst = reinterpret_cast<uint4*>(&p);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(typename C::A) / 16); k++) dst[k] = __ldg(src + k);
+    return p;
+#else
+    return bases[ref];
+#endif
+}
+
+// Thread t owns sorted entries [t*L, (t+1)*L). *total_entries is read from device memory (no host sync).
+template <class C>
+__global__ void __launch_bounds__(128)
+msm_accumulate_kernel(const typename C::A* __restrict__ bases, const uint2* __restrict__ entries,
+                      const uint32_t* __restrict__ total_entries, int L, typename C::X* __restrict__ bucket_sums,
+                      typename C::X* __restrict__ head, uint32_t* __restrict__ head_key,
+                      typename C::X* __restrict__ tail, uint32_t* __restrict__ tail_key) {
+    typedef typename C::X X;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t M = *total_entries;
+    size_t start = t * (size_t)L;
+    if (start >= M) return;
+    size_t end = start + L < M ? start + L : M;
+    uint32_t cur = entries[start].x;
+    X acc = X::inf();
+    bool first = true;
+    for (size_t j = start; j < end; j++) {
+        uint2 e = entries[j];
+        if (e.x != cur) {
+            if (first) { head[t] = acc; head_key[t] = cur; first = false; }
+            else bucket_sums[cur] = acc;
+            acc = X::inf();
+            cur = e.x;
+        }
+        typename C::A p = load_point<C>(bases, e.y >> 1);
+        acc.madd(p, (e.y & 1u) != 0);
+    }
+    if (first) {
+        head[t] = acc; head_key[t] = cur;
+        tail_key[t] = MSM_INVALID;
+    } else {
+        tail[t] = acc; tail_key[t] = cur;
+    }
+}
+
+// boundary sequence: head[0], tail[0], head[1], tail[1], ... (non-decreasing keys, tails may be INVALID).
+// The first entry of every key run sums the run and writes the bucket.
+template <class C>
+__global__ void __launch_bounds__(128)
+msm_merge_kernel(const uint32_t* __restrict__ total_entries, int L, const typename C::X* __restrict__ head,
+                 const uint32_t* __restrict__ head_key, const typename C::X* __restrict__ tail,
+                 const uint32_t* __restrict__ tail_key, typename C::X* __restrict__ bucket_sums) {
+    typedef typename C::X X;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t M = *total_entries;
+    size_t T = (M + L - 1) / L;
+    if (i >= 2 * T) return;
+    uint32_t key = (i & 1) ? tail_key[i >> 1] : head_key[i >> 1];
+    if (key == MSM_INVALID) return;
+    if (i > 0) {
+        size_t pi = i - 1;
+        uint32_t pk = (pi & 1) ? tail_key[pi >> 1] : head_key[pi >> 1];
+        if (pk == MSM_INVALID) { pi--; pk = head_key[pi >> 1]; }   // an INVALID tail always follows a valid head
+        if (pk == key) return;                                     // not the leader of this run
+    }
+    X acc = (i & 1) ? tail[i >> 1] : head[i >> 1];
+    for (size_t j = i + 1; j < 2 * T; j++) {
+        uint32_t k = (j & 1) ? tail_key[j >> 1] : head_key[j >> 1];
+        if (k == MSM_INVALID) continue;
+        if (k != key) break;
+        acc.add((j & 1) ? tail[j >> 1] : head[j >> 1]);
+    }
+    bucket_sums[key] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ bucket reduction tree
+// Node = (R, V): R = sum of the B_k below it, V = sum (k - base)*B_k. Leaves are the buckets (weight 1..g inside a
+// level-1 node), upper levels use 0-based child weights:  V = sum_i V_i + span_child * sum_i i*R_i.
+// Segment = one (row, window) bucket set of `n_in` items; thread = one output node.
+template <class C>
+__global__ void __launch_bounds__(128)
+msm_tree_kernel(const typename C::X* __restrict__ in_R, const typename C::X* __restrict__ in_V, uint32_t n_in,
+                uint32_t n_out, uint32_t segs, int level, int log_span_child, typename C::X* __restrict__ out_R,
+                typename C::X* __restrict__ out_V) {
+    typedef typename C::X X;
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)segs * n_out) return;
+    uint32_t seg = (uint32_t)(gid / n_out), node = (uint32_t)(gid % n_out);
+    const X* R = in_R + (size_t)seg * n_in;
+    uint32_t lo = node * MSM_TREE_G;
+    uint32_t hi = lo + MSM_TREE_G < n_in ? lo + MSM_TREE_G : n_in;   // children [lo, hi)
+    X run = X::inf(), tot = X::inf(), vsum = X::inf();
+    if (level == 1) {
+        // weights 1..g: tot accumulates run after every add
+        for (uint32_t k = hi; k > lo; k--) {
+            run.add(R[k - 1]);
+            tot.add(run);
+        }
+    } else {
+        const X* V = in_V + (size_t)seg * n_in;
+        // weights 0..g-1: child lo (weight 0) joins run after the last tot update
+        for (uint32_t k = hi; k > lo + 1; k--) {
+            run.add(R[k - 1]);
+            tot.add(run);
+        }
+        run.add(R[lo]);
+        for (uint32_t k = lo; k < hi; k++) vsum.add(V[k]);
+        for (int d = 0; d < log_span_child; d++) tot = tot.dbl();
+        tot.add(vsum);
+    }
+    out_R[gid] = run;
+    out_V[gid] = tot;
+}
+
+// Horner over windows: out[row] = sum_w 2^(c*w) * S[row][w]   (S = the V of the tree roots)
+template <class C>
+__global__ void msm_combine_kernel(const typename C::X* __restrict__ S, uint32_t rows, int nwin, int c,
+                                   typename C::X* __restrict__ out) {
+    typedef typename C::X X;
+    uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    X acc = X::inf();
+    for (int w = nwin - 1; w >= 0; w--) {
+        for (int k = 0; k < c; k++) acc = acc.dbl();
+        acc.add(S[(size_t)row * nwin + w]);
+    }
+    out[row] = acc;
+}
+
+template <class C>
+__global__ void xyzz_to_affine_kernel(const typename C::X* __restrict__ in, uint32_t n, typename C::A* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = in[i].to_affine();
+}
+
+// table[w*n + i] = 2^(c*w) * P_i  (affine). One thread per point.
+template <class C>
+__global__ void msm_precompute_kernel(const typename C::A* __restrict__ pts, uint32_t n, int nwin, int c,
+                                      typename C::A* __restrict__ table) {
+    typedef typename C::X X;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    typename C::A p = pts[i];
+    table[i] = p;
+    X acc = X::from_affine(p);
+    for (int w = 1; w < nwin; w++) {
+        for (int k = 0; k < c; k++) acc = acc.dbl();
+        table[(size_t)w * n + i] = acc.to_affine();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host driver
+// Runs the whole pipeline on `stream`; result XYZZ per row is left in ws.result (device). No host synchronisation.
+template <class C>
+void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases, const Fr* scalars, size_t row_stride,
+             const uint32_t* map, int is_mont, cudaStream_t stream, StageTimer* tm, int chunk_len) {
+    typedef typename C::X X;
+    const size_t nbuckets = (size_t)sh.rows * sh.buckets_per_row();
+    const size_t max_entries = (size_t)sh.rows * sh.n * sh.nwin;
+    if (nbuckets >= 0xFFFFFFF0ull || max_entries >= 0xFFFFFFF0ull || (size_t)sh.n * sh.nwin >= (1ull << 31))
+        throw std::runtime_error("msm: problem too large for 32-bit keys");
+    int L = chunk_len;
+    if (L <= 0) {
+        // enough chunks to fill the machine a few times over, but not shorter than 8 / longer than 64 entries
+        size_t want_threads = 148 * 512 * 4;
+        size_t l = max_entries / want_threads;
+        L = l < 8 ? 8 : (l > 64 ? 64 : (int)l);
+    }
+    const size_t max_chunks = (max_entries + L - 1) / L;
+    const size_t ntiles = (nbuckets + SCAN_T * SCAN_I - 1) / (SCAN_T * SCAN_I);
+
+    ws.counts.ensure(nbuckets);
+    ws.tile_sums.ensure(ntiles);
+    ws.total.ensure(1);
+    ws.entries.ensure(max_entries);
+    ws.buckets.ensure(nbuckets);
+    ws.head.ensure(max_chunks);
+    ws.tail.ensure(max_chunks);
+    ws.head_key.ensure(max_chunks);
+    ws.tail_key.ensure(max_chunks);
+    ws.result.ensure(sh.rows);
+
+    if (tm) tm->mark(ST_MSM_SORT, stream);
+    G16_CUDA(cudaMemsetAsync(ws.counts.p, 0, nbuckets * sizeof(uint32_t), stream));
+    G16_CUDA(cudaMemsetAsync(ws.buckets.p, 0, nbuckets * sizeof(X), stream));
+    const size_t nthreads = (size_t)sh.n * sh.rows;
+    G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, map, is_mont, 0,
+               ws.counts.p, ws.entries.p);
+    G16_LAUNCH(scan_tile_sums, (unsigned)ntiles, SCAN_T, 0, stream, true, ws.counts.p, nbuckets, ws.tile_sums.p);
+    G16_LAUNCH(scan_of_sums, 1, SCAN_T, 0, stream, true, ws.tile_sums.p, ntiles, ws.total.p);
+    G16_LAUNCH(scan_tiles, (unsigned)ntiles, SCAN_T, 0, stream, true, ws.counts.p, nbuckets, ws.tile_sums.p, ws.counts.p);
+    G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, map, is_mont, 1,
+               ws.counts.p, ws.entries.p);
+    G16_CHECK_LAUNCH();
+    if (tm) tm->mark(ST_MSM_ACC, stream);
+    {
+        auto k = msm_accumulate_kernel<C>;
+        G16_LAUNCH(k, div_up(max_chunks, 128), 128, 0, stream, false, bases, ws.entries.p, ws.total.p, L, ws.buckets.p,
+                   ws.head.p, ws.head_key.p, ws.tail.p, ws.tail_key.p);
+    }
+    if (tm) tm->mark(ST_MSM_REDUCE, stream);
+    {
+        auto k = msm_merge_kernel<C>;
+        G16_LAUNCH(k, div_up(2 * max_chunks, 128), 128, 0, stream, false, ws.total.p, L, ws.head.p, ws.head_key.p,
+                   ws.tail.p, ws.tail_key.p, ws.buckets.p);
+    }
+    G16_CHECK_LAUNCH();
+    ws.launches += 7;
+    // reduction tree
+    const uint32_t segs = sh.rows * sh.segs_per_row();
+    uint32_t n_in = (uint32_t)sh.nbk;
+    const X* inR = ws.buckets.p;
+    const X* inV = nullptr;
+    int level = 1, log_span = 0, pp = 0;
+    while (true) {
+        uint32_t n_out = (n_in + MSM_TREE_G - 1) / MSM_TREE_G;
+        ws.lvlR[pp].ensure((size_t)segs * n_out);
+        ws.lvlV[pp].ensure((size_t)segs * n_out);
+        auto k = msm_tree_kernel<C>;
+        G16_LAUNCH(k, div_up((size_t)segs * n_out, 128), 128, 0, stream, false, inR, inV, n_in, n_out, segs, level,
+                   log_span, ws.lvlR[pp].p, ws.lvlV[pp].p);
+        ws.launches++;
+        inR = ws.lvlR[pp].p;
+        inV = ws.lvlV[pp].p;
+        n_in = n_out;
+        log_span += 5;   // log2(MSM_TREE_G)
+        level++;
+        pp ^= 1;
+        if (n_out == 1) break;
+    }
+    // inV now holds one root V per segment
+    if (sh.precomp) {
+        G16_CUDA(cudaMemcpyAsync(ws.result.p, inV, (size_t)sh.rows * sizeof(X), cudaMemcpyDeviceToDevice, stream));
+    } else {
+        auto k = msm_combine_kernel<C>;
+        G16_LAUNCH(k, div_up(sh.rows, 64), 64, 0, stream, false, inV, sh.rows, sh.nwin, sh.c, ws.result.p);
+        ws.launches++;
+    }
+    G16_CHECK_LAUNCH();
+    if (tm) tm->mark(-1, stream);
+}
+
+}  // namespace g16

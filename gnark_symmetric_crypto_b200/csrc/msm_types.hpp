@@ -1,0 +1,74 @@
+// Host-visible types of the MSM pipeline (see msm.cuh for the kernels) and the per-group entry points, each compiled in
+// its own translation unit: k_msm_g1.cu (hot: Montgomery product inlined) and k_msm_g2.cu (cold).
+#pragma once
+#include "common.cuh"
+
+namespace g16 {
+
+struct G1 {
+    typedef Fp F;
+    typedef Affine<Fp> A;
+    typedef XYZZ<Fp> X;
+};
+struct G2 {
+    typedef Fp2 F;
+    typedef Affine<Fp2> A;
+    typedef XYZZ<Fp2> X;
+};
+
+struct MsmShape {
+    int c;          // window bits
+    int nwin;       // ceil(254 / c)
+    int nbk;        // buckets per window = 2^(c-1)
+    int precomp;    // bases = nwin tables, table w holds 2^(c*w) P_i ; all windows share one bucket set
+    uint32_t n;     // points per row
+    uint32_t rows;
+    FD uint32_t buckets_per_row() const { return precomp ? (uint32_t)nbk : (uint32_t)nwin * nbk; }
+    FD uint32_t segs_per_row() const { return precomp ? 1u : (uint32_t)nwin; }
+};
+
+static const uint32_t MSM_INVALID = 0xFFFFFFFFu;
+static const int MSM_TREE_G = 32;   // arity of the bucket-reduction tree
+
+template <class C>
+struct MsmWorkspace {
+    typedef typename C::X X;
+    DevBuf<uint32_t> counts, tile_sums, total, head_key, tail_key;
+    DevBuf<uint2> entries;
+    DevBuf<X> buckets, head, tail, lvlR[2], lvlV[2], result;
+    size_t launches = 0;
+};
+
+static inline int msm_pick_window(size_t n) {
+    // argmin over c of ceil(254/c) * (n + 2^c)  (SURVEY §8d adds_alg), clamped to what the key layout supports
+    int best = 4;
+    double bc = 1e300;
+    for (int c = 4; c <= 22; c++) {
+        double cost = (double)((254 + c - 1) / c) * ((double)n + (double)(1u << c));
+        if (cost < bc) { bc = cost; best = c; }
+    }
+    return best;
+}
+static inline MsmShape msm_make_shape(uint32_t n, uint32_t rows, int c, int precomp) {
+    MsmShape s;
+    s.c = c;
+    s.nwin = (254 + c - 1) / c;
+    s.nbk = 1 << (c - 1);
+    s.precomp = precomp;
+    s.n = n;
+    s.rows = rows;
+    return s;
+}
+
+
+void msm_run_g1(MsmWorkspace<G1>& ws, const MsmShape& sh, const G1Affine* bases, const Fr* scalars, size_t row_stride,
+                const uint32_t* map, int is_mont, cudaStream_t stream, StageTimer* tm = nullptr, int chunk_len = 0);
+void msm_run_g2(MsmWorkspace<G2>& ws, const MsmShape& sh, const G2Affine* bases, const Fr* scalars, size_t row_stride,
+                const uint32_t* map, int is_mont, cudaStream_t stream, StageTimer* tm = nullptr, int chunk_len = 0);
+// table[w*n + i] = 2^(c*w) * P_i
+void msm_precompute_g1(const G1Affine* pts, uint32_t n, int nwin, int c, G1Affine* table, cudaStream_t stream);
+void msm_precompute_g2(const G2Affine* pts, uint32_t n, int nwin, int c, G2Affine* table, cudaStream_t stream);
+void xyzz_to_affine_g1(const G1XYZZ* in, uint32_t n, G1Affine* out, cudaStream_t stream);
+void xyzz_to_affine_g2(const G2XYZZ* in, uint32_t n, G2Affine* out, cudaStream_t stream);
+
+}  // namespace g16

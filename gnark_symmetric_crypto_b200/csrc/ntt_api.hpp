@@ -1,0 +1,52 @@
+// Host-visible types and entry points of the Fr NTT / compute_h stage (kernels: ntt.cuh, compiled in k_ntt.cu).
+#pragma once
+#include "common.cuh"
+
+namespace g16 {
+
+static const int NTT_MAX_TILE_LG = 11;   // 2048 elements * 32 B = 64 KiB shared memory
+static const int NTT_THREADS = 256;
+
+struct NttPass {
+    int k;         // log2 n
+    int b_lo;      // lowest butterfly bit of this pass
+    int m;         // number of butterfly bits [b_lo, b_lo+m)
+    int q;         // number of contiguous low bits carried along (strided passes); 0 when b_lo == 0
+    int lg_tile;   // log2 of the tile element count
+    int dif;       // 1: process bits high -> low (DIF) ; 0: low -> high (DIT)
+};
+
+struct NttDomain {
+    int k = 0;
+    uint32_t n = 0;
+    DevBuf<Fr> tw_fwd, tw_inv;          // w^i, w^-i  (i < n/2)
+    DevBuf<Fr> scale_ninv;              // 1/n
+    DevBuf<Fr> scale_coset_fwd;         // g^brev(j) / n    (iNTT output -> coset coefficients)
+    DevBuf<Fr> scale_coset_inv;         // g^-brev(j) / n   (coset iNTT output -> coefficients)
+    DevBuf<Fr> scale_coset_only;        // g^brev(j)
+    Fr den;                             // 1/(g^n - 1), Montgomery
+    std::vector<NttPass> dif_passes, dit_passes;
+    size_t launches = 0;
+};
+
+// w, g: Montgomery limbs of the n-th root of unity and of the coset generator (read from the pk header)
+void ntt_domain_init(NttDomain& d, int k, const Fr& w, const Fr& g, cudaStream_t stream);
+// domain for a standalone transform of size 2^k: w = root28^(2^(28-k)), g = 5 (derived on the device)
+void ntt_standalone_domain(NttDomain& d, int k, cudaStream_t stream);
+// DIF: natural -> bit-reversed ; DIT: bit-reversed -> natural. `scale` (optional, n entries) is indexed by the position
+// on the bit-reversed side and applied there. No other normalisation.
+void ntt_run(NttDomain& d, Fr* data, size_t vec_stride, uint32_t batch, bool dif, bool inverse_root, const Fr* scale,
+             cudaStream_t stream);
+// a, b, c: `batch` contiguous vectors of n Fr each (vec_stride == n), zero-padded evaluations in natural order. On
+// return `a` holds the coefficients of H in gnark's array order (bit-reversed); b and c are clobbered.
+void compute_h_run(NttDomain& d, Fr* a, Fr* b, Fr* c, size_t vec_stride, uint32_t batch, cudaStream_t stream);
+void ntt_bitrev(const Fr* in, Fr* out, int k, cudaStream_t stream);
+// big-endian canonical 32-byte scalars -> Montgomery Fr (reduced mod r)
+void fr_be_to_mont(const uint8_t* d_in, uint32_t n, Fr* d_out, cudaStream_t stream);
+// test / bench helpers
+void ntt_fill_pattern(Fr* out, size_t total, cudaStream_t stream);
+void ntt_count_mismatches(const Fr* a, const Fr* b, size_t total, uint32_t* d_count, cudaStream_t stream);
+// integer-multiply microbenchmarks (ops per second)
+void imad_peak_measure(double* imad_per_s, double* imad_wide_per_s, double* modmul_per_s);
+
+}  // namespace g16

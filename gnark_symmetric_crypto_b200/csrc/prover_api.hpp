@@ -1,0 +1,59 @@
+// Host-visible types and launch wrappers of the non-MSM / non-NTT prover kernels (prover_kernels.cuh, compiled in the
+// cold translation unit k_prover.cu).
+#pragma once
+#include "common.cuh"
+
+namespace g16 {
+
+static const uint32_t SOLVE_WIRE_NONE = 0xFFFFFFFFu;
+static const uint32_t WIRE_CONST = 0xFFFFFFFFu;
+static const uint32_t HINT_NBITS = 4115454955u, HINT_COUNT = 2138922168u, HINT_RANDOMIZE = 1774611027u,
+                      HINT_BSB22 = 4156202267u;
+static const int SOLVER_WARPS = 16;
+
+struct InsMeta {
+    uint32_t cd_start;     // index into calldata
+    uint32_t kind;         // InstrKind | (solve_side << 8)
+    uint32_t solve_wire;   // wire this R1C defines, or SOLVE_WIRE_NONE (pure check)
+    uint32_t cons_off;
+    uint32_t wire_off;
+    uint32_t lookup_tab;   // lookup instructions: index of the 256-entry table
+};
+
+struct SolverProgram {
+    const uint32_t* calldata;
+    const InsMeta* meta;
+    const uint32_t* level_instr;   // instruction ids grouped by level
+    const uint32_t* level_off;     // nlevels + 1
+    const Fr* coeffs;              // Montgomery
+    const Fr* ucoef_inv;           // per instruction: 1 / (sum of the coefficients of the solved wire)
+    const Fr* lookup_tabs;         // [ntab][256]
+    uint32_t nlevels;
+    uint32_t n_wires;
+    uint32_t n_dom;                // stride of the A/B/C vectors (domain size)
+    int fast_coeffs;               // coefficient ids 1,2,3,4 are +1,+2,-1,-2 (verified on the device at init)
+};
+
+struct AssemblyKeys {
+    G1Affine alpha, beta, delta;
+    G2Affine beta2, delta2;
+};
+
+// all pointers are device pointers
+void launch_decompress_g1(const uint8_t* in, uint32_t n, G1Affine* out, uint32_t* err, cudaStream_t st);
+void launch_decompress_g2(const uint8_t* in, uint32_t n, G2Affine* out, uint32_t* err, cudaStream_t st);
+void launch_scalars_from_be(const uint8_t* in, uint32_t n, Fr* out, cudaStream_t st);
+void launch_chacha_witness(const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters, const uint8_t* inputs,
+                           uint32_t n, Fr* W, size_t w_stride, uint8_t* ct_out, cudaStream_t st);
+void launch_witness_copy(const Fr* witness, uint32_t n_witness, uint32_t batch, Fr* W, size_t w_stride, cudaStream_t st);
+void launch_solver(const SolverProgram& sp, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C, uint32_t* status,
+                   cudaStream_t st);
+// fills ucoef_inv (n_instr entries) and returns whether coefficient ids 0..4 are 0,1,2,-1,-2 (synchronises the stream)
+int launch_solver_init(const SolverProgram& sp, uint32_t n_instr, uint32_t n_coeffs, Fr* ucoef_inv, cudaStream_t st);
+void launch_assemble(const AssemblyKeys& keys, uint32_t n, const G1XYZZ* mA, const G1XYZZ* mB1, const G1XYZZ* mK,
+                     const G1XYZZ* mZ, const G2XYZZ* mB2, const Fr* rs, uint8_t* out, size_t out_stride, cudaStream_t st);
+// stage-level test entry points
+void launch_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, cudaStream_t st);
+void launch_group_op(int group, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, cudaStream_t st);
+
+}  // namespace g16

@@ -1,0 +1,140 @@
+/* g16b200 — C-ABI of the B200-native Groth16/BN254 prover backend (libg16b200.so).
+ *
+ * Drop-in boundary for the prove path of reclaimprotocol/gnark-symmetric-crypto. Two layers are exported:
+ *
+ *  (1) the OUTER ABI of the reference's own c-shared library, byte-compatible with what cgo generates from
+ *      libraries/prover/libprove.go:  InitAlgorithm (:20-23), Prove (:30-47), Free (:25-28), enforce_binding (:17-18).
+ *      A C / FFI caller that loads libprove.so today can load libg16b200.so instead.
+ *  (2) the INNER seam that a Go shim under gnark's groth16.Prove binds with cgo:
+ *      g16_init / g16_prove_witness / g16_prove_chacha_batch ..., replacing
+ *      groth16.Prove(r1cs, pk, witness)                     libraries/prover/impl/provers.go:148,216
+ *      ProvingKey.ReadFrom / NewCS(...).ReadFrom            libraries/prover/impl/prove_impl.go:86-91,102-107
+ *      Proof.WriteTo                                        libraries/prover/impl/provers.go:152-157
+ *
+ * Conventions: every function returns an int status (0 = G16_OK) unless stated; nothing aborts or throws across the
+ * ABI; the message of the last failure on the calling thread is available from g16_last_error(). Outputs are
+ * caller-allocated unless stated. Field elements are "gnark in-memory" form: 4 x uint64 little-endian limbs in
+ * Montgomery representation (R = 2^256) — exactly fr.Element / fp.Element, so a Go caller passes unsafe.Pointer(&v[0]).
+ * Affine points are x|y (G1: 8 x uint64, G2: 16 x uint64 as X.A0,X.A1,Y.A0,Y.A1) = gnark's G1Affine / G2Affine;
+ * (0,0) is the point at infinity. Serialized proofs are gnark's Proof.WriteTo bytes.
+ * There is NO CPU fallback: every compute entry point needs a CUDA device and fails with G16_ERR_CUDA otherwise.
+ */
+#ifndef G16B200_H
+#define G16B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G16_OK 0
+#define G16_ERR_ARG 1        /* bad argument (NULL, size mismatch, unknown id) */
+#define G16_ERR_PARSE 2      /* malformed pk / r1cs / json */
+#define G16_ERR_CUDA 3       /* CUDA runtime error or no device */
+#define G16_ERR_UNSAT 4      /* witness does not satisfy the constraint system */
+#define G16_ERR_UNSUPPORTED 5
+#define G16_ERR_STATE 6      /* e.g. cipher not initialised */
+
+typedef struct g16_ctx g16_ctx;
+
+int g16_version(void);
+const char* g16_last_error(void);
+int g16_device_count(int* n);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * (2) inner seam: context = one (proving key, constraint system) pair resident on one GPU.
+ * Replaces prove_impl.go:86-91 (pk ReadFrom: ~89k G1 + 12.5k G2 decompressions, done on the GPU here) and :102-107.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int g16_init(const uint8_t* pk, size_t pk_len, const uint8_t* r1cs, size_t r1cs_len, int device, g16_ctx** out);
+void g16_free(g16_ctx* ctx);
+
+/* info[0..15]: 0 domain size n, 1 |G1.A|, 2 |G1.B|, 3 |G1.Z|, 4 |G1.K|, 5 |G2.B|, 6 nbWires, 7 nbPublic (incl. ONE),
+ * 8 nbSecret, 9 nbConstraints, 10 nbInstructions, 11 nbLevels, 12 nbCommitments, 13 proof bytes, 14 device, 15 reserved */
+int g16_info(const g16_ctx* ctx, uint64_t info[16]);
+
+/* gnark-shaped entry: `witness` = the nbPublic-1 public then nbSecret secret assignments (what frontend.NewWitness
+ * yields, provers.go:144), Montgomery limbs. rs = r|s as 2 x 32-byte big-endian canonical scalars, or NULL to draw them
+ * from the OS CSPRNG (gnark draws from crypto/rand). proof_out must hold g16_info()[13] bytes. */
+int g16_prove_witness(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, const uint8_t* rs, uint8_t* proof_out,
+                      size_t* proof_len);
+
+/* library-shaped batch entry for cipher "chacha20" (provers.go:79-158 for n independent requests): computes the
+ * ciphertext, the witness, and the proof of each request on the GPU.
+ * keys n*32, nonces n*12, counters n (host order), inputs n*64, rs n*64 (or NULL) -> proofs n*164, ciphertexts n*64. */
+int g16_prove_chacha_batch(g16_ctx* ctx, size_t n, const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters,
+                           const uint8_t* inputs, const uint8_t* rs, uint8_t* proofs_out, uint8_t* ct_out);
+
+/* The same batch split into its three phases so a benchmark can time the device part with inputs already resident in
+ * HBM: stage (H2D) -> run (all kernels, returns after the stream drained; device time in *ms if non-NULL) -> fetch (D2H). */
+int g16_chacha_batch_stage(g16_ctx* ctx, size_t n, const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters,
+                           const uint8_t* inputs, const uint8_t* rs);
+int g16_chacha_batch_run(g16_ctx* ctx, float* ms);
+int g16_chacha_batch_fetch(g16_ctx* ctx, uint8_t* proofs_out, uint8_t* ct_out);
+
+/* per-stage timings of the last g16_chacha_batch_run, milliseconds: 0 witness+solve, 1 compute_h (7 NTT + pointwise),
+ * 2 MSM scalar prep + sort, 3 MSM bucket accumulation, 4 MSM reductions, 5 proof assembly, 6 total, 7 kernel launches */
+int g16_last_stage_ms(const g16_ctx* ctx, float ms[8]);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * stage-level entry points (parity tests against the oracle; standalone MSM / NTT sweeps of BASELINE config 5)
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* field: 0 = Fp, 1 = Fr. op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 sqr(a), 5 neg(a), 6 to_mont(a), 7 from_mont(a) */
+int g16_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+/* group: 1 = G1, 2 = G2. op 0: out = a + b (affine in/out) ; op 1: out = k * a, k = canonical scalar limbs in b (4 u64)
+ * ; op 2: out = 2a */
+int g16_group_op(int group, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+/* decompression of gnark-crypto compressed points (32 / 64 bytes each) -> affine Montgomery */
+int g16_decompress(int group, const uint8_t* in, uint64_t* out, size_t n);
+
+/* Pippenger MSM over n affine points (replaces (*G1Jac).MultiExp / (*G2Jac).MultiExp).
+ * scalars: n x 4 u64; scalars_mont != 0 if they are in Montgomery form (gnark passes fr.Element vectors).
+ * window = 0 picks c automatically. out = affine result. timing (optional): ms[0] total device time,
+ * ms[1] bucket-accumulation kernel, ms[2] sort (digits+scan+scatter), ms[3] reductions. Host buffers. */
+int g16_msm(int group, const uint64_t* points, const uint64_t* scalars, int scalars_mont, size_t n, int window,
+            uint64_t* out, float ms[4]);
+/* device-resident variant for benchmarking: upload once, run many times */
+typedef struct g16_msm_plan g16_msm_plan;
+int g16_msm_plan_create(int group, const uint64_t* points, size_t n, int window, int device, g16_msm_plan** out);
+int g16_msm_plan_set_scalars(g16_msm_plan* plan, const uint64_t* scalars, int scalars_mont);
+int g16_msm_plan_run(g16_msm_plan* plan, uint64_t* out, float ms[4]);
+void g16_msm_plan_free(g16_msm_plan* plan);
+
+/* Fr NTT of size n = 2^k on host data (replaces fft.(*Domain).FFT / FFTInverse). Natural order in and
+ * out; inverse != 0 applies w^-1 and the 1/n scaling; coset != 0 evaluates on / interpolates from the coset 5*<w>.
+ * ms (optional) = device time of the transform kernels only. */
+int g16_ntt(uint64_t* data, size_t n, int inverse, int coset, float* ms);
+/* device-resident batched variant: `batch` vectors of size n, repeated `iters` times forward+inverse; returns ms/iter */
+int g16_ntt_bench(size_t n, size_t batch, int iters, float* ms_per_iter, uint64_t* checksum);
+
+/* H = (A.B - C)/Z (replaces prove.go:computeH): a,b,c = nbConstraints evaluations each.
+ * h_out = n coefficients in gnark's array order (bit-reversed), which pairs index-for-index with pk.G1.Z. */
+int g16_compute_h(g16_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint64_t* h_out);
+/* R1CS solve (replaces constraint/bn254 (*system).Solve) for `batch` independent witnesses.
+ * witness: batch x n_witness. Outputs (any may be NULL): W batch x nbWires, A/B/C batch x nbConstraints. */
+int g16_solve(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, size_t batch, uint64_t* W, uint64_t* A,
+              uint64_t* B, uint64_t* C);
+/* the five MSM results of one proof before assembly: affine msmA, msmB1, msmK, msmZ (G1) and msmB2 (G2) */
+int g16_prove_witness_detail(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, const uint8_t* rs,
+                             uint8_t* proof_out, size_t* proof_len, uint64_t* msm_g1_out /* 4 x 8 */,
+                             uint64_t* msm_g2_out /* 16 */, uint64_t* h_out /* n x 4 or NULL */);
+
+/* integer-multiply microbenchmark: sustained 32-bit IMAD and IMAD.WIDE rates of this GPU (ops/s), the roofline
+ * denominator the MSM numbers are quoted against (not in MEASURED_PEAKS.json). */
+int g16_imad_peak(double* imad_per_s, double* imad_wide_per_s, double* modmul_per_s);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * (1) outer ABI: byte-compatible with the cgo exports of libraries/prover/libprove.go
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct { void* data; long long len; long long cap; } GoSlice_g16;
+typedef struct { void* r0; long long r1; } Prove_return_g16;
+void enforce_binding(void);                                                        /* libprove.go:17-18 */
+unsigned char InitAlgorithm(unsigned char algorithmID, GoSlice_g16 provingKey, GoSlice_g16 r1cs);   /* libprove.go:20-23 */
+void Free(void* pointer);                                                          /* libprove.go:25-28 */
+Prove_return_g16 Prove(GoSlice_g16 params);                                        /* libprove.go:30-47 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G16B200_H */
