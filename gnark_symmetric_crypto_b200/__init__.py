@@ -1,0 +1,6 @@
+"""gnark_symmetric_crypto_b200 — B200-native Groth16/BN254 prover backend for the ChaCha20-V3 / AES-V2 circuits of
+reclaimprotocol/gnark-symmetric-crypto. The compute path is the CUDA library lib/libg16b200.so (sm_100a); importing the
+package does not load it, the first call does, and a missing library is an ImportError (no CPU fallback)."""
+from . import _lib  # noqa: F401
+from .prover import (AES_128, AES_256, CHACHA20, Groth16Context, InitAlgorithm, InputParams, MsmPlan, OutputParams,  # noqa: F401
+                     Prove, ProverError, decompress, field_op, group_op, imad_peak, msm, ntt, ntt_bench)

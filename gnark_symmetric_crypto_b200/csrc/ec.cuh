@@ -120,15 +120,32 @@ struct XYZZ {
     }
 };
 
-// k * P for a scalar of `nbits` bits given as little-endian 32-bit limbs (double-and-add, MSB first)
+// k * P, k = 8 little-endian 32-bit limbs (double-and-add, MSB first). The limbs are passed BY VALUE in a struct and
+// indexed with compile-time constants only (outer loop unrolled): a dynamically indexed thread-local scalar array plus
+// an operand passed by reference was miscompiled by nvcc 12.9 / ptxas for sm_100a in a cold translation unit
+// (observed on B200: the scalar bits read back garbage), so neither appears here.
+struct Scalar256 {
+    uint32_t w[8];
+};
 template <class F>
-FD XYZZ<F> scalar_mul(const XYZZ<F>& p, const uint32_t* k, int nbits) {
+FD XYZZ<F> scalar_mul(XYZZ<F> p, Scalar256 k) {
     XYZZ<F> r = XYZZ<F>::inf();
-    for (int i = nbits - 1; i >= 0; i--) {
-        r = r.dbl();
-        if ((k[i >> 5] >> (i & 31)) & 1) r.add(p);
+#pragma unroll
+    for (int wi = 7; wi >= 0; wi--) {
+        uint32_t word = k.w[wi];
+#pragma unroll 1
+        for (int b = 31; b >= 0; b--) {
+            r = r.dbl();
+            if ((word >> b) & 1u) r.add(p);
+        }
     }
     return r;
+}
+template <class F, class P>
+FD XYZZ<F> scalar_mul(const XYZZ<F>& p, const Fe<P>& k) {
+    Scalar256 s;
+    for (int i = 0; i < 8; i++) s.w[i] = k.l[i];
+    return scalar_mul(p, s);
 }
 
 typedef Affine<Fp> G1Affine;

@@ -232,6 +232,13 @@ int g16_last_stage_ms(const g16_ctx* ctx, float ms[8]) {
     });
 }
 
+int g16_last_counters(const g16_ctx* ctx, uint64_t out[8]) {
+    return guarded([&] {
+        REQUIRE(ctx && out, "NULL argument");
+        memcpy(out, ctx->cx->counters, sizeof(uint64_t) * 8);
+    });
+}
+
 int g16_prove_witness(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, const uint8_t* rs, uint8_t* proof_out,
                       size_t* proof_len) {
     return guarded([&] { prove_witness_impl(ctx, witness, n_witness, rs, proof_out, proof_len, nullptr, nullptr, nullptr); });

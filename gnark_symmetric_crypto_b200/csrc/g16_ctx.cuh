@@ -55,7 +55,9 @@ struct Ctx {
     StageTimer timer;
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     size_t launches = 0;
+    uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t sub_batch = 64;
+    bool tables_ready = false;
 
     ~Ctx() {
         if (stream) cudaStreamDestroy(stream);
@@ -67,6 +69,25 @@ static inline int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     if (!v || !*v) return dflt;
     return atoi(v);
+}
+
+// table[w][i] = 2^(c w) * P_i for every query, so each MSM needs a single bucket set per proof
+static void ctx_build_tables(Ctx& cx) {
+    if (cx.tables_ready) return;
+    cudaStream_t st = cx.stream;
+    auto nwin = [](int c) { return (254 + c - 1) / c; };
+    cx.qA.table.alloc((size_t)cx.nA * nwin(cx.qA.c));
+    cx.qB.table.alloc((size_t)cx.nB * nwin(cx.qB.c));
+    cx.qZ.table.alloc((size_t)cx.nZ * nwin(cx.qZ.c));
+    cx.qK.table.alloc((size_t)cx.nK * nwin(cx.qK.c));
+    cx.tabB2.alloc((size_t)cx.nB2 * nwin(cx.cB2));
+    msm_precompute_g1(cx.A.p, cx.nA, nwin(cx.qA.c), cx.qA.c, cx.qA.table.p, st);
+    msm_precompute_g1(cx.B.p, cx.nB, nwin(cx.qB.c), cx.qB.c, cx.qB.table.p, st);
+    msm_precompute_g1(cx.Z.p, cx.nZ, nwin(cx.qZ.c), cx.qZ.c, cx.qZ.table.p, st);
+    msm_precompute_g1(cx.K.p, cx.nK, nwin(cx.qK.c), cx.qK.c, cx.qK.table.p, st);
+    msm_precompute_g2(cx.B2.p, cx.nB2, nwin(cx.cB2), cx.cB2, cx.tabB2.p, st);
+    G16_CUDA(cudaStreamSynchronize(st));
+    cx.tables_ready = true;
 }
 
 static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, const uint8_t* r1cs_bytes, size_t r1cs_len,
@@ -156,25 +177,15 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     cx->qK.map.upload(mapK.data(), mapK.size(), st);
     G16_CUDA(cudaStreamSynchronize(st));
 
-    // ---- fixed-base tables: table[w][i] = 2^(c w) * P_i, so each MSM needs a single bucket set per proof
+    // ---- fixed-base tables (built now, or on the first prove when G16_LAZY_TABLES=1 — gnark's icicle backend also
+    //      defers its device set-up to the first Prove)
     cx->qZ.c = env_int("G16_C_Z", 16);
     cx->qA.c = env_int("G16_C_A", 13);
     cx->qB.c = env_int("G16_C_B", 13);
     cx->qK.c = env_int("G16_C_K", 13);
     cx->cB2 = env_int("G16_C_B2", 13);
     cx->qA.n = pk.nA; cx->qB.n = pk.nB; cx->qZ.n = pk.nZ; cx->qK.n = pk.nK;
-    auto nwin = [](int c) { return (254 + c - 1) / c; };
-    cx->qA.table.alloc((size_t)pk.nA * nwin(cx->qA.c));
-    cx->qB.table.alloc((size_t)pk.nB * nwin(cx->qB.c));
-    cx->qZ.table.alloc((size_t)pk.nZ * nwin(cx->qZ.c));
-    cx->qK.table.alloc((size_t)pk.nK * nwin(cx->qK.c));
-    cx->tabB2.alloc((size_t)pk.nB2 * nwin(cx->cB2));
-    msm_precompute_g1(cx->A.p, pk.nA, nwin(cx->qA.c), cx->qA.c, cx->qA.table.p, st);
-    msm_precompute_g1(cx->B.p, pk.nB, nwin(cx->qB.c), cx->qB.c, cx->qB.table.p, st);
-    msm_precompute_g1(cx->Z.p, pk.nZ, nwin(cx->qZ.c), cx->qZ.c, cx->qZ.table.p, st);
-    msm_precompute_g1(cx->K.p, pk.nK, nwin(cx->qK.c), cx->qK.c, cx->qK.table.p, st);
-    msm_precompute_g2(cx->B2.p, pk.nB2, nwin(cx->cB2), cx->cB2, cx->tabB2.p, st);
-    G16_CUDA(cudaStreamSynchronize(st));
+    if (!env_int("G16_LAZY_TABLES", 0)) ctx_build_tables(*cx);
 
     // ---- FFT domain from the pk header (w, g big-endian canonical -> Montgomery on the device)
     {
@@ -317,11 +328,14 @@ static void run_query_g1(Ctx& cx, const PrecompQuery& q, const Fr* scalars, size
 static float ctx_run_batch(Ctx& cx, size_t n, bool chacha) {
     if (!cx.solver_supported) throw std::runtime_error("unsupported circuit: " + cx.solver_unsupported_reason);
     cudaStream_t st = cx.stream;
+    ctx_build_tables(cx);
     ctx_ensure_batch(cx, n);
     StageTimer& tm = cx.timer;
     tm.reset();
     size_t l0 = cx.ws1.launches + cx.ws2.launches + cx.dom.launches;
     size_t own = 0;
+    cx.ws1.log_reset();
+    cx.ws2.log_reset();
     tm.mark(ST_SOLVE, st);
     G16_CUDA(cudaMemsetAsync(cx.d_status.p, 0, 4, st));
     G16_CUDA(cudaMemsetAsync(cx.Aev.p, 0, n * cx.n_dom * sizeof(Fr), st));
@@ -369,6 +383,12 @@ static float ctx_run_batch(Ctx& cx, size_t n, bool chacha) {
     cx.stage_ms[6] = total;
     cx.launches = own + (cx.ws1.launches + cx.ws2.launches + cx.dom.launches - l0);
     cx.stage_ms[7] = (float)cx.launches;
+    cx.counters[0] = cx.ws1.log_sum(st);   // G1 mixed additions performed by the accumulate kernel
+    cx.counters[1] = cx.ws2.log_sum(st);   // G2 mixed additions
+    cx.counters[2] = cx.ws1.log_n;         // G1 accumulate launches
+    cx.counters[3] = cx.ws2.log_n;
+    cx.counters[4] = cx.launches;
+    cx.counters[5] = n;
     if (status & 4u) throw std::runtime_error("solver: unsupported hint");
     if (status & 3u) throw std::domain_error("witness does not satisfy the constraint system");
     return total;

@@ -36,9 +36,10 @@ __global__ void group_op_kernel(int op, const typename C::A* __restrict__ a, con
     if (op == 0) {
         acc.madd(((const typename C::A*)b)[i], false);
     } else if (op == 1) {
-        uint32_t k[8];
-        for (int j = 0; j < 8; j++) k[j] = ((const uint32_t*)b)[8 * i + j];
-        acc = scalar_mul(acc, k, 256);
+        Scalar256 k;
+        for (int j = 0; j < 8; j++) k.w[j] = ((const uint32_t*)b)[8 * i + j];
+        X res = scalar_mul(acc, k);
+        acc = res;
     } else if (op == 2) {
         acc = acc.dbl();
     } else {

@@ -372,6 +372,14 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     }
     G16_CHECK_LAUNCH();
     ws.launches += 7;
+    if (ws.entry_log.n < ws.log_n + 1) {   // grow the log (rare; keeps old values)
+        DevBuf<uint32_t> bigger((ws.log_n + 1) * 2 + 64);
+        if (ws.log_n) G16_CUDA(cudaMemcpyAsync(bigger.p, ws.entry_log.p, ws.log_n * 4, cudaMemcpyDeviceToDevice, stream));
+        G16_CUDA(cudaStreamSynchronize(stream));
+        ws.entry_log = std::move(bigger);
+    }
+    G16_CUDA(cudaMemcpyAsync(ws.entry_log.p + ws.log_n, ws.total.p, 4, cudaMemcpyDeviceToDevice, stream));
+    ws.log_n++;
     // reduction tree
     const uint32_t segs = sh.rows * sh.segs_per_row();
     uint32_t n_in = (uint32_t)sh.nbk;

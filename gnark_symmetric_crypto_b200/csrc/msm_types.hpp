@@ -37,6 +37,19 @@ struct MsmWorkspace {
     DevBuf<uint2> entries;
     DevBuf<X> buckets, head, tail, lvlR[2], lvlV[2], result;
     size_t launches = 0;
+    // number of sorted entries (= mixed additions of the accumulate kernel) of every run since log_reset()
+    DevBuf<uint32_t> entry_log;
+    size_t log_n = 0;
+    void log_reset() { log_n = 0; }
+    uint64_t log_sum(cudaStream_t st) {   // synchronises the stream
+        if (!log_n) return 0;
+        std::vector<uint32_t> h(log_n);
+        entry_log.download(h.data(), log_n, st);
+        G16_CUDA(cudaStreamSynchronize(st));
+        uint64_t s = 0;
+        for (uint32_t v : h) s += v;
+        return s;
+    }
 };
 
 static inline int msm_pick_window(size_t n) {

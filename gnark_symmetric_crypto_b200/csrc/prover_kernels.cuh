@@ -345,21 +345,21 @@ assemble_kernel(AssemblyKeys keys, uint32_t n, const G1XYZZ* __restrict__ mA, co
     G1XYZZ d1 = G1XYZZ::from_affine(keys.delta);
     G1XYZZ Ar = mA[i];
     Ar.madd(keys.alpha, false);
-    Ar.add(scalar_mul(d1, r.l, 254));
+    Ar.add(scalar_mul(d1, r));
     G1XYZZ Bs1 = mB1[i];
     Bs1.madd(keys.beta, false);
-    Bs1.add(scalar_mul(d1, s.l, 254));
+    Bs1.add(scalar_mul(d1, s));
     G1XYZZ Krs = mK[i];
     Krs.add(mZ[i]);
-    Krs.add(scalar_mul(Ar, s.l, 254));
-    Krs.add(scalar_mul(Bs1, r.l, 254));
-    Krs.add(scalar_mul(d1, rsm.l, 254).neg());
+    Krs.add(scalar_mul(Ar, s));
+    Krs.add(scalar_mul(Bs1, r));
+    Krs.add(scalar_mul(d1, rsm).neg());
     uint8_t* o = out + (size_t)i * out_stride;
     g1_compress(Ar.to_affine(), o);
     g1_compress(Krs.to_affine(), o + 96);
     G2XYZZ Bs = mB2[i];
     Bs.madd(keys.beta2, false);
-    Bs.add(scalar_mul(G2XYZZ::from_affine(keys.delta2), s.l, 254));
+    Bs.add(scalar_mul(G2XYZZ::from_affine(keys.delta2), s));
     g2_compress(Bs.to_affine(), o + 32);
     o[128] = 0; o[129] = 0; o[130] = 0; o[131] = 0;
     o[132] = 0x40;

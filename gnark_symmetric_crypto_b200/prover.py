@@ -1,0 +1,323 @@
+"""Host-side mirror of the reference's prover package, over the C-ABI of libg16b200.so.
+
+Same names, argument meaning and error behaviour as `libraries/prover/impl` of reclaimprotocol/gnark-symmetric-crypto:
+
+    CHACHA20, AES_128, AES_256            prove_impl.go:15-19
+    InitAlgorithm(id, pk, r1cs) -> bool   prove_impl.go:65-114   (False + message on stdout for bad ids / keys)
+    Prove(params: bytes) -> bytes         prove_impl.go:116-143  (raises = the reference's panic, cf. TestPanic
+                                                                  libraries/core_test.go:120-128)
+    InputParams / OutputParams            provers.go:53-59, prove_impl.go:45-52
+
+plus the batched entry the B200 backend adds: `Groth16Context.prove_chacha_batch`.
+Everything computes on the GPU through ctypes; there is no CPU path in this module.
+"""
+from __future__ import annotations
+
+import base64
+import ctypes as C
+import json
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import GoSlice, u8p, u32p, u64p, f32p
+
+CHACHA20 = 0
+AES_128 = 1
+AES_256 = 2
+
+_STATUS = {1: "bad argument", 2: "parse error", 3: "CUDA error", 4: "unsatisfied witness", 5: "unsupported", 6: "bad state"}
+
+
+class ProverError(RuntimeError):
+    def __init__(self, rc: int, msg: str):
+        super().__init__(f"g16 status {rc} ({_STATUS.get(rc, '?')}): {msg}")
+        self.rc = rc
+
+
+def _check(rc: int):
+    if rc:
+        raise ProverError(rc, _lib.load().g16_last_error().decode(errors="replace"))
+
+
+def _p8(a):
+    return a.ctypes.data_as(u8p)
+
+
+def _p64(a):
+    return a.ctypes.data_as(u64p)
+
+
+@dataclass
+class InputParams:   # provers.go:53-59
+    cipher: str
+    key: bytes
+    nonce: bytes
+    counter: int
+    input: bytes
+
+    def to_json(self) -> bytes:
+        return json.dumps({"cipher": self.cipher, "key": list(self.key), "nonce": list(self.nonce),
+                           "counter": self.counter, "input": list(self.input)}).encode()
+
+
+@dataclass
+class OutputParams:   # prove_impl.go:45-52
+    proof_json: bytes
+    public_signals: bytes
+
+    @staticmethod
+    def from_json(data: bytes) -> "OutputParams":
+        d = json.loads(data)
+        return OutputParams(base64.b64decode(d["proof"]["proofJson"]), base64.b64decode(d["publicSignals"]))
+
+
+def _slice(b: bytes):
+    buf = (C.c_uint8 * len(b)).from_buffer_copy(b) if len(b) else (C.c_uint8 * 1)()
+    return GoSlice(C.cast(buf, C.c_void_p), len(b), len(b)), buf
+
+
+def InitAlgorithm(algorithm_id: int, proving_key: bytes, r1cs: bytes) -> bool:
+    """libprove.go:20-23 / prove_impl.go:65-114 — through the library's own `InitAlgorithm` export."""
+    L = _lib.load()
+    if not 0 <= int(algorithm_id) <= 255:
+        return False
+    s1, k1 = _slice(proving_key)
+    s2, k2 = _slice(r1cs)
+    return bool(L.InitAlgorithm(int(algorithm_id), s1, s2))
+
+
+def Prove(params: bytes) -> bytes:
+    """libprove.go:30-47 — returns the JSON payload; a payload that is a bare JSON string is the reference's
+    panic-as-payload convention and is raised here as RuntimeError (Go callers of impl.Prove see a panic)."""
+    L = _lib.load()
+    s, keep = _slice(bytes(params))
+    r = L.Prove(s)
+    try:
+        out = C.string_at(r.r0, r.r1)
+    finally:
+        L.Free(r.r0)
+    if out[:1] == b'"':
+        raise RuntimeError(json.loads(out))
+    return out
+
+
+class Groth16Context:
+    """One (pk, r1cs) pair resident on one GPU: the inner seam under gnark's groth16.Prove."""
+
+    def __init__(self, pk: bytes, r1cs: bytes, device: int = 0):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        _check(self._L.g16_init(pk, len(pk), r1cs, len(r1cs), device, C.byref(self._h)))
+        info = np.zeros(16, dtype=np.uint64)
+        _check(self._L.g16_info(self._h, _p64(info)))
+        (self.n, self.nA, self.nB, self.nZ, self.nK, self.nB2, self.nb_wires, self.nb_public, self.nb_secret,
+         self.nb_constraints, self.nb_instructions, self.nb_levels, self.nb_commitments, self.proof_bytes, self.device,
+         self.supported) = [int(x) for x in info]
+
+    def close(self):
+        if self._h:
+            self._L.g16_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- gnark-shaped: witness (nbPublic-1+nbSecret Montgomery Fr, [n,4] u64) -> proof bytes
+    def prove_witness(self, witness: np.ndarray, rs: bytes | None = None, detail: bool = False):
+        w = np.ascontiguousarray(witness, dtype=np.uint64).reshape(-1, 4)
+        proof = np.zeros(self.proof_bytes, dtype=np.uint8)
+        plen = C.c_size_t(0)
+        rsb = np.frombuffer(rs, dtype=np.uint8).copy() if rs is not None else None
+        if not detail:
+            _check(self._L.g16_prove_witness(self._h, _p64(w), len(w), _p8(rsb) if rsb is not None else None, _p8(proof),
+                                             C.byref(plen)))
+            return proof[:plen.value].tobytes()
+        g1 = np.zeros((4, 8), dtype=np.uint64)
+        g2 = np.zeros(16, dtype=np.uint64)
+        h = np.zeros((self.n, 4), dtype=np.uint64)
+        _check(self._L.g16_prove_witness_detail(self._h, _p64(w), len(w), _p8(rsb) if rsb is not None else None,
+                                                _p8(proof), C.byref(plen), _p64(g1), _p64(g2), _p64(h)))
+        return proof[:plen.value].tobytes(), dict(msmA=g1[0], msmB1=g1[1], msmK=g1[2], msmZ=g1[3], msmB2=g2, h=h)
+
+    # ---- library-shaped batch (cipher "chacha20")
+    @staticmethod
+    def _pack(keys, nonces, counters, inputs, rs):
+        n = len(counters)
+        k = np.frombuffer(b"".join(keys), dtype=np.uint8).copy()
+        no = np.frombuffer(b"".join(nonces), dtype=np.uint8).copy()
+        i = np.frombuffer(b"".join(inputs), dtype=np.uint8).copy()
+        c = np.asarray(counters, dtype=np.uint32).copy()
+        if k.size != 32 * n:
+            raise ValueError(f"key length must be 32: {k.size // max(n, 1)}")
+        if no.size != 12 * n:
+            raise ValueError(f"nonce length must be 12: {no.size // max(n, 1)}")
+        if i.size != 64 * n:
+            raise ValueError(f"plaintext length must be 64: {i.size // max(n, 1)}")
+        r = None
+        if rs is not None:
+            r = np.frombuffer(b"".join(rs) if not isinstance(rs, (bytes, bytearray)) else bytes(rs), dtype=np.uint8).copy()
+            if r.size != 64 * n:
+                raise ValueError("rs must hold 64 bytes per proof")
+        return n, k, no, c, i, r
+
+    def prove_chacha_batch(self, keys, nonces, counters, inputs, rs=None):
+        """-> (list of 164-byte proofs, list of 64-byte ciphertexts)"""
+        n, k, no, c, i, r = self._pack(keys, nonces, counters, inputs, rs)
+        proofs = np.zeros(n * self.proof_bytes, dtype=np.uint8)
+        cts = np.zeros(n * 64, dtype=np.uint8)
+        _check(self._L.g16_prove_chacha_batch(self._h, n, _p8(k), _p8(no), c.ctypes.data_as(u32p), _p8(i),
+                                              _p8(r) if r is not None else None, _p8(proofs), _p8(cts)))
+        pb = self.proof_bytes
+        return [proofs[j * pb:(j + 1) * pb].tobytes() for j in range(n)], [cts[j * 64:(j + 1) * 64].tobytes() for j in range(n)]
+
+    # phase-split variant for benchmarks (arrays already packed by the caller)
+    def stage(self, k, no, c, i, r):
+        _check(self._L.g16_chacha_batch_stage(self._h, len(c), _p8(k), _p8(no), c.ctypes.data_as(u32p), _p8(i),
+                                              _p8(r) if r is not None else None))
+
+    def run(self) -> float:
+        ms = C.c_float(0)
+        _check(self._L.g16_chacha_batch_run(self._h, C.byref(ms)))
+        return ms.value
+
+    def fetch(self, proofs: np.ndarray, cts: np.ndarray):
+        _check(self._L.g16_chacha_batch_fetch(self._h, _p8(proofs), _p8(cts)))
+
+    def stage_ms(self) -> dict:
+        ms = np.zeros(8, dtype=np.float32)
+        _check(self._L.g16_last_stage_ms(self._h, ms.ctypes.data_as(f32p)))
+        names = ["solve", "compute_h", "msm_sort", "msm_accumulate", "msm_reduce", "assemble", "total", "launches"]
+        return {k: float(v) for k, v in zip(names, ms)}
+
+    def counters(self) -> dict:
+        c = np.zeros(8, dtype=np.uint64)
+        _check(self._L.g16_last_counters(self._h, _p64(c)))
+        names = ["g1_madds", "g2_madds", "g1_acc_launches", "g2_acc_launches", "launches", "proofs"]
+        return {k: int(v) for k, v in zip(names, c)}
+
+    # ---- stage-level
+    def solve(self, witness: np.ndarray, batch: int = 1):
+        w = np.ascontiguousarray(witness, dtype=np.uint64).reshape(batch, -1, 4)
+        nw = w.shape[1]
+        W = np.zeros((batch, self.nb_wires, 4), dtype=np.uint64)
+        A = np.zeros((batch, self.nb_constraints, 4), dtype=np.uint64)
+        B = np.zeros_like(A)
+        Cc = np.zeros_like(A)
+        _check(self._L.g16_solve(self._h, _p64(w), nw, batch, _p64(W), _p64(A), _p64(B), _p64(Cc)))
+        return W, A, B, Cc
+
+    def compute_h(self, a, b, c) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint64); b = np.ascontiguousarray(b, dtype=np.uint64)
+        c = np.ascontiguousarray(c, dtype=np.uint64)
+        h = np.zeros((self.n, 4), dtype=np.uint64)
+        _check(self._L.g16_compute_h(self._h, _p64(a), _p64(b), _p64(c), _p64(h)))
+        return h
+
+
+# ---------------------------------------------------------------------------------------------- stage-level free functions
+def field_op(field: int, op: str, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:
+    code = {"add": 0, "sub": 1, "mul": 2, "inv": 3, "sqr": 4, "neg": 5, "to_mont": 6, "from_mont": 7}[op]
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    out = np.empty_like(a)
+    bp = None
+    if b is not None:
+        b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+        bp = _p64(b)
+    _check(_lib.load().g16_field_op(field, code, _p64(a), bp, _p64(out), len(a)))
+    return out
+
+
+def group_op(group: int, op: str, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:
+    code = {"add": 0, "mul": 1, "dbl": 2, "add_xyzz": 3}[op]
+    w = 8 if group == 1 else 16
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, w)
+    out = np.empty_like(a)
+    bp = None
+    if b is not None:
+        b = np.ascontiguousarray(b, dtype=np.uint64)
+        bp = _p64(b)
+    _check(_lib.load().g16_group_op(group, code, _p64(a), bp, _p64(out), len(a)))
+    return out
+
+
+def decompress(group: int, raw: bytes) -> np.ndarray:
+    sz = 32 if group == 1 else 64
+    n = len(raw) // sz
+    buf = np.frombuffer(raw, dtype=np.uint8).copy()
+    out = np.zeros((n, 8 if group == 1 else 16), dtype=np.uint64)
+    _check(_lib.load().g16_decompress(group, _p8(buf), _p64(out), n))
+    return out
+
+
+def msm(group: int, points: np.ndarray, scalars: np.ndarray, scalars_mont: bool = False, window: int = 0):
+    """-> (affine result, [total, accumulate, sort, reduce] ms)"""
+    w = 8 if group == 1 else 16
+    pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, w)
+    sc = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    assert len(pts) == len(sc)
+    out = np.zeros(w, dtype=np.uint64)
+    ms = np.zeros(4, dtype=np.float32)
+    _check(_lib.load().g16_msm(group, _p64(pts), _p64(sc), int(scalars_mont), len(pts), window, _p64(out),
+                               ms.ctypes.data_as(f32p)))
+    return out, ms
+
+
+class MsmPlan:
+    """Device-resident MSM (points uploaded once) for the standalone sweeps of BASELINE config 5."""
+
+    def __init__(self, group: int, points: np.ndarray, window: int = 0, device: int = 0):
+        self._L = _lib.load()
+        self.group = group
+        w = 8 if group == 1 else 16
+        pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, w)
+        self.n = len(pts)
+        self._h = C.c_void_p()
+        _check(self._L.g16_msm_plan_create(group, _p64(pts), self.n, window, device, C.byref(self._h)))
+
+    def set_scalars(self, scalars: np.ndarray, mont: bool = False):
+        sc = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+        assert len(sc) == self.n
+        _check(self._L.g16_msm_plan_set_scalars(self._h, _p64(sc), int(mont)))
+
+    def run(self):
+        out = np.zeros(8 if self.group == 1 else 16, dtype=np.uint64)
+        ms = np.zeros(4, dtype=np.float32)
+        _check(self._L.g16_msm_plan_run(self._h, _p64(out), ms.ctypes.data_as(f32p)))
+        return out, ms
+
+    def close(self):
+        if self._h:
+            self._L.g16_msm_plan_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ntt(data: np.ndarray, inverse: bool = False, coset: bool = False):
+    d = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 4).copy()
+    ms = C.c_float(0)
+    _check(_lib.load().g16_ntt(_p64(d), len(d), int(inverse), int(coset), C.byref(ms)))
+    return d, ms.value
+
+
+def ntt_bench(n: int, batch: int, iters: int):
+    """-> (ms per transform of the whole batch, mismatches after forward+inverse round trips)"""
+    ms = C.c_float(0)
+    chk = C.c_uint64(0)
+    _check(_lib.load().g16_ntt_bench(n, batch, iters, C.byref(ms), C.byref(chk)))
+    return ms.value, chk.value
+
+
+def imad_peak():
+    a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+    _check(_lib.load().g16_imad_peak(C.byref(a), C.byref(b), C.byref(c)))
+    return {"imad_per_s": a.value, "imad_wide_per_s": b.value, "modmul_per_s": c.value}

@@ -76,6 +76,9 @@ int g16_chacha_batch_fetch(g16_ctx* ctx, uint8_t* proofs_out, uint8_t* ct_out);
 /* per-stage timings of the last g16_chacha_batch_run, milliseconds: 0 witness+solve, 1 compute_h (7 NTT + pointwise),
  * 2 MSM scalar prep + sort, 3 MSM bucket accumulation, 4 MSM reductions, 5 proof assembly, 6 total, 7 kernel launches */
 int g16_last_stage_ms(const g16_ctx* ctx, float ms[8]);
+/* work counters of the last run: 0 G1 mixed additions done by the bucket-accumulation kernel (= sorted entries),
+ * 1 G2 mixed additions, 2 G1 accumulate launches, 3 G2 accumulate launches, 4 kernel launches, 5 proofs */
+int g16_last_counters(const g16_ctx* ctx, uint64_t out[8]);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * stage-level entry points (parity tests against the oracle; standalone MSM / NTT sweeps of BASELINE config 5)

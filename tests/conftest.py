@@ -1,0 +1,105 @@
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def pk_bytes():
+    return (GOLDEN / "pk.chacha20").read_bytes()
+
+
+@pytest.fixture(scope="session")
+def r1cs_bytes():
+    return (GOLDEN / "r1cs.chacha20").read_bytes()
+
+
+@pytest.fixture(scope="session")
+def vk_bytes():
+    return (GOLDEN / "vk.chacha20").read_bytes()
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+    O.lib()
+    return O
+
+
+@pytest.fixture(scope="session")
+def oracle_prover(oracle, pk_bytes, r1cs_bytes):
+    return oracle.ChaChaOracleProver(pk_bytes, r1cs_bytes)
+
+
+@pytest.fixture(scope="session")
+def oracle_vk(oracle, vk_bytes):
+    return oracle.VerifyingKeyOracle(vk_bytes)
+
+
+@pytest.fixture(scope="session")
+def emu():
+    """TEST-ONLY host-emulation build of the product sources (tests/emu). Never reachable through the package API."""
+    subprocess.check_call(["make", "-C", str(ROOT / "tests" / "emu"), "-j", str(os.cpu_count() or 1), "-s"])
+    from gnark_symmetric_crypto_b200 import _lib
+    return _lib.bind(ROOT / "tests" / "emu" / "_build" / "libg16emu.so")
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx(pk_bytes, r1cs_bytes):
+    import gnark_symmetric_crypto_b200 as G
+    ctx = G.Groth16Context(pk_bytes, r1cs_bytes, device=0)
+    yield ctx
+    ctx.close()
+
+
+# the reference's own benchmark inputs, libraries/core_test.go:285 (config 1) + SURVEY.md Appendix H
+KAT = dict(
+    key=bytes([2]) * 32, nonce=bytes([3]) * 12, counter=3,
+    input=bytes.fromhex("a3f7e592aeda1507a7f51b35812dfc50a263d5a6d2df625e563b02e49c08bf30"
+                        "d0e7483f5b13ff079532224ee8fbc31ab1899b18e453d36d9793a8355eb0dee9"),
+    ct=bytes.fromhex("e11ef0b2e6d3e450ab1a3509c0a6a2c79ece1376a8a0a6c09603f26b15b106de"
+                     "e60711d709ca21ac7e545f7d2c040f1ba1933d4eff4823a142da7aaffa483224"),
+    r=int("11" * 20, 16), s=int("22" * 20, 16),
+    proof=bytes.fromhex(
+        "d73f52bc6800d1c4a07c95d0b21876d2ed029d442b2df690a2fe2a711b77f6e1"
+        "95200aa0384e7f1ea31d47954f1fa672350b66ecf2608c5db062aa7f9ff7153b"
+        "0f0896aa890cca5296834e8bf266931d6df1f412d99cfcf9d5786b7f3e7cb441"
+        "ddfbcad67781ec5c223db4246c4c4e3860638f210422b7c296e145b1df4153f8"
+        "00000000" "40" + "00" * 31),
+)
+
+
+@pytest.fixture(scope="session")
+def kat():
+    return KAT
+
+
+def batch_inputs(n, seed=b"g16-b200-batch"):
+    """BASELINE config 4 input stream: ChaCha20(key=SHA-256(seed), nonce=0) keystream cut into
+    key(32) | nonce(12) | counter(4, LE) | input(64) | r(32) | s(32) per request; r, s reduced mod the group order."""
+    import hashlib
+    import struct
+    from oracle import oracle as O
+    k = hashlib.sha256(seed).digest()
+    per = 32 + 12 + 4 + 64 + 64
+    nblocks = (n * per + 63) // 64
+    stream = b"".join(O.chacha20_block(k, i, bytes(12)) for i in range(nblocks))
+    keys, nonces, ctrs, ins, rs = [], [], [], [], []
+    for i in range(n):
+        b = stream[i * per:(i + 1) * per]
+        keys.append(b[:32]); nonces.append(b[32:44]); ctrs.append(struct.unpack("<I", b[44:48])[0]); ins.append(b[48:112])
+        r = int.from_bytes(b[112:144], "big") % O.R_MOD
+        s = int.from_bytes(b[144:176], "big") % O.R_MOD
+        rs.append(r.to_bytes(32, "big") + s.to_bytes(32, "big"))
+    return keys, nonces, ctrs, ins, rs

@@ -1,0 +1,205 @@
+"""CPU: kernel logic and host orchestration of the product, exercised through the TEST-ONLY host-emulation build
+(tests/emu: the same .cu sources compiled as C++ with -DG16_EMU) and compared with the oracle. The PTX carry chains
+themselves only run on the GPU (tests/test_gpu.py); their C twins run here."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from gnark_symmetric_crypto_b200 import _lib
+
+
+def p64(a):
+    return a.ctypes.data_as(_lib.u64p)
+
+
+def p8(a):
+    return a.ctypes.data_as(_lib.u8p)
+
+
+def ok(L, rc):
+    assert rc == 0, L.g16_last_error().decode()
+
+
+@pytest.mark.parametrize("fld", [0, 1])
+def test_field_ops(emu, oracle, fld):
+    rng = np.random.default_rng(100 + fld)
+    n = 300
+    mod = oracle.P_MOD if fld == 0 else oracle.R_MOD
+    a = oracle.to_mont(fld, oracle.rand_field(rng, fld, n)); b = oracle.to_mont(fld, oracle.rand_field(rng, fld, n))
+    a[0] = 0; b[1] = 0
+    a[2] = b[2] = oracle.to_mont(fld, oracle.ints_to_limbs([mod - 1]))[0]
+    a[3] = oracle.to_mont(fld, oracle.ints_to_limbs([1]))[0]
+    for op, code in (("add", 0), ("sub", 1), ("mul", 2), ("inv", 3), ("sqr", 4), ("neg", 5)):
+        out = np.empty_like(a)
+        ok(emu, emu.g16_field_op(fld, code, p64(a), p64(b) if code < 3 else None, p64(out), n))
+        assert np.array_equal(out, oracle.f_op(fld, op, a, b if code < 3 else None)), op
+    can = oracle.rand_field(rng, fld, n)
+    out = np.empty_like(can)
+    ok(emu, emu.g16_field_op(fld, 6, p64(can), None, p64(out), n))
+    assert np.array_equal(out, oracle.to_mont(fld, can))
+    back = np.empty_like(can)
+    ok(emu, emu.g16_field_op(fld, 7, p64(out), None, p64(back), n))
+    assert np.array_equal(back, can)
+
+
+def test_group_ops_and_special_cases(emu, oracle):
+    rng = np.random.default_rng(7)
+    P = oracle.g1_fixed_base(oracle.rand_field(rng, 1, 12)); Q = oracle.g1_fixed_base(oracle.rand_field(rng, 1, 12))
+    Q[0] = P[0]                                                             # P + P
+    Q[1] = P[1]; Q[1][4:8] = oracle.f_op(0, "neg", P[1][4:8].reshape(1, 4))[0]   # P + (-P)
+    Q[2] = 0; P[3] = 0                                                      # infinity on either side
+    out = np.empty_like(P)
+    ref = np.array([oracle.g1_add(P[i], Q[i]) for i in range(12)])
+    for op in (0, 3):
+        ok(emu, emu.g16_group_op(1, op, p64(P), p64(Q), p64(out), 12))
+        assert np.array_equal(out, ref), op
+    assert not ref[1].any()
+    sc = oracle.rand_field(rng, 1, 12)
+    ok(emu, emu.g16_group_op(1, 1, p64(P), p64(sc), p64(out), 12))
+    assert np.array_equal(out, np.array([oracle.g1_mul(P[i], oracle.limbs_to_ints(sc[i:i + 1])[0]) for i in range(12)]))
+    P2 = oracle.g2_fixed_base(oracle.rand_field(rng, 1, 6)); Q2 = oracle.g2_fixed_base(oracle.rand_field(rng, 1, 6)); Q2[0] = P2[0]
+    out2 = np.empty_like(P2)
+    ref2 = np.array([oracle.g2_add(P2[i], Q2[i]) for i in range(6)])
+    for op in (0, 3):
+        ok(emu, emu.g16_group_op(2, op, p64(P2), p64(Q2), p64(out2), 6))
+        assert np.array_equal(out2, ref2), op
+    c1 = np.frombuffer(oracle.g1_compress(P), dtype=np.uint8).copy(); d1 = np.empty_like(P)
+    ok(emu, emu.g16_decompress(1, p8(c1), p64(d1), 12)); assert np.array_equal(d1, P)
+    c2 = np.frombuffer(oracle.g2_compress(P2), dtype=np.uint8).copy(); d2 = np.empty_like(P2)
+    ok(emu, emu.g16_decompress(2, p8(c2), p64(d2), 6)); assert np.array_equal(d2, P2)
+    bad = c1.copy(); bad[0] &= 0x3F   # "uncompressed" flag in a 32-byte slot
+    assert emu.g16_decompress(1, p8(bad), p64(d1), 12) == 2   # G16_ERR_PARSE
+
+
+@pytest.mark.parametrize("n,c", [(1, 0), (7, 3), (300, 0), (300, 7), (700, 10)])
+def test_msm_g1(emu, oracle, n, c):
+    rng = np.random.default_rng(n * 31 + c)
+    pts = oracle.g1_fixed_base(oracle.rand_field(rng, 1, n)); sc = oracle.rand_field(rng, 1, n)
+    if n >= 300:   # zeros, +-1 runs (one huge bucket), duplicate points, infinity, empty buckets
+        sc[0] = 0; sc[1] = oracle.ints_to_limbs([1])[0]; sc[2] = oracle.ints_to_limbs([oracle.R_MOD - 1])[0]
+        pts[5] = pts[4]; sc[5] = sc[4]; pts[7] = 0
+        sc[10:130] = oracle.ints_to_limbs([1] * 120); sc[130:200] = oracle.ints_to_limbs([oracle.R_MOD - 1] * 70)
+    out = np.empty(8, dtype=np.uint64)
+    ok(emu, emu.g16_msm(1, p64(pts), p64(sc), 0, n, c, p64(out), None))
+    ref = oracle.g1_msm(pts, sc)
+    assert np.array_equal(out, ref)
+    scm = oracle.to_mont(1, sc)
+    ok(emu, emu.g16_msm(1, p64(pts), p64(scm), 1, n, c, p64(out), None))
+    assert np.array_equal(out, ref)
+
+
+def test_msm_edge_cases(emu, oracle):
+    rng = np.random.default_rng(2)
+    pts = oracle.g1_fixed_base(oracle.rand_field(rng, 1, 50))
+    out = np.empty(8, dtype=np.uint64)
+    zeros = np.zeros((50, 4), dtype=np.uint64)
+    ok(emu, emu.g16_msm(1, p64(pts), p64(zeros), 0, 50, 0, p64(out), None))
+    assert not out.any()                                   # all-zero scalars -> infinity
+    sc = oracle.rand_field(rng, 1, 50)
+    same = np.repeat(pts[:1], 50, axis=0).copy()           # 50 copies of one point: every bucket add is a doubling
+    ok(emu, emu.g16_msm(1, p64(same), p64(sc), 0, 50, 4, p64(out), None))
+    assert np.array_equal(out, oracle.g1_msm(same, sc))
+    assert emu.g16_msm(1, p64(pts), p64(sc), 0, 0, 0, p64(out), None) == 1   # n = 0 -> G16_ERR_ARG
+    p2 = oracle.g2_fixed_base(oracle.rand_field(rng, 1, 60)); s2 = oracle.rand_field(rng, 1, 60)
+    out2 = np.empty(16, dtype=np.uint64)
+    ok(emu, emu.g16_msm(2, p64(p2), p64(s2), 0, 60, 5, p64(out2), None))
+    assert np.array_equal(out2, oracle.g2_msm(p2, s2))
+
+
+@pytest.mark.parametrize("n", [2, 8, 256, 4096])
+def test_ntt(emu, oracle, n):
+    rng = np.random.default_rng(n)
+    x = oracle.to_mont(1, oracle.rand_field(rng, 1, n))
+    y = x.copy(); ok(emu, emu.g16_ntt(p64(y), n, 0, 0, None)); assert np.array_equal(y, oracle.ntt(x))
+    z = y.copy(); ok(emu, emu.g16_ntt(p64(z), n, 1, 0, None)); assert np.array_equal(z, x)
+    # coset transforms invert each other
+    y = x.copy(); ok(emu, emu.g16_ntt(p64(y), n, 0, 1, None))
+    z = y.copy(); ok(emu, emu.g16_ntt(p64(z), n, 1, 1, None)); assert np.array_equal(z, x)
+    assert emu.g16_ntt(p64(x), 3, 0, 0, None) == 1   # not a power of two
+
+
+def test_ntt_multi_pass_plan(emu, oracle):
+    # 2^13 needs a strided pass on top of the 2^11 tile pass
+    rng = np.random.default_rng(13)
+    n = 1 << 13
+    x = oracle.to_mont(1, oracle.rand_field(rng, 1, n))
+    y = x.copy(); ok(emu, emu.g16_ntt(p64(y), n, 0, 0, None)); assert np.array_equal(y, oracle.ntt(x))
+    z = y.copy(); ok(emu, emu.g16_ntt(p64(z), n, 1, 0, None)); assert np.array_equal(z, x)
+
+
+@pytest.fixture(scope="module")
+def emu_ctx(emu, pk_bytes, r1cs_bytes):
+    os.environ["G16_LAZY_TABLES"] = "1"   # the fixed-base tables take minutes to build under emulation
+    h = C.c_void_p()
+    try:
+        ok(emu, emu.g16_init(pk_bytes, len(pk_bytes), r1cs_bytes, len(r1cs_bytes), 0, C.byref(h)))
+    finally:
+        os.environ.pop("G16_LAZY_TABLES", None)
+    yield h
+    emu.g16_free(h)
+
+
+def test_host_parsers_and_solver_match_oracle(emu, emu_ctx, oracle, oracle_prover, kat):
+    info = np.zeros(16, dtype=np.uint64)
+    ok(emu, emu.g16_info(emu_ctx, p64(info)))
+    r = oracle_prover.cs.r
+    assert [int(x) for x in info[:13]] == [32768, 22001, 12529, 32767, 22128, 12529, r.n_wires, r.n_public, r.n_secret,
+                                          r.n_constraints, r.n_instr, len(r.levels), 0]
+    rng = np.random.default_rng(9)
+    reqs = [(kat["key"], kat["nonce"], kat["counter"], kat["input"]), (rng.bytes(32), rng.bytes(12), 0xFFFFFFFF, rng.bytes(64))]
+    wit = []
+    refs = []
+    for k, n, c, i in reqs:
+        inputs, _ = oracle.chacha_assignment(k, n, c, i)
+        wit.append(oracle.to_mont(1, oracle.ints_to_limbs(inputs[1:])))
+        refs.append(oracle_prover.cs.solve(inputs))
+    w = np.stack(wit)
+    nw, nc = r.n_wires, r.n_constraints
+    W = np.zeros((2, nw, 4), dtype=np.uint64); A = np.zeros((2, nc, 4), dtype=np.uint64); B = np.zeros_like(A); Cc = np.zeros_like(A)
+    ok(emu, emu.g16_solve(emu_ctx, p64(w), w.shape[1], 2, p64(W), p64(A), p64(B), p64(Cc)))
+    for j in range(2):
+        for got, ref in zip((W[j], A[j], B[j], Cc[j]), refs[j]):
+            assert np.array_equal(got, ref)
+    # a witness with one flipped ciphertext bit is rejected with G16_ERR_UNSAT
+    bad = w.copy()
+    bad[0, 640] = oracle.to_mont(1, oracle.ints_to_limbs([1 - oracle.limbs_to_ints(oracle.from_mont(1, w[0, 640:641]))[0]]))[0]
+    assert emu.g16_solve(emu_ctx, p64(bad), bad.shape[1], 2, None, None, None, None) == 4
+    assert emu.g16_solve(emu_ctx, p64(w), 5, 1, None, None, None, None) == 1   # wrong witness length
+
+
+def test_compute_h_matches_oracle(emu, emu_ctx, oracle, oracle_prover, kat):
+    inputs, _ = oracle.chacha_assignment(kat["key"], kat["nonce"], kat["counter"], kat["input"])
+    W, A, B, Cc = oracle_prover.cs.solve(inputs)
+    n = oracle_prover.pk.n
+    h = np.zeros((n, 4), dtype=np.uint64)
+    ok(emu, emu.g16_compute_h(emu_ctx, p64(A), p64(B), p64(Cc), p64(h)))
+    ref = oracle.compute_h(A, B, Cc, n)
+    assert np.array_equal(h, ref[oracle.bitrev_perm(n)])   # gnark's array order = bit-reversed coefficients
+    assert not h[oracle.bitrev_perm(n)[n - 1]].any()       # h_{n-1} = 0
+
+
+def test_malformed_keys_are_rejected(emu, pk_bytes, r1cs_bytes):
+    h = C.c_void_p()
+    assert emu.g16_init(pk_bytes[:1000], 1000, r1cs_bytes, len(r1cs_bytes), 0, C.byref(h)) == 2
+    assert b"truncated" in emu.g16_last_error()
+    assert emu.g16_init(pk_bytes, len(pk_bytes), r1cs_bytes[:-7], len(r1cs_bytes) - 7, 0, C.byref(h)) == 2
+    assert emu.g16_init(None, 0, r1cs_bytes, len(r1cs_bytes), 0, C.byref(h)) == 1
+
+
+def test_libprove_json_layer(emu):
+    """Error behaviour of the outer ABI (libprove.go:30-47, prove_impl.go:116-143) without any initialised cipher."""
+    import json
+
+    def prove(payload: bytes):
+        buf = (C.c_uint8 * len(payload)).from_buffer_copy(payload)
+        r = emu.Prove(_lib.GoSlice(C.cast(buf, C.c_void_p), len(payload), len(payload)))
+        out = C.string_at(r.r0, r.r1)
+        emu.Free(r.r0)
+        return json.loads(out)
+
+    assert "could not find prover" in prove(b'{"cipher":"aes-256-ctr1","key":[1],"nonce":[1],"counter":1,"input":[1]}')
+    assert "not initialized" in prove(b'{"cipher":"chacha20","key":"AAEC","nonce":[],"counter":1,"input":[]}')
+    assert isinstance(prove(b"{not json"), str)
+    assert "counter" in prove(b'{"cipher":"chacha20","counter":[0,1]}')   # core_test.go:122 passes an array: unmarshal error

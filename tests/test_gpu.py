@@ -1,0 +1,239 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI (ctypes), against the oracle on the same seeded
+inputs; the committed golden vectors; and size-independent properties at BASELINE.json's full sizes.
+Bit-exact everywhere — all arithmetic is integer (254-bit prime fields)."""
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import batch_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gnark_symmetric_crypto_b200 as G
+    return G
+
+
+@pytest.mark.parametrize("fld", [0, 1])
+def test_field_ops(G, oracle, fld):
+    rng = np.random.default_rng(200 + fld)
+    n = 1 << 14
+    mod = oracle.P_MOD if fld == 0 else oracle.R_MOD
+    a = oracle.to_mont(fld, oracle.rand_field(rng, fld, n)); b = oracle.to_mont(fld, oracle.rand_field(rng, fld, n))
+    a[0] = 0; b[1] = 0
+    a[2] = b[2] = oracle.to_mont(fld, oracle.ints_to_limbs([mod - 1]))[0]
+    a[3] = oracle.to_mont(fld, oracle.ints_to_limbs([1]))[0]
+    # limbs of all-ones / carries through every limb
+    a[4] = oracle.ints_to_limbs([mod - 1])[0]; b[4] = oracle.ints_to_limbs([mod - 2])[0]
+    for op in ("add", "sub", "mul", "sqr", "neg"):
+        bb = b if op in ("add", "sub", "mul") else None
+        assert np.array_equal(G.field_op(fld, op, a, bb), oracle.f_op(fld, op, a, bb)), op
+    assert np.array_equal(G.field_op(fld, "inv", a[:512]), oracle.f_op(fld, "inv", a[:512]))
+    can = oracle.rand_field(rng, fld, 1024)
+    m = G.field_op(fld, "to_mont", can)
+    assert np.array_equal(m, oracle.to_mont(fld, can))
+    assert np.array_equal(G.field_op(fld, "from_mont", m), can)
+
+
+def test_group_ops(G, oracle):
+    rng = np.random.default_rng(17)
+    n = 128
+    P = oracle.g1_fixed_base(oracle.rand_field(rng, 1, n)); Q = oracle.g1_fixed_base(oracle.rand_field(rng, 1, n))
+    Q[0] = P[0]; Q[1] = P[1]; Q[1][4:8] = oracle.f_op(0, "neg", P[1][4:8].reshape(1, 4))[0]; Q[2] = 0; P[3] = 0
+    ref = np.array([oracle.g1_add(P[i], Q[i]) for i in range(n)])
+    for op in ("add", "add_xyzz"):
+        assert np.array_equal(G.group_op(1, op, P, Q), ref), op
+    sc = oracle.rand_field(rng, 1, n)
+    ref = np.array([oracle.g1_mul(P[i], oracle.limbs_to_ints(sc[i:i + 1])[0]) for i in range(n)])
+    assert np.array_equal(G.group_op(1, "mul", P, sc), ref)
+    P2 = oracle.g2_fixed_base(oracle.rand_field(rng, 1, 32)); Q2 = oracle.g2_fixed_base(oracle.rand_field(rng, 1, 32)); Q2[0] = P2[0]
+    ref2 = np.array([oracle.g2_add(P2[i], Q2[i]) for i in range(32)])
+    for op in ("add", "add_xyzz"):
+        assert np.array_equal(G.group_op(2, op, P2, Q2), ref2), op
+    ref2 = np.array([oracle.g2_mul(P2[i], oracle.limbs_to_ints(sc[i:i + 1])[0]) for i in range(32)])
+    assert np.array_equal(G.group_op(2, "mul", P2, sc[:32]), ref2)
+
+
+def test_decompress_whole_proving_key(G, oracle, oracle_prover, pk_bytes):
+    from oracle import formats
+    lay = formats.parse_pk_layout(pk_bytes)
+    pk = oracle_prover.pk
+    for name in ("A", "B", "Z", "K"):
+        raw = pk_bytes[lay.offs[name]:lay.offs[name] + 32 * lay.counts[name]]
+        assert np.array_equal(G.decompress(1, raw), pk.array(name)), name
+    raw = pk_bytes[lay.offs["B2"]:lay.offs["B2"] + 64 * lay.counts["B2"]]
+    assert np.array_equal(G.decompress(2, raw), pk.array("B2"))
+    with pytest.raises(G.ProverError):
+        G.decompress(1, b"\x00" * 32)   # uncompressed flag in a compressed slot
+
+
+@pytest.mark.parametrize("n,c", [(1, 0), (2, 0), (300, 7), (5000, 0), (5000, 16), (1 << 16, 0)])
+def test_msm_g1(G, oracle, n, c):
+    rng = np.random.default_rng(n + c)
+    pts = oracle.g1_fixed_base(oracle.rand_field(rng, 1, n)); sc = oracle.rand_field(rng, 1, n)
+    if n >= 300:
+        sc[0] = 0; sc[1] = oracle.ints_to_limbs([1])[0]; sc[2] = oracle.ints_to_limbs([oracle.R_MOD - 1])[0]
+        pts[5] = pts[4]; sc[5] = sc[4]; pts[7] = 0
+        sc[10:130] = oracle.ints_to_limbs([1] * 120); sc[130:200] = oracle.ints_to_limbs([oracle.R_MOD - 1] * 70)
+    ref = oracle.g1_msm(pts, sc)
+    got, _ = G.msm(1, pts, sc, False, c)
+    assert np.array_equal(got, ref)
+    got, _ = G.msm(1, pts, oracle.to_mont(1, sc), True, c)
+    assert np.array_equal(got, ref)
+
+
+def test_msm_g2_and_edges(G, oracle):
+    rng = np.random.default_rng(23)
+    pts = oracle.g2_fixed_base(oracle.rand_field(rng, 1, 3000)); sc = oracle.rand_field(rng, 1, 3000)
+    got, _ = G.msm(2, pts, sc)
+    assert np.array_equal(got, oracle.g2_msm(pts, sc))
+    p1 = oracle.g1_fixed_base(oracle.rand_field(rng, 1, 64))
+    got, _ = G.msm(1, p1, np.zeros((64, 4), dtype=np.uint64))
+    assert not got.any()
+    same = np.repeat(p1[:1], 64, axis=0).copy(); s = oracle.rand_field(rng, 1, 64)
+    got, _ = G.msm(1, same, s, False, 4)
+    assert np.array_equal(got, oracle.g1_msm(same, s))
+
+
+def test_msm_2_20_against_field_only_oracle(G, oracle):
+    """BASELINE config 5 at 2^20: P_i = a_i*G (a small set of distinct points tiled), result must equal (sum a_i s_i)*G."""
+    rng = np.random.default_rng(5)
+    n, distinct = 1 << 20, 1 << 12
+    a = oracle.rand_field(rng, 1, distinct)
+    base = oracle.g1_fixed_base(a)
+    idx = rng.integers(0, distinct, n)
+    pts = base[idx]
+    sc = oracle.rand_field(rng, 1, n)
+    ai = np.array(oracle.limbs_to_ints(a), dtype=object)[idx]
+    tot = int(sum(int(x) * int(y) for x, y in zip(ai, oracle.limbs_to_ints(sc))) % oracle.R_MOD)
+    got, ms = G.msm(1, pts, sc)
+    assert np.array_equal(got, oracle.g1_mul(oracle.g1_gen(), tot))
+
+
+@pytest.mark.parametrize("n", [2, 256, 1 << 11, 1 << 12, 1 << 15, 1 << 17, 1 << 20])
+def test_ntt(G, oracle, n):
+    rng = np.random.default_rng(n)
+    x = oracle.to_mont(1, oracle.rand_field(rng, 1, n))
+    y, _ = G.ntt(x)
+    assert np.array_equal(y, oracle.ntt(x))
+    z, _ = G.ntt(y, inverse=True)
+    assert np.array_equal(z, x)
+    yc, _ = G.ntt(x, coset=True)
+    zc, _ = G.ntt(yc, inverse=True, coset=True)
+    assert np.array_equal(zc, x)
+
+
+def test_ntt_2_24_round_trip_and_point_checks(G, oracle):
+    n = 1 << 24
+    ms, mismatches = G.ntt_bench(n, 1, 1)
+    assert mismatches == 0
+    # 8 random output positions of a forward transform against direct evaluation sum x_j w^(ij) on a sparse input
+    rng = np.random.default_rng(24)
+    x = np.zeros((n, 4), dtype=np.uint64)
+    pos = rng.integers(0, n, 64)
+    vals = oracle.rand_field(rng, 1, 64)
+    x[pos] = oracle.to_mont(1, vals)
+    y, _ = G.ntt(x)
+    w = oracle.root_of_unity(n)
+    yi = oracle.from_mont(1, y)
+    vi = oracle.limbs_to_ints(vals)
+    last = {int(p): v for p, v in zip(pos, vi)}   # duplicate positions: last write wins, as in numpy
+    for i in rng.integers(0, n, 8):
+        want = sum(v * pow(w, (int(i) * p) % n, oracle.R_MOD) for p, v in last.items()) % oracle.R_MOD
+        assert oracle.limbs_to_ints(yi[int(i):int(i) + 1])[0] == want
+
+
+def test_solver_and_h_match_oracle(G, gpu_ctx, oracle, oracle_prover, kat):
+    rng = np.random.default_rng(31)
+    reqs = [(kat["key"], kat["nonce"], kat["counter"], kat["input"])] + \
+           [(rng.bytes(32), rng.bytes(12), int(rng.integers(0, 1 << 32)), rng.bytes(64)) for _ in range(3)]
+    wit, refs = [], []
+    for k, n, c, i in reqs:
+        inputs, _ = oracle.chacha_assignment(k, n, c, i)
+        wit.append(oracle.to_mont(1, oracle.ints_to_limbs(inputs[1:])))
+        refs.append(oracle_prover.cs.solve(inputs))
+    W, A, B, Cc = gpu_ctx.solve(np.stack(wit), batch=4)
+    for j in range(4):
+        for got, ref in zip((W[j], A[j], B[j], Cc[j]), refs[j]):
+            assert np.array_equal(got, ref)
+    n = gpu_ctx.n
+    h = gpu_ctx.compute_h(refs[0][1], refs[0][2], refs[0][3])
+    assert np.array_equal(h, oracle.compute_h(refs[0][1], refs[0][2], refs[0][3], n)[oracle.bitrev_perm(n)])
+    bad = np.stack(wit)
+    bad[1, 700] = oracle.to_mont(1, oracle.ints_to_limbs([1 - oracle.limbs_to_ints(oracle.from_mont(1, bad[1, 700:701]))[0]]))[0]
+    with pytest.raises(G.ProverError) as e:
+        gpu_ctx.solve(bad, batch=4)
+    assert e.value.rc == 4   # G16_ERR_UNSAT
+
+
+def test_kat_proof_msm_points_and_h(G, gpu_ctx, oracle, oracle_prover, oracle_vk, kat):
+    """BASELINE config 1: the reference's benchmark input (core_test.go:285), fixed r,s: serialized proof, the five MSM
+    points and every H coefficient equal the oracle's; the proof equals the committed KAT and vk.chacha20 accepts it."""
+    rs = kat["r"].to_bytes(32, "big") + kat["s"].to_bytes(32, "big")
+    inputs, ct = oracle.chacha_assignment(kat["key"], kat["nonce"], kat["counter"], kat["input"])
+    wit = oracle.to_mont(1, oracle.ints_to_limbs(inputs[1:]))
+    proof, det = gpu_ctx.prove_witness(wit, rs, detail=True)
+    assert proof == kat["proof"]
+    pr, _, ref = oracle_prover.prove(kat["key"], kat["nonce"], kat["counter"], kat["input"], kat["r"], kat["s"], detail=True)
+    assert pr == proof
+    for k in ("msmA", "msmB1", "msmK", "msmZ", "msmB2"):
+        assert np.array_equal(det[k], ref[k]), k
+    assert np.array_equal(det["h"], ref["h"][oracle.bitrev_perm(gpu_ctx.n)])
+    assert oracle_vk.verify(proof, inputs[1:gpu_ctx.nb_public])
+    # library-shaped entry gives the same bytes and the ciphertext
+    proofs, cts = gpu_ctx.prove_chacha_batch([kat["key"]], [kat["nonce"]], [kat["counter"]], [kat["input"]], [rs])
+    assert proofs[0] == proof and cts[0] == kat["ct"] == ct
+    # fresh randomness (rs = None): different bytes, still accepted
+    p2 = gpu_ctx.prove_witness(wit, None)
+    assert p2 != proof and oracle_vk.verify(p2, inputs[1:gpu_ctx.nb_public])
+
+
+def test_libprove_abi_round_trip(G, oracle, oracle_vk, pk_bytes, r1cs_bytes):
+    """The reference's own integration test shape (core_test.go:130-172 TestFullChaCha20, :120-128 TestPanic) through
+    the libprove-compatible exports: InitAlgorithm -> Prove(JSON) -> verifier accepts."""
+    assert G.InitAlgorithm(G.CHACHA20, pk_bytes, r1cs_bytes) is True
+    assert G.InitAlgorithm(G.CHACHA20, pk_bytes, r1cs_bytes) is True   # initDone short-cut
+    assert G.InitAlgorithm(9, pk_bytes, r1cs_bytes) is False
+    rng = np.random.default_rng(77)
+    key, nonce, pt, counter = rng.bytes(32), rng.bytes(12), rng.bytes(64), 1
+    out = G.OutputParams.from_json(G.Prove(G.InputParams("chacha20", key, nonce, counter, pt).to_json()))
+    assert len(out.proof_json) == 164
+    signals = out.public_signals + nonce + struct.pack("<I", counter) + pt   # core_test.go:157-163
+    assert out.public_signals == oracle.chacha20_xor(key, nonce, counter, pt)
+    assert oracle_vk.verify(out.proof_json, oracle.chacha_public_from_signals(signals))
+    with pytest.raises(RuntimeError, match="could not find prover"):
+        G.Prove(b'{"cipher":"aes-256-ctr1","key":[0],"nonce":[0],"counter":1,"input":[0]}')
+    with pytest.raises(RuntimeError, match="counter"):   # TestPanic's payload has an array there: json.Unmarshal fails
+        G.Prove(b'{"cipher":"aes-256-ctr1","key":[0],"nonce":[0],"counter":[0,1],"input":[0]}')
+    with pytest.raises(RuntimeError, match="key length must be 32"):
+        G.Prove(G.InputParams("chacha20", key[:31], nonce, counter, pt).to_json())
+    with pytest.raises(RuntimeError, match="plaintext length must be 64"):
+        G.Prove(G.InputParams("chacha20", key, nonce, counter, pt + b"x").to_json())
+    with pytest.raises(RuntimeError, match="not initialized"):
+        G.Prove(G.InputParams("aes-128-ctr", key[:16], nonce, counter, pt).to_json())
+
+
+def test_batch_1024_config4(G, gpu_ctx, oracle, oracle_prover, oracle_vk):
+    """BASELINE config 4: 1 024 seeded requests in one batch. Every ciphertext is checked; a 1/16 sample of the proofs is
+    compared byte-for-byte with the oracle and pairing-verified against the reference's vk.chacha20; all proofs must be
+    distinct and well-formed."""
+    n = 1024
+    keys, nonces, ctrs, ins, rs = batch_inputs(n)
+    proofs, cts = gpu_ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)
+    assert len(set(proofs)) == n
+    for i in range(n):
+        assert cts[i] == oracle.chacha20_xor(keys[i], nonces[i], ctrs[i], ins[i])
+        assert proofs[i][128:] == b"\x00\x00\x00\x00\x40" + b"\x00" * 31 and proofs[i][0] & 0x80
+    rng = np.random.default_rng(4)
+    for i in sorted(rng.choice(n, n // 16, replace=False).tolist()):
+        r = int.from_bytes(rs[i][:32], "big"); s = int.from_bytes(rs[i][32:], "big")
+        pr, ct = oracle_prover.prove(keys[i], nonces[i], ctrs[i], ins[i], r, s)
+        assert pr == proofs[i], i
+        signals = cts[i] + nonces[i] + struct.pack("<I", ctrs[i]) + ins[i]
+        assert oracle_vk.verify(proofs[i], oracle.chacha_public_from_signals(signals)), i
+    # sub-batching must not matter: proving request 5 alone gives the same bytes
+    p5, _ = gpu_ctx.prove_chacha_batch(keys[5:6], nonces[5:6], ctrs[5:6], ins[5:6], rs[5:6])
+    assert p5[0] == proofs[5]
