@@ -267,7 +267,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "sub_batch": int(os.environ.get("G16_SUBBATCH", "64")),
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "sub_batch": int(os.environ.get("G16_SUBBATCH", "256")),
                        "l2": "working set per step (wires 0.76 GB + A/B/C 3.2 GB + MSM scratch) exceeds the 126 MB L2; no flush needed",
                        "parallelism": f"{world} x independent proof shards, no collective"},
             "e2e": {"value": total_units / (e2e_total_ms / 1e3), "unit": UNIT,

@@ -55,6 +55,7 @@ EXPORTS = {
     "g16_solve": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_size_t, u64p, u64p, u64p, u64p]),
     "g16_prove_witness_detail": (C.c_int, [C.c_void_p, u64p, C.c_size_t, u8p, u8p, C.POINTER(C.c_size_t), u64p, u64p, u64p]),
     "g16_imad_peak": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "g16_imad_chain_rate": (C.c_int, [C.POINTER(C.c_double)]),
     "enforce_binding": (None, []),
     "InitAlgorithm": (C.c_ubyte, [C.c_ubyte, GoSlice, GoSlice]),
     "Free": (None, [C.c_void_p]),

@@ -153,4 +153,16 @@ typedef Affine<Fp2> G2Affine;
 typedef XYZZ<Fp> G1XYZZ;
 typedef XYZZ<Fp2> G2XYZZ;
 
+// group traits used as template arguments of the kernels
+struct G1 {
+    typedef Fp F;
+    typedef Affine<Fp> A;
+    typedef XYZZ<Fp> X;
+};
+struct G2 {
+    typedef Fp2 F;
+    typedef Affine<Fp2> A;
+    typedef XYZZ<Fp2> X;
+};
+
 }  // namespace g16

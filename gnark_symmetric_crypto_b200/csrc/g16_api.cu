@@ -264,11 +264,16 @@ int g16_solve(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, size_t ba
         G16_CUDA(cudaMemsetAsync(c.Aev.p, 0, batch * c.n_dom * sizeof(Fr), st));
         G16_CUDA(cudaMemsetAsync(c.Bev.p, 0, batch * c.n_dom * sizeof(Fr), st));
         G16_CUDA(cudaMemsetAsync(c.Cev.p, 0, batch * c.n_dom * sizeof(Fr), st));
-        launch_witness_copy(c.d_witness.p, (uint32_t)n_witness, (uint32_t)batch, c.W.p, (size_t)c.nb_wires, st);
-        launch_solver(c.sp, (uint32_t)batch, c.W.p, (size_t)c.nb_wires, c.Aev.p, c.Bev.p, c.Cev.p, c.d_status.p, st);
+        launch_witness_copy(c.d_witness.p, (uint32_t)n_witness, (uint32_t)batch, c.W.p, batch, st);
+        launch_solver(c.sp, c.h_level_off.data(), (uint32_t)batch, c.W.p, batch, c.Aev.p, c.Bev.p, c.Cev.p, c.d_status.p, st);
         uint32_t status = 0;
         c.d_status.download(&status, 1, st);
-        if (W) c.W.download((Fr*)W, batch * c.nb_wires, st);
+        DevBuf<Fr> rows;
+        if (W) {
+            rows.alloc(batch * c.nb_wires);
+            launch_wires_to_rows(c.W.p, batch, (uint32_t)batch, c.nb_wires, rows.p, st);
+            rows.download((Fr*)W, batch * c.nb_wires, st);
+        }
         for (size_t i = 0; i < batch; i++) {
             if (A) G16_CUDA(cudaMemcpyAsync(A + i * 4 * c.n_constraints, c.Aev.p + i * c.n_dom, (size_t)c.n_constraints * 32, cudaMemcpyDeviceToHost, st));
             if (B) G16_CUDA(cudaMemcpyAsync(B + i * 4 * c.n_constraints, c.Bev.p + i * c.n_dom, (size_t)c.n_constraints * 32, cudaMemcpyDeviceToHost, st));
@@ -391,11 +396,11 @@ int g16_msm_plan_run(g16_msm_plan* plan, uint64_t* out, float ms[4]) {
         MsmShape sh = msm_make_shape(plan->n, 1, plan->c, 0);
         plan->tm.reset();
         if (plan->group == 1) {
-            msm_run_g1(plan->ws1, sh, plan->p1.p, plan->scalars.p, plan->n, nullptr, plan->scalars_mont, st, &plan->tm);
+            msm_run_g1(plan->ws1, sh, plan->p1.p, plan->scalars.p, plan->n, 1, nullptr, plan->scalars_mont, st, &plan->tm);
             xyzz_to_affine_g1(plan->ws1.result.p, 1, plan->o1.p, st);
             plan->o1.download((G1Affine*)out, 1, st);
         } else {
-            msm_run_g2(plan->ws2, sh, plan->p2.p, plan->scalars.p, plan->n, nullptr, plan->scalars_mont, st, &plan->tm);
+            msm_run_g2(plan->ws2, sh, plan->p2.p, plan->scalars.p, plan->n, 1, nullptr, plan->scalars_mont, st, &plan->tm);
             xyzz_to_affine_g2(plan->ws2.result.p, 1, plan->o2.p, st);
             plan->o2.download((G2Affine*)out, 1, st);
         }
@@ -504,6 +509,12 @@ int g16_ntt_bench(size_t n, size_t batch, int iters, float* ms_per_iter, uint64_
     });
 }
 
+int g16_imad_chain_rate(double* wide_carry_mads_per_s) {
+    return guarded([&] {
+        REQUIRE(wide_carry_mads_per_s, "NULL argument");
+        *wide_carry_mads_per_s = imad_chain_rate();
+    });
+}
 int g16_imad_peak(double* imad_per_s, double* imad_wide_per_s, double* modmul_per_s) {
     return guarded([&] {
         REQUIRE(imad_per_s && imad_wide_per_s && modmul_per_s, "NULL argument");

@@ -34,12 +34,16 @@ struct Ctx {
     DevBuf<G2Affine> tabB2;
     int cB2 = 0;
     AssemblyKeys keys;
+    AssemblyScratch asm_scratch;
+    DevBuf<G1Affine> delta_tab;
+    DevBuf<G2Affine> delta2_tab;
     NttDomain dom;
     // solver program
     DevBuf<uint32_t> d_calldata, d_level_instr, d_level_off;
     DevBuf<InsMeta> d_meta;
     DevBuf<Fr> d_coeffs, d_ucoef_inv, d_lookup_tabs;
     SolverProgram sp;
+    std::vector<uint32_t> h_level_off;
     bool solver_supported = true;
     std::string solver_unsupported_reason;
     // batch state
@@ -56,7 +60,7 @@ struct Ctx {
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     size_t launches = 0;
     uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    uint32_t sub_batch = 64;
+    uint32_t sub_batch = 256;
     bool tables_ready = false;
 
     ~Ctx() {
@@ -97,7 +101,7 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     G16_CUDA(cudaSetDevice(device));
     G16_CUDA(cudaStreamCreate(&cx->stream));
     cudaStream_t st = cx->stream;
-    cx->sub_batch = (uint32_t)env_int("G16_SUBBATCH", 64);
+    cx->sub_batch = (uint32_t)env_int("G16_SUBBATCH", 256);
     if (cx->sub_batch == 0) cx->sub_batch = 1;
 
     PkFile pk = parse_pk(pk_bytes, pk_len);
@@ -154,6 +158,12 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
         G16_CUDA(cudaStreamSynchronize(st));
         cx->keys.alpha = h1[0]; cx->keys.beta = h1[1]; cx->keys.delta = h1[2];
         cx->keys.beta2 = h2[0]; cx->keys.delta2 = h2[1];
+        cx->delta_tab.alloc(64 * 15);
+        cx->delta2_tab.alloc(64 * 15);
+        cx->keys.delta_tab = cx->delta_tab.p;
+        cx->keys.delta2_tab = cx->delta2_tab.p;
+        launch_fixed_base_tables(cx->keys, cx->delta_tab.p, cx->delta2_tab.p, st);
+        G16_CUDA(cudaStreamSynchronize(st));
     }
 
     // ---- wire maps of the four G1 queries (the G2 query shares B's)
@@ -284,6 +294,7 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
         cx->d_meta.upload(meta.data(), meta.size(), st);
         cx->d_level_instr.upload(lvl_instr.data(), lvl_instr.size(), st);
         cx->d_level_off.upload(lvl_off.data(), lvl_off.size(), st);
+        cx->h_level_off = lvl_off;
         cx->d_coeffs.upload((const Fr*)cs.coeffs.data(), cs.coeffs.size() / 4, st);
         cx->d_lookup_tabs.upload((const Fr*)tabs.data(), tabs.size() / 4, st);
         cx->d_ucoef_inv.alloc(cs.n_instr());
@@ -317,10 +328,10 @@ static void ctx_ensure_batch(Ctx& cx, size_t n) {
     cx.d_rs.ensure(2 * n);
 }
 
-static void run_query_g1(Ctx& cx, const PrecompQuery& q, const Fr* scalars, size_t row_stride, bool use_map, uint32_t rows,
-                         G1XYZZ* out, StageTimer* tm) {
+static void run_query_g1(Ctx& cx, const PrecompQuery& q, const Fr* scalars, size_t row_stride, size_t elem_stride, bool use_map,
+                         uint32_t rows, G1XYZZ* out, StageTimer* tm) {
     MsmShape sh = msm_make_shape(q.n, rows, q.c, 1);
-    msm_run_g1(cx.ws1, sh, q.table.p, scalars, row_stride, use_map ? q.map.p : nullptr, 1, cx.stream, tm);
+    msm_run_g1(cx.ws1, sh, q.table.p, scalars, row_stride, elem_stride, use_map ? q.map.p : nullptr, 1, cx.stream, tm);
     G16_CUDA(cudaMemcpyAsync(out, cx.ws1.result.p, (size_t)rows * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, cx.stream));
 }
 
@@ -342,37 +353,36 @@ static float ctx_run_batch(Ctx& cx, size_t n, bool chacha) {
     G16_CUDA(cudaMemsetAsync(cx.Bev.p, 0, n * cx.n_dom * sizeof(Fr), st));
     G16_CUDA(cudaMemsetAsync(cx.Cev.p, 0, n * cx.n_dom * sizeof(Fr), st));
     if (chacha) {
-        launch_chacha_witness(cx.d_keys.p, cx.d_nonces.p, cx.d_counters.p, cx.d_inputs.p, (uint32_t)n, cx.W.p,
-                              (size_t)cx.nb_wires, cx.d_ct.p, st);
+        launch_chacha_witness(cx.d_keys.p, cx.d_nonces.p, cx.d_counters.p, cx.d_inputs.p, (uint32_t)n, cx.W.p, n, cx.d_ct.p, st);
     } else {
-        launch_witness_copy(cx.d_witness.p, cx.n_public - 1 + cx.n_secret, (uint32_t)n, cx.W.p, (size_t)cx.nb_wires, st);
+        launch_witness_copy(cx.d_witness.p, cx.n_public - 1 + cx.n_secret, (uint32_t)n, cx.W.p, n, st);
     }
     launch_scalars_from_be(cx.d_rs_be.p, (uint32_t)(2 * n), cx.d_rs.p, st);
-    launch_solver(cx.sp, (uint32_t)n, cx.W.p, (size_t)cx.nb_wires, cx.Aev.p, cx.Bev.p, cx.Cev.p, cx.d_status.p, st);
-    own += 3;
+    // W is wire-major: wire k of proof i at W[k*n + i]
+    own += 2 + launch_solver(cx.sp, cx.h_level_off.data(), (uint32_t)n, cx.W.p, n, cx.Aev.p, cx.Bev.p, cx.Cev.p,
+                             cx.d_status.p, st);
     for (size_t sb = 0; sb < n; sb += cx.sub_batch) {
         uint32_t rows = (uint32_t)((n - sb) < cx.sub_batch ? (n - sb) : cx.sub_batch);
         Fr* a = cx.Aev.p + sb * cx.n_dom;
         Fr* b = cx.Bev.p + sb * cx.n_dom;
         Fr* c = cx.Cev.p + sb * cx.n_dom;
-        const Fr* w = cx.W.p + sb * cx.nb_wires;
+        const Fr* w = cx.W.p + sb;   // column offset into the wire-major array
         tm.mark(ST_H, st);
         compute_h_run(cx.dom, a, b, c, cx.n_dom, rows, st);
         // h (gnark order) pairs index-for-index with G1.Z; the other queries read wire values through their maps
-        run_query_g1(cx, cx.qZ, a, cx.n_dom, false, rows, cx.resZ.p + sb, &tm);
-        run_query_g1(cx, cx.qA, w, cx.nb_wires, true, rows, cx.resA.p + sb, &tm);
-        run_query_g1(cx, cx.qB, w, cx.nb_wires, true, rows, cx.resB1.p + sb, &tm);
-        run_query_g1(cx, cx.qK, w, cx.nb_wires, true, rows, cx.resK.p + sb, &tm);
+        run_query_g1(cx, cx.qZ, a, cx.n_dom, 1, false, rows, cx.resZ.p + sb, &tm);
+        run_query_g1(cx, cx.qA, w, 1, n, true, rows, cx.resA.p + sb, &tm);
+        run_query_g1(cx, cx.qB, w, 1, n, true, rows, cx.resB1.p + sb, &tm);
+        run_query_g1(cx, cx.qK, w, 1, n, true, rows, cx.resK.p + sb, &tm);
         {
             MsmShape sh = msm_make_shape(cx.nB2, rows, cx.cB2, 1);
-            msm_run_g2(cx.ws2, sh, cx.tabB2.p, w, cx.nb_wires, cx.qB.map.p, 1, st, &tm);
+            msm_run_g2(cx.ws2, sh, cx.tabB2.p, w, 1, n, cx.qB.map.p, 1, st, &tm);
             G16_CUDA(cudaMemcpyAsync(cx.resB2.p + sb, cx.ws2.result.p, (size_t)rows * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st));
         }
     }
     tm.mark(ST_ASSEMBLE, st);
-    launch_assemble(cx.keys, (uint32_t)n, cx.resA.p, cx.resB1.p, cx.resK.p, cx.resZ.p, cx.resB2.p, cx.d_rs.p, cx.d_proofs.p,
-                    cx.proof_bytes(), st);
-    own += 1;
+    own += launch_assemble(cx.keys, cx.asm_scratch, (uint32_t)n, cx.resA.p, cx.resB1.p, cx.resK.p, cx.resZ.p, cx.resB2.p,
+                           cx.d_rs.p, cx.d_proofs.p, cx.proof_bytes(), st);
     tm.mark(-1, st);
     uint32_t status = 0;
     cx.d_status.download(&status, 1, st);

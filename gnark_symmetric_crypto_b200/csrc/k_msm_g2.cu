@@ -4,8 +4,8 @@
 namespace g16 {
 
 void msm_run_g2(MsmWorkspace<G2>& ws, const MsmShape& sh, const G2Affine* bases, const Fr* scalars, size_t row_stride,
-                const uint32_t* map, int is_mont, cudaStream_t stream, StageTimer* tm, int chunk_len) {
-    msm_run<G2>(ws, sh, bases, scalars, row_stride, map, is_mont, stream, tm, chunk_len);
+                size_t elem_stride, const uint32_t* map, int is_mont, cudaStream_t stream, StageTimer* tm, int chunk_len) {
+    msm_run<G2>(ws, sh, bases, scalars, row_stride, elem_stride, map, is_mont, stream, tm, chunk_len);
 }
 void msm_precompute_g2(const G2Affine* pts, uint32_t n, int nwin, int c, G2Affine* table, cudaStream_t stream) {
     auto k = msm_precompute_kernel<G2>;

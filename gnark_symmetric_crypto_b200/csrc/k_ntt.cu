@@ -173,6 +173,24 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, int iters
         if (s == 0x1234567u) out[0] = s;
     }
 }
+// carry-chain wide MADs (mad.lo.cc / madc.hi.cc pairs = IMAD.WIDE.U32.X with a predicate carry), four independent
+// 8-limb accumulators per thread: the instruction mix of the Montgomery product itself
+__global__ void __launch_bounds__(256) imad_chain_peak_kernel(uint32_t* out, int iters) {
+    uint32_t a = threadIdx.x * 2654435761u + 1, b = blockIdx.x * 40503u + 7;
+    uint32_t acc[4][8];
+    for (int k = 0; k < 4; k++) for (int j = 0; j < 8; j++) acc[k][j] = a + 17 * k + j;
+    uint32_t sink = 0;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) sink += mad4(acc[k], a, b, a ^ b, a + b, b + u);
+        }
+    }
+    uint32_t s = sink;
+    for (int k = 0; k < 4; k++) for (int j = 0; j < 8; j++) s ^= acc[k][j];
+    if (s == 0x1234567u) out[0] = s;
+}
 // two independent dependent-chains of Fp products per thread
 __global__ void __launch_bounds__(256) modmul_peak_kernel(Fp* out, int iters) {
     Fp a = Fp::one(), b = Fp::r2(), c = Fp::one(), d = Fp::r2();
@@ -190,6 +208,8 @@ __global__ void __launch_bounds__(256) modmul_peak_kernel(Fp* out, int iters) {
 }
 #endif
 
+static double g_chain_rate = 0;
+double imad_chain_rate() { return g_chain_rate; }
 void imad_peak_measure(double* imad_per_s, double* imad_wide_per_s, double* modmul_per_s) {
 #if defined(G16_EMU)
     throw std::runtime_error("imad peak needs a GPU");
@@ -217,6 +237,9 @@ void imad_peak_measure(double* imad_per_s, double* imad_wide_per_s, double* modm
     double ops = (double)blocks * threads * iters * 16.0 * 8.0;
     double t0 = time_it([&] { imad_peak_kernel<0><<<blocks, threads>>>(out.p, iters); });
     double t1 = time_it([&] { imad_peak_kernel<1><<<blocks, threads>>>(out.p, iters); });
+    // 4 unrolled x 4 chains x 4 wide MADs per iteration
+    double t3 = time_it([&] { imad_chain_peak_kernel<<<blocks, threads>>>(out.p, iters); });
+    g_chain_rate = (double)blocks * threads * iters * 64.0 / t3;
     const int mm_iters = 400;
     double t2 = time_it([&] { modmul_peak_kernel<<<blocks, threads>>>((Fp*)out.p, mm_iters); });
     G16_CHECK_LAUNCH();

@@ -91,25 +91,29 @@ void launch_witness_copy(const Fr* witness, uint32_t n_witness, uint32_t batch, 
                batch, W, w_stride);
     G16_CHECK_LAUNCH();
 }
-void launch_solver(const SolverProgram& sp, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C, uint32_t* status,
-                   cudaStream_t st) {
-    G16_LAUNCH(solver_kernel, div_up(batch, 32), dim3(32, SOLVER_WARPS), 0, st, true, sp, batch, W, w_stride, A, B, C, status);
+void launch_wires_to_rows(const Fr* W, size_t w_stride, uint32_t batch, uint32_t nb_wires, Fr* out, cudaStream_t st) {
+    G16_LAUNCH(wires_to_rows_kernel, div_up((size_t)batch * nb_wires, 256), 256, 0, st, false, W, w_stride, batch, nb_wires, out);
     G16_CHECK_LAUNCH();
 }
-int launch_solver_init(const SolverProgram& sp, uint32_t n_instr, uint32_t n_coeffs, Fr* ucoef_inv, cudaStream_t st) {
-    DevBuf<uint32_t> flag(1);
-    G16_LAUNCH(solver_check_coeffs_kernel, 1, 1, 0, st, false, sp.coeffs, n_coeffs, flag.p);
-    G16_LAUNCH(solver_ucoef_kernel, div_up(n_instr, 128), 128, 0, st, false, sp, n_instr, ucoef_inv);
+void launch_fixed_base_tables(const AssemblyKeys& keys, G1Affine* tab1, G2Affine* tab2, cudaStream_t st) {
+    auto k1 = fixed_base_table_kernel<G1>;
+    auto k2 = fixed_base_table_kernel<G2>;
+    G16_LAUNCH(k1, 1, 64, 0, st, false, keys.delta, tab1);
+    G16_LAUNCH(k2, 1, 64, 0, st, false, keys.delta2, tab2);
     G16_CHECK_LAUNCH();
-    uint32_t hf = 0;
-    flag.download(&hf, 1, st);
-    G16_CUDA(cudaStreamSynchronize(st));
-    return (int)hf;
 }
-void launch_assemble(const AssemblyKeys& keys, uint32_t n, const G1XYZZ* mA, const G1XYZZ* mB1, const G1XYZZ* mK,
-                     const G1XYZZ* mZ, const G2XYZZ* mB2, const Fr* rs, uint8_t* out, size_t out_stride, cudaStream_t st) {
-    G16_LAUNCH(assemble_kernel, div_up(n, 64), 64, 0, st, false, keys, n, mA, mB1, mK, mZ, mB2, rs, out, out_stride);
+size_t launch_assemble(const AssemblyKeys& keys, AssemblyScratch& sc, uint32_t n, const G1XYZZ* mA, const G1XYZZ* mB1,
+                       const G1XYZZ* mK, const G1XYZZ* mZ, const G2XYZZ* mB2, const Fr* rs, uint8_t* out, size_t out_stride,
+                       cudaStream_t st) {
+    sc.Ar.ensure(n); sc.Bs1.ensure(n); sc.sAr.ensure(n); sc.rBs1.ensure(n);
+    const unsigned gx = div_up(n, 64);
+    G16_LAUNCH(assemble_phase1_kernel, dim3(gx, 3), 64, 0, st, false, keys, n, mA, mB1, mB2, rs, sc.Ar.p, sc.Bs1.p, out, out_stride);
+    G16_LAUNCH(assemble_phase2_kernel, dim3(gx, 2), 64, 0, st, false, n, (const G1XYZZ*)sc.Ar.p, (const G1XYZZ*)sc.Bs1.p, rs,
+               sc.sAr.p, sc.rBs1.p);
+    G16_LAUNCH(assemble_phase3_kernel, dim3(gx, 2), 64, 0, st, false, keys, n, mK, mZ, (const G1XYZZ*)sc.Ar.p,
+               (const G1XYZZ*)sc.sAr.p, (const G1XYZZ*)sc.rBs1.p, rs, out, out_stride);
     G16_CHECK_LAUNCH();
+    return 3;
 }
 
 }  // namespace g16

@@ -1,0 +1,33 @@
+// Hot translation unit: the batched R1CS solver (solver.cuh) with the Montgomery product inlined, so that the four
+// independent coefficient products of an unrolled term group overlap.
+#include "solver.cuh"
+
+namespace g16 {
+
+size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, uint32_t batch, Fr* W, size_t w_stride, Fr* A,
+                     Fr* B, Fr* C, uint32_t* status, cudaStream_t st) {
+    const uint32_t groups = div_up(batch, 32);
+    size_t launches = 0;
+    for (uint32_t lev = 0; lev < sp.nlevels; lev++) {
+        uint32_t lo = h_level_off[lev], hi = h_level_off[lev + 1];
+        if (hi == lo) continue;
+        dim3 grid(div_up(hi - lo, SOLVER_WARPS), groups);
+        G16_LAUNCH(solver_level_kernel, grid, dim3(32, SOLVER_WARPS), 0, st, false, sp, lo, hi, batch, W, w_stride, A, B, C,
+                   status);
+        launches++;
+    }
+    G16_CHECK_LAUNCH();
+    return launches;
+}
+int launch_solver_init(const SolverProgram& sp, uint32_t n_instr, uint32_t n_coeffs, Fr* ucoef_inv, cudaStream_t st) {
+    DevBuf<uint32_t> flag(1);
+    G16_LAUNCH(solver_check_coeffs_kernel, 1, 1, 0, st, false, sp.coeffs, n_coeffs, flag.p);
+    G16_LAUNCH(solver_ucoef_kernel, div_up(n_instr, 128), 128, 0, st, false, sp, n_instr, ucoef_inv);
+    G16_CHECK_LAUNCH();
+    uint32_t hf = 0;
+    flag.download(&hf, 1, st);
+    G16_CUDA(cudaStreamSynchronize(st));
+    return (int)hf;
+}
+
+}  // namespace g16

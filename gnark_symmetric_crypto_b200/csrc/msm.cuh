@@ -54,14 +54,17 @@ FD int recode_digit(const Recoded& r, int w, int c, int& carry) {
 }
 
 // One thread per (row, point). pass 0: histogram ; pass 1: scatter into the sorted entry array.
-// scalars: row-major, row r at scalars + r*row_stride ; map (optional): scalar of point i is scalars[map[i]].
-static __global__ void msm_digits_kernel(MsmShape sh, const Fr* __restrict__ scalars, size_t row_stride,
+// scalar of (row r, point i) = scalars[r*row_stride + e*elem_stride], e = map ? map[i] : i. Consecutive threads walk the
+// unit-stride dimension (points for row-major h vectors, rows for the wire-major witness array).
+static __global__ void msm_digits_kernel(MsmShape sh, const Fr* __restrict__ scalars, size_t row_stride, size_t elem_stride,
                                   const uint32_t* __restrict__ map, int is_mont, int pass, uint32_t* __restrict__ counts,
                                   uint2* __restrict__ entries) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)sh.n * sh.rows) return;
-    uint32_t row = (uint32_t)(gid / sh.n), i = (uint32_t)(gid % sh.n);
-    size_t sidx = (size_t)row * row_stride + (map ? map[i] : i);
+    uint32_t row, i;
+    if (elem_stride == 1) { row = (uint32_t)(gid / sh.n); i = (uint32_t)(gid % sh.n); }
+    else { row = (uint32_t)(gid % sh.rows); i = (uint32_t)(gid / sh.rows); }
+    size_t sidx = (size_t)row * row_stride + (size_t)(map ? map[i] : i) * elem_stride;
     Fr raw = scalars[sidx];
     if (raw.is_zero()) return;
     Recoded r = recode_load(scalars, sidx, is_mont);
@@ -175,11 +178,10 @@ FD typename C::A load_point(const typename C::A* __restrict__ bases, uint32_t re
 
 // Thread t owns sorted entries [t*L, (t+1)*L). *total_entries is read from device memory (no host sync).
 template <class C>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 msm_accumulate_kernel(const typename C::A* __restrict__ bases, const uint2* __restrict__ entries,
                       const uint32_t* __restrict__ total_entries, int L, typename C::X* __restrict__ bucket_sums,
-                      typename C::X* __restrict__ head, uint32_t* __restrict__ head_key,
-                      typename C::X* __restrict__ tail, uint32_t* __restrict__ tail_key) {
+                      typename C::X* __restrict__ part_val, uint32_t* __restrict__ part_key) {
     typedef typename C::X X;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t M = *total_entries;
@@ -192,7 +194,7 @@ msm_accumulate_kernel(const typename C::A* __restrict__ bases, const uint2* __re
     for (size_t j = start; j < end; j++) {
         uint2 e = entries[j];
         if (e.x != cur) {
-            if (first) { head[t] = acc; head_key[t] = cur; first = false; }
+            if (first) { part_val[2 * t] = acc; part_key[2 * t] = cur; first = false; }
             else bucket_sums[cur] = acc;
             acc = X::inf();
             cur = e.x;
@@ -201,39 +203,90 @@ msm_accumulate_kernel(const typename C::A* __restrict__ bases, const uint2* __re
         acc.madd(p, (e.y & 1u) != 0);
     }
     if (first) {
-        head[t] = acc; head_key[t] = cur;
-        tail_key[t] = MSM_INVALID;
+        part_val[2 * t] = acc; part_key[2 * t] = cur;
+        part_key[2 * t + 1] = MSM_INVALID;
     } else {
-        tail[t] = acc; tail_key[t] = cur;
+        part_val[2 * t + 1] = acc; part_key[2 * t + 1] = cur;
     }
 }
 
-// boundary sequence: head[0], tail[0], head[1], tail[1], ... (non-decreasing keys, tails may be INVALID).
-// The first entry of every key run sums the run and writes the bucket.
+// Partial sums of buckets that straddle chunk edges form a sequence with non-decreasing keys (holes = MSM_INVALID):
+// level 0 = (head, tail) of every accumulate chunk. Each merge level lets a thread reduce MSM_MERGE_C consecutive
+// entries: runs strictly inside its slice are complete buckets and are written out, the first and the last run go to the
+// next level. The sequence shrinks by MSM_MERGE_C/2 per level, so even a bucket that holds every point of a row (the
+// {0,+-1} wire vectors of the ChaCha circuit) is summed by a log-depth tree instead of one serial chain.
+static const int MSM_MERGE_C = 8;
+FD size_t msm_level_len(size_t M, int L, int level) {   // entries of the sequence at `level` (0 = accumulate output)
+    size_t n = 2 * ((M + L - 1) / L);
+    for (int l = 0; l < level; l++) n = 2 * ((n + MSM_MERGE_C - 1) / MSM_MERGE_C);
+    return n;
+}
 template <class C>
 __global__ void __launch_bounds__(128)
-msm_merge_kernel(const uint32_t* __restrict__ total_entries, int L, const typename C::X* __restrict__ head,
-                 const uint32_t* __restrict__ head_key, const typename C::X* __restrict__ tail,
-                 const uint32_t* __restrict__ tail_key, typename C::X* __restrict__ bucket_sums) {
+msm_merge_level_kernel(const uint32_t* __restrict__ total_entries, int L, int level_in,
+                       const uint32_t* __restrict__ in_key, const typename C::X* __restrict__ in_val,
+                       uint32_t* __restrict__ out_key, typename C::X* __restrict__ out_val,
+                       typename C::X* __restrict__ bucket_sums) {
+    typedef typename C::X X;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n_in = msm_level_len(*total_entries, L, level_in);
+    size_t start = t * MSM_MERGE_C;
+    if (start >= n_in) return;
+    size_t end = start + MSM_MERGE_C < n_in ? start + MSM_MERGE_C : n_in;
+    uint32_t cur = MSM_INVALID;
+    X acc = X::inf();
+    bool first = true;
+    for (size_t j = start; j < end; j++) {
+        uint32_t k = in_key[j];
+        if (k == MSM_INVALID) continue;
+        if (cur == MSM_INVALID) {
+            cur = k;
+            acc = in_val[j];
+            continue;
+        }
+        if (k != cur) {
+            if (first) { out_val[2 * t] = acc; out_key[2 * t] = cur; first = false; }
+            else bucket_sums[cur] = acc;
+            acc = in_val[j];
+            cur = k;
+        } else {
+            acc.add(in_val[j]);
+        }
+    }
+    if (cur == MSM_INVALID) {
+        out_key[2 * t] = MSM_INVALID;
+        out_key[2 * t + 1] = MSM_INVALID;
+    } else if (first) {
+        out_val[2 * t] = acc; out_key[2 * t] = cur;
+        out_key[2 * t + 1] = MSM_INVALID;
+    } else {
+        out_val[2 * t + 1] = acc; out_key[2 * t + 1] = cur;
+    }
+}
+// last level (short): the first valid entry of every key run sums the run and writes the bucket
+template <class C>
+__global__ void __launch_bounds__(128)
+msm_merge_final_kernel(const uint32_t* __restrict__ total_entries, int L, int level_in,
+                       const uint32_t* __restrict__ in_key, const typename C::X* __restrict__ in_val,
+                       typename C::X* __restrict__ bucket_sums) {
     typedef typename C::X X;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t M = *total_entries;
-    size_t T = (M + L - 1) / L;
-    if (i >= 2 * T) return;
-    uint32_t key = (i & 1) ? tail_key[i >> 1] : head_key[i >> 1];
+    size_t n = msm_level_len(*total_entries, L, level_in);
+    if (i >= n) return;
+    uint32_t key = in_key[i];
     if (key == MSM_INVALID) return;
-    if (i > 0) {
-        size_t pi = i - 1;
-        uint32_t pk = (pi & 1) ? tail_key[pi >> 1] : head_key[pi >> 1];
-        if (pk == MSM_INVALID) { pi--; pk = head_key[pi >> 1]; }   // an INVALID tail always follows a valid head
-        if (pk == key) return;                                     // not the leader of this run
+    for (size_t p = i; p > 0; p--) {
+        uint32_t pk = in_key[p - 1];
+        if (pk == MSM_INVALID) continue;
+        if (pk == key) return;   // not the leader of this run
+        break;
     }
-    X acc = (i & 1) ? tail[i >> 1] : head[i >> 1];
-    for (size_t j = i + 1; j < 2 * T; j++) {
-        uint32_t k = (j & 1) ? tail_key[j >> 1] : head_key[j >> 1];
+    X acc = in_val[i];
+    for (size_t j = i + 1; j < n; j++) {
+        uint32_t k = in_key[j];
         if (k == MSM_INVALID) continue;
         if (k != key) break;
-        acc.add((j & 1) ? tail[j >> 1] : head[j >> 1]);
+        acc.add(in_val[j]);
     }
     bucket_sums[key] = acc;
 }
@@ -242,10 +295,10 @@ msm_merge_kernel(const uint32_t* __restrict__ total_entries, int L, const typena
 // Node = (R, V): R = sum of the B_k below it, V = sum (k - base)*B_k. Leaves are the buckets (weight 1..g inside a
 // level-1 node), upper levels use 0-based child weights:  V = sum_i V_i + span_child * sum_i i*R_i.
 // Segment = one (row, window) bucket set of `n_in` items; thread = one output node.
-template <class C>
+template <class C, int LEVEL1>
 __global__ void __launch_bounds__(128)
 msm_tree_kernel(const typename C::X* __restrict__ in_R, const typename C::X* __restrict__ in_V, uint32_t n_in,
-                uint32_t n_out, uint32_t segs, int level, int log_span_child, typename C::X* __restrict__ out_R,
+                uint32_t n_out, uint32_t segs, int log_span_child, typename C::X* __restrict__ out_R,
                 typename C::X* __restrict__ out_V) {
     typedef typename C::X X;
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -254,8 +307,8 @@ msm_tree_kernel(const typename C::X* __restrict__ in_R, const typename C::X* __r
     const X* R = in_R + (size_t)seg * n_in;
     uint32_t lo = node * MSM_TREE_G;
     uint32_t hi = lo + MSM_TREE_G < n_in ? lo + MSM_TREE_G : n_in;   // children [lo, hi)
-    X run = X::inf(), tot = X::inf(), vsum = X::inf();
-    if (level == 1) {
+    X run = X::inf(), tot = X::inf();
+    if (LEVEL1) {
         // weights 1..g: tot accumulates run after every add
         for (uint32_t k = hi; k > lo; k--) {
             run.add(R[k - 1]);
@@ -269,9 +322,8 @@ msm_tree_kernel(const typename C::X* __restrict__ in_R, const typename C::X* __r
             tot.add(run);
         }
         run.add(R[lo]);
-        for (uint32_t k = lo; k < hi; k++) vsum.add(V[k]);
         for (int d = 0; d < log_span_child; d++) tot = tot.dbl();
-        tot.add(vsum);
+        for (uint32_t k = lo; k < hi; k++) tot.add(V[k]);
     }
     out_R[gid] = run;
     out_V[gid] = tot;
@@ -319,7 +371,7 @@ __global__ void msm_precompute_kernel(const typename C::A* __restrict__ pts, uin
 // Runs the whole pipeline on `stream`; result XYZZ per row is left in ws.result (device). No host synchronisation.
 template <class C>
 void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases, const Fr* scalars, size_t row_stride,
-             const uint32_t* map, int is_mont, cudaStream_t stream, StageTimer* tm, int chunk_len) {
+             size_t elem_stride, const uint32_t* map, int is_mont, cudaStream_t stream, StageTimer* tm, int chunk_len) {
     typedef typename C::X X;
     const size_t nbuckets = (size_t)sh.rows * sh.buckets_per_row();
     const size_t max_entries = (size_t)sh.rows * sh.n * sh.nwin;
@@ -340,38 +392,54 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     ws.total.ensure(1);
     ws.entries.ensure(max_entries);
     ws.buckets.ensure(nbuckets);
-    ws.head.ensure(max_chunks);
-    ws.tail.ensure(max_chunks);
-    ws.head_key.ensure(max_chunks);
-    ws.tail_key.ensure(max_chunks);
+    const size_t n_l0 = 2 * max_chunks;                                              // level-0 partial sequence
+    const size_t n_l1 = 2 * ((n_l0 + MSM_MERGE_C - 1) / MSM_MERGE_C);
+    ws.part_val[0].ensure(n_l0);
+    ws.part_key[0].ensure(n_l0);
+    ws.part_val[1].ensure(n_l1);
+    ws.part_key[1].ensure(n_l1);
     ws.result.ensure(sh.rows);
 
     if (tm) tm->mark(ST_MSM_SORT, stream);
     G16_CUDA(cudaMemsetAsync(ws.counts.p, 0, nbuckets * sizeof(uint32_t), stream));
     G16_CUDA(cudaMemsetAsync(ws.buckets.p, 0, nbuckets * sizeof(X), stream));
     const size_t nthreads = (size_t)sh.n * sh.rows;
-    G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, map, is_mont, 0,
+    G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, elem_stride, map, is_mont, 0,
                ws.counts.p, ws.entries.p);
     G16_LAUNCH(scan_tile_sums, (unsigned)ntiles, SCAN_T, 0, stream, true, ws.counts.p, nbuckets, ws.tile_sums.p);
     G16_LAUNCH(scan_of_sums, 1, SCAN_T, 0, stream, true, ws.tile_sums.p, ntiles, ws.total.p);
     G16_LAUNCH(scan_tiles, (unsigned)ntiles, SCAN_T, 0, stream, true, ws.counts.p, nbuckets, ws.tile_sums.p, ws.counts.p);
-    G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, map, is_mont, 1,
+    G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, elem_stride, map, is_mont, 1,
                ws.counts.p, ws.entries.p);
     G16_CHECK_LAUNCH();
     if (tm) tm->mark(ST_MSM_ACC, stream);
     {
         auto k = msm_accumulate_kernel<C>;
         G16_LAUNCH(k, div_up(max_chunks, 128), 128, 0, stream, false, bases, ws.entries.p, ws.total.p, L, ws.buckets.p,
-                   ws.head.p, ws.head_key.p, ws.tail.p, ws.tail_key.p);
+                   ws.part_val[0].p, ws.part_key[0].p);
     }
     if (tm) tm->mark(ST_MSM_REDUCE, stream);
+    ws.launches += 6;
     {
-        auto k = msm_merge_kernel<C>;
-        G16_LAUNCH(k, div_up(2 * max_chunks, 128), 128, 0, stream, false, ws.total.p, L, ws.head.p, ws.head_key.p,
-                   ws.tail.p, ws.tail_key.p, ws.buckets.p);
+        // merge tree over the partial sequence; grids are sized for the upper bound, threads past the live length exit
+        size_t n_up = n_l0;
+        int level = 0, pp = 0;
+        while (n_up > 64) {
+            size_t slices = (n_up + MSM_MERGE_C - 1) / MSM_MERGE_C;
+            auto k = msm_merge_level_kernel<C>;
+            G16_LAUNCH(k, div_up(slices, 128), 128, 0, stream, false, ws.total.p, L, level, ws.part_key[pp].p,
+                       ws.part_val[pp].p, ws.part_key[pp ^ 1].p, ws.part_val[pp ^ 1].p, ws.buckets.p);
+            n_up = 2 * slices;
+            level++;
+            pp ^= 1;
+            ws.launches++;
+        }
+        auto k = msm_merge_final_kernel<C>;
+        G16_LAUNCH(k, div_up(n_up, 128), 128, 0, stream, false, ws.total.p, L, level, ws.part_key[pp].p, ws.part_val[pp].p,
+                   ws.buckets.p);
+        ws.launches++;
     }
     G16_CHECK_LAUNCH();
-    ws.launches += 7;
     if (ws.entry_log.n < ws.log_n + 1) {   // grow the log (rare; keeps old values)
         DevBuf<uint32_t> bigger((ws.log_n + 1) * 2 + 64);
         if (ws.log_n) G16_CUDA(cudaMemcpyAsync(bigger.p, ws.entry_log.p, ws.log_n * 4, cudaMemcpyDeviceToDevice, stream));
@@ -390,9 +458,15 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
         uint32_t n_out = (n_in + MSM_TREE_G - 1) / MSM_TREE_G;
         ws.lvlR[pp].ensure((size_t)segs * n_out);
         ws.lvlV[pp].ensure((size_t)segs * n_out);
-        auto k = msm_tree_kernel<C>;
-        G16_LAUNCH(k, div_up((size_t)segs * n_out, 128), 128, 0, stream, false, inR, inV, n_in, n_out, segs, level,
-                   log_span, ws.lvlR[pp].p, ws.lvlV[pp].p);
+        if (level == 1) {
+            auto k = msm_tree_kernel<C, 1>;
+            G16_LAUNCH(k, div_up((size_t)segs * n_out, 128), 128, 0, stream, false, inR, inV, n_in, n_out, segs, log_span,
+                       ws.lvlR[pp].p, ws.lvlV[pp].p);
+        } else {
+            auto k = msm_tree_kernel<C, 0>;
+            G16_LAUNCH(k, div_up((size_t)segs * n_out, 128), 128, 0, stream, false, inR, inV, n_in, n_out, segs, log_span,
+                       ws.lvlR[pp].p, ws.lvlV[pp].p);
+        }
         ws.launches++;
         inR = ws.lvlR[pp].p;
         inV = ws.lvlV[pp].p;

@@ -5,17 +5,6 @@
 
 namespace g16 {
 
-struct G1 {
-    typedef Fp F;
-    typedef Affine<Fp> A;
-    typedef XYZZ<Fp> X;
-};
-struct G2 {
-    typedef Fp2 F;
-    typedef Affine<Fp2> A;
-    typedef XYZZ<Fp2> X;
-};
-
 struct MsmShape {
     int c;          // window bits
     int nwin;       // ceil(254 / c)
@@ -33,9 +22,9 @@ static const int MSM_TREE_G = 32;   // arity of the bucket-reduction tree
 template <class C>
 struct MsmWorkspace {
     typedef typename C::X X;
-    DevBuf<uint32_t> counts, tile_sums, total, head_key, tail_key;
+    DevBuf<uint32_t> counts, tile_sums, total, part_key[2];
     DevBuf<uint2> entries;
-    DevBuf<X> buckets, head, tail, lvlR[2], lvlV[2], result;
+    DevBuf<X> buckets, part_val[2], lvlR[2], lvlV[2], result;
     size_t launches = 0;
     // number of sorted entries (= mixed additions of the accumulate kernel) of every run since log_reset()
     DevBuf<uint32_t> entry_log;
@@ -75,9 +64,9 @@ static inline MsmShape msm_make_shape(uint32_t n, uint32_t rows, int c, int prec
 
 
 void msm_run_g1(MsmWorkspace<G1>& ws, const MsmShape& sh, const G1Affine* bases, const Fr* scalars, size_t row_stride,
-                const uint32_t* map, int is_mont, cudaStream_t stream, StageTimer* tm = nullptr, int chunk_len = 0);
+                size_t elem_stride, const uint32_t* map, int is_mont, cudaStream_t stream, StageTimer* tm = nullptr, int chunk_len = 0);
 void msm_run_g2(MsmWorkspace<G2>& ws, const MsmShape& sh, const G2Affine* bases, const Fr* scalars, size_t row_stride,
-                const uint32_t* map, int is_mont, cudaStream_t stream, StageTimer* tm = nullptr, int chunk_len = 0);
+                size_t elem_stride, const uint32_t* map, int is_mont, cudaStream_t stream, StageTimer* tm = nullptr, int chunk_len = 0);
 // table[w*n + i] = 2^(c*w) * P_i
 void msm_precompute_g1(const G1Affine* pts, uint32_t n, int nwin, int c, G1Affine* table, cudaStream_t stream);
 void msm_precompute_g2(const G2Affine* pts, uint32_t n, int nwin, int c, G2Affine* table, cudaStream_t stream);

@@ -48,5 +48,7 @@ void ntt_fill_pattern(Fr* out, size_t total, cudaStream_t stream);
 void ntt_count_mismatches(const Fr* a, const Fr* b, size_t total, uint32_t* d_count, cudaStream_t stream);
 // integer-multiply microbenchmarks (ops per second)
 void imad_peak_measure(double* imad_per_s, double* imad_wide_per_s, double* modmul_per_s);
+// carry-chain wide MAD rate (IMAD.WIDE.U32.X) measured by the last imad_peak_measure call
+double imad_chain_rate();
 
 }  // namespace g16

@@ -9,7 +9,7 @@ static const uint32_t SOLVE_WIRE_NONE = 0xFFFFFFFFu;
 static const uint32_t WIRE_CONST = 0xFFFFFFFFu;
 static const uint32_t HINT_NBITS = 4115454955u, HINT_COUNT = 2138922168u, HINT_RANDOMIZE = 1774611027u,
                       HINT_BSB22 = 4156202267u;
-static const int SOLVER_WARPS = 16;
+static const int SOLVER_WARPS = 4;
 
 struct InsMeta {
     uint32_t cd_start;     // index into calldata
@@ -37,6 +37,11 @@ struct SolverProgram {
 struct AssemblyKeys {
     G1Affine alpha, beta, delta;
     G2Affine beta2, delta2;
+    const G1Affine* delta_tab;    // device: j*16^i*delta,  64 x 15 entries
+    const G2Affine* delta2_tab;   // device: j*16^i*delta2
+};
+struct AssemblyScratch {
+    DevBuf<G1XYZZ> Ar, Bs1, sAr, rBs1;
 };
 
 // all pointers are device pointers
@@ -46,12 +51,18 @@ void launch_scalars_from_be(const uint8_t* in, uint32_t n, Fr* out, cudaStream_t
 void launch_chacha_witness(const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters, const uint8_t* inputs,
                            uint32_t n, Fr* W, size_t w_stride, uint8_t* ct_out, cudaStream_t st);
 void launch_witness_copy(const Fr* witness, uint32_t n_witness, uint32_t batch, Fr* W, size_t w_stride, cudaStream_t st);
-void launch_solver(const SolverProgram& sp, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C, uint32_t* status,
-                   cudaStream_t st);
+// h_level_off: host copy of the level offsets (nlevels + 1). Returns the number of kernel launches.
+size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, uint32_t batch, Fr* W, size_t w_stride, Fr* A,
+                     Fr* B, Fr* C, uint32_t* status, cudaStream_t st);
 // fills ucoef_inv (n_instr entries) and returns whether coefficient ids 0..4 are 0,1,2,-1,-2 (synchronises the stream)
 int launch_solver_init(const SolverProgram& sp, uint32_t n_instr, uint32_t n_coeffs, Fr* ucoef_inv, cudaStream_t st);
-void launch_assemble(const AssemblyKeys& keys, uint32_t n, const G1XYZZ* mA, const G1XYZZ* mB1, const G1XYZZ* mK,
-                     const G1XYZZ* mZ, const G2XYZZ* mB2, const Fr* rs, uint8_t* out, size_t out_stride, cudaStream_t st);
+// builds the 64 x 15 fixed-base tables of delta / delta2 (device buffers owned by the caller)
+void launch_fixed_base_tables(const AssemblyKeys& keys, G1Affine* tab1, G2Affine* tab2, cudaStream_t st);
+// three launches; returns the launch count
+size_t launch_assemble(const AssemblyKeys& keys, AssemblyScratch& sc, uint32_t n, const G1XYZZ* mA, const G1XYZZ* mB1,
+                       const G1XYZZ* mK, const G1XYZZ* mZ, const G2XYZZ* mB2, const Fr* rs, uint8_t* out, size_t out_stride,
+                       cudaStream_t st);
+void launch_wires_to_rows(const Fr* W, size_t w_stride, uint32_t batch, uint32_t nb_wires, Fr* out, cudaStream_t st);
 // stage-level test entry points
 void launch_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, cudaStream_t st);
 void launch_group_op(int group, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, cudaStream_t st);

@@ -1,7 +1,7 @@
 // Device kernels of the Groth16 prove path other than MSM / NTT:
 //   * point decompression of the proving key            (replaces gnark marshal.go:311-348 ProvingKey.readFrom — a19)
 //   * ChaCha20 witness assignment                        (replaces provers.go:79-142 + utils/bytes.go:11-47 — a3..a6)
-//   * batched R1CS solver                                (replaces gnark constraint/bn254 solver.go:177-586 — a9, a10)
+//   (the batched R1CS solver lives in solver.cuh / k_solver.cu)
 //   * proof assembly + serialisation                     (replaces prove.go:174-295 tail, marshal.go:32-59 — a16, a18)
 #pragma once
 #include "prover_api.hpp"
@@ -163,12 +163,14 @@ __global__ void chacha_witness_kernel(const uint8_t* __restrict__ keys, const ui
         for (int b = 0; b < 4; b++) ct[4 * k + b] = in[4 * k + b] ^ (uint8_t)(ks >> (8 * b));
     }
     for (int k = 0; k < 64; k++) ct_out[(size_t)i * 64 + k] = ct[k];
-    Fr* w = W + (size_t)i * w_stride;
+    // wire-major layout: wire k of request i lives at W[k * w_stride + i] (coalesced across the requests of a warp)
+    Fr* w = W + i;
     const Fr one = Fr::one(), zero = Fr::zero();
-    uint32_t pos = 0;
-    w[pos++] = one;
+    size_t pos = 0;
+    w[pos] = one;
+    pos += w_stride;
     auto put_word = [&](uint32_t word) {
-        for (int b = 0; b < 32; b++) w[pos++] = ((word >> b) & 1u) ? one : zero;
+        for (int b = 0; b < 32; b++) { w[pos] = ((word >> b) & 1u) ? one : zero; pos += w_stride; }
     };
     put_word(counters[i]);
     for (int k = 0; k < 3; k++) put_word(le32(nonce + 4 * k));
@@ -177,195 +179,127 @@ __global__ void chacha_witness_kernel(const uint8_t* __restrict__ keys, const ui
     for (int k = 0; k < 8; k++) put_word(le32(key + 4 * k));
 }
 
-// generic: W[i][0] = 1, W[i][1..1+nw) = witness[i][..]
+// generic: wire 0 = 1, wires 1..nw = witness[i][..]   (wire-major output, see above)
 __global__ void witness_copy_kernel(const Fr* __restrict__ witness, uint32_t n_witness, uint32_t batch, Fr* __restrict__ W,
                                     size_t w_stride) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)batch * (n_witness + 1)) return;
     uint32_t i = (uint32_t)(gid / (n_witness + 1)), k = (uint32_t)(gid % (n_witness + 1));
-    W[(size_t)i * w_stride + k] = k == 0 ? Fr::one() : witness[(size_t)i * n_witness + (k - 1)];
+    W[(size_t)k * w_stride + i] = k == 0 ? Fr::one() : witness[(size_t)i * n_witness + (k - 1)];
 }
 
-// ------------------------------------------------------------------------------------------------ R1CS solver
-FD void acc_term(Fr& acc, const SolverProgram& sp, const Fr* W, uint32_t cid, uint32_t wid) {
-    if (wid == WIRE_CONST) { acc = acc + sp.coeffs[cid]; return; }
-    Fr w = W[wid];
-    if (sp.fast_coeffs && cid <= 4) {   // uniform across the warp: all lanes run the same instruction
-        switch (cid) {
-            case 0: break;
-            case 1: acc = acc + w; break;
-            case 2: acc = acc + w.dbl(); break;
-            case 3: acc = acc - w; break;
-            default: acc = acc - w.dbl(); break;
-        }
-    } else {
-        acc = acc + sp.coeffs[cid] * w;
-    }
-}
-FD Fr eval_le(const SolverProgram& sp, const Fr* W, uint32_t& pos) {
-    uint32_t nt = sp.calldata[pos++];
-    Fr acc = Fr::zero();
-    for (uint32_t t = 0; t < nt; t++) {
-        uint32_t cid = sp.calldata[pos], wid = sp.calldata[pos + 1];
-        pos += 2;
-        acc_term(acc, sp, W, cid, wid);
-    }
-    return acc;
-}
-
-// executes instruction `ins` for one instance. status bits: 1 unsatisfied constraint, 2 division by zero, 4 unsupported
-__device__ __forceinline__ void solve_instruction(const SolverProgram& sp, uint32_t ins, Fr* W, Fr* A, Fr* B, Fr* C, uint32_t* status) {
-    const InsMeta m = sp.meta[ins];
-    uint32_t kind = m.kind & 0xFF;
-    uint32_t base = m.cd_start;
-    if (kind == 0) {
-        uint32_t n[3] = {sp.calldata[base + 1], sp.calldata[base + 2], sp.calldata[base + 3]};
-        uint32_t pos = base + 4;
-        uint32_t uside = (m.kind >> 8) & 0xFF;
-        Fr sum[3], ucoef = Fr::zero();
-        for (int side = 0; side < 3; side++) {
-            Fr acc = Fr::zero();
-            for (uint32_t t = 0; t < n[side]; t++) {
-                uint32_t cid = sp.calldata[pos], wid = sp.calldata[pos + 1];
-                pos += 2;
-                if (wid == m.solve_wire && (uint32_t)side == uside) ucoef = ucoef + sp.coeffs[cid];
-                else acc_term(acc, sp, W, cid, wid);
-            }
-            sum[side] = acc;
-        }
-        if (m.solve_wire != SOLVE_WIRE_NONE) {
-            Fr w;
-            Fr kinv = sp.ucoef_inv[ins];
-            if (uside == 2) {
-                w = (sum[0] * sum[1] - sum[2]) * kinv;
-            } else {
-                const Fr& other = sum[1 - uside];
-                if (other.is_zero()) { atomicOr(status, 2u); w = Fr::zero(); }
-                else w = (sum[2] * other.inv() - sum[uside]) * kinv;
-            }
-            W[m.solve_wire] = w;
-            sum[uside] = sum[uside] + ucoef * w;
-        } else if (sum[0] * sum[1] != sum[2]) {
-            atomicOr(status, 1u);
-        }
-        A[m.cons_off] = sum[0];
-        B[m.cons_off] = sum[1];
-        C[m.cons_off] = sum[2];
-    } else if (kind == 1) {
-        uint32_t hid = sp.calldata[base + 1], nin = sp.calldata[base + 2];
-        uint32_t pos = base + 3;
-        if (hid == HINT_NBITS && nin == 1) {
-            Fr v = eval_le(sp, W, pos).from_mont();
-            uint32_t o0 = sp.calldata[pos], o1 = sp.calldata[pos + 1];
-            const Fr one = Fr::one(), zero = Fr::zero();
-            for (uint32_t k = 0; k < o1 - o0; k++) {
-                uint32_t bit = k < 256 ? (v.l[k >> 5] >> (k & 31)) & 1u : 0u;
-                W[o0 + k] = bit ? one : zero;
-            }
-        } else {
-            atomicOr(status, 4u);
-        }
-    } else {
-        // lookup: [len, nbEntries, nIn, inputs...] -> W[wire_off + k] = table[value(input k)]
-        uint32_t nent = sp.calldata[base + 1], nin = sp.calldata[base + 2];
-        uint32_t pos = base + 3;
-        const Fr* tab = sp.lookup_tabs + (size_t)m.lookup_tab * 256;
-        for (uint32_t k = 0; k < nin; k++) {
-            Fr v = eval_le(sp, W, pos).from_mont();
-            uint32_t hi = v.l[1] | v.l[2] | v.l[3] | v.l[4] | v.l[5] | v.l[6] | v.l[7];
-            if (hi || v.l[0] >= nent || v.l[0] >= 256) { atomicOr(status, 1u); W[m.wire_off + k] = Fr::zero(); }
-            else W[m.wire_off + k] = tab[v.l[0]];
-        }
-    }
-}
-
-// CTA = 32 instances (threadIdx.x) x SOLVER_WARPS instruction slots (threadIdx.y). All lanes of a warp execute the same
-// instruction on different instances (no divergence); the warps of a CTA share out the instructions of a level and
-// meet at a barrier between levels (the level schedule comes from the r1cs file).
-__global__ void __launch_bounds__(32 * SOLVER_WARPS)
-solver_kernel(SolverProgram sp, uint32_t batch, Fr* __restrict__ W, size_t w_stride, Fr* __restrict__ A, Fr* __restrict__ B,
-              Fr* __restrict__ C, uint32_t* __restrict__ status) {
-    uint32_t inst = blockIdx.x * 32 + threadIdx.x;
-    bool active = inst < batch;
-    Fr* w = W + (size_t)inst * w_stride;
-    Fr* a = A + (size_t)inst * sp.n_dom;
-    Fr* b = B + (size_t)inst * sp.n_dom;
-    Fr* c = C + (size_t)inst * sp.n_dom;
-    for (uint32_t lev = 0; lev < sp.nlevels; lev++) {
-        uint32_t lo = sp.level_off[lev], hi = sp.level_off[lev + 1];
-        if (active)
-            for (uint32_t k = lo + threadIdx.y; k < hi; k += blockDim.y) solve_instruction(sp, sp.level_instr[k], w, a, b, c, status);
-        __syncthreads();
-    }
-}
-
-// per instruction: 1 / (sum of coefficients of the wire it solves)   (init-time)
-__global__ void solver_ucoef_kernel(SolverProgram sp, uint32_t n_instr, Fr* __restrict__ out) {
-    uint32_t ins = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ins >= n_instr) return;
-    const InsMeta m = sp.meta[ins];
-    Fr r = Fr::one();
-    if ((m.kind & 0xFF) == 0 && m.solve_wire != SOLVE_WIRE_NONE) {
-        uint32_t base = m.cd_start;
-        uint32_t n[3] = {sp.calldata[base + 1], sp.calldata[base + 2], sp.calldata[base + 3]};
-        uint32_t pos = base + 4, uside = (m.kind >> 8) & 0xFF;
-        Fr uc = Fr::zero();
-        for (int side = 0; side < 3; side++)
-            for (uint32_t t = 0; t < n[side]; t++) {
-                uint32_t cid = sp.calldata[pos], wid = sp.calldata[pos + 1];
-                pos += 2;
-                if (wid == m.solve_wire && (uint32_t)side == uside) uc = uc + sp.coeffs[cid];
-            }
-        r = uc.inv();
-    }
-    out[ins] = r;
-}
-// flag = 1 iff coefficient ids 0..4 are 0, 1, 2, -1, -2
-__global__ void solver_check_coeffs_kernel(const Fr* __restrict__ coeffs, uint32_t ncoef, uint32_t* __restrict__ flag) {
-    if (threadIdx.x || blockIdx.x) return;
-    Fr one = Fr::one(), two = one + one;
-    bool ok = ncoef >= 5 && coeffs[0].is_zero() && coeffs[1] == one && coeffs[2] == two && coeffs[3] == one.neg() &&
-              coeffs[4] == two.neg();
-    *flag = ok ? 1u : 0u;
+// wire-major W -> one row of nb_wires values per witness (test / gnark-shaped output only)
+__global__ void wires_to_rows_kernel(const Fr* __restrict__ W, size_t w_stride, uint32_t batch, uint32_t nb_wires,
+                                     Fr* __restrict__ out) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)batch * nb_wires) return;
+    uint32_t i = (uint32_t)(gid % batch), k = (uint32_t)(gid / batch);
+    out[(size_t)i * nb_wires + k] = W[(size_t)k * w_stride + i];
 }
 
 // ------------------------------------------------------------------------------------------------ proof assembly
-// One thread per proof:
+// 
 //   Ar  = msmA + alpha + r*delta          Bs1 = msmB1 + beta + s*delta        Bs = msmB2 + beta2 + s*delta2
 //   Krs = msmK + msmZ + s*Ar + r*Bs1 - (r*s)*delta
-// rs: canonical limbs, r at [2i], s at [2i+1]. out: Proof.WriteTo bytes without commitments (164 B, Appendix C).
-__global__ void __launch_bounds__(64)
-assemble_kernel(AssemblyKeys keys, uint32_t n, const G1XYZZ* __restrict__ mA, const G1XYZZ* __restrict__ mB1,
-                const G1XYZZ* __restrict__ mK, const G1XYZZ* __restrict__ mZ, const G2XYZZ* __restrict__ mB2,
-                const Fr* __restrict__ rs, uint8_t* __restrict__ out, size_t out_stride) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fr r = rs[2 * i], s = rs[2 * i + 1];
-    Fr rsm = (r.to_mont() * s.to_mont()).from_mont();
-    G1XYZZ d1 = G1XYZZ::from_affine(keys.delta);
-    G1XYZZ Ar = mA[i];
-    Ar.madd(keys.alpha, false);
-    Ar.add(scalar_mul(d1, r));
-    G1XYZZ Bs1 = mB1[i];
-    Bs1.madd(keys.beta, false);
-    Bs1.add(scalar_mul(d1, s));
-    G1XYZZ Krs = mK[i];
-    Krs.add(mZ[i]);
-    Krs.add(scalar_mul(Ar, s));
-    Krs.add(scalar_mul(Bs1, r));
-    Krs.add(scalar_mul(d1, rsm).neg());
-    uint8_t* o = out + (size_t)i * out_stride;
-    g1_compress(Ar.to_affine(), o);
-    g1_compress(Krs.to_affine(), o + 96);
-    G2XYZZ Bs = mB2[i];
-    Bs.madd(keys.beta2, false);
-    Bs.add(scalar_mul(G2XYZZ::from_affine(keys.delta2), s));
-    g2_compress(Bs.to_affine(), o + 32);
-    o[128] = 0; o[129] = 0; o[130] = 0; o[131] = 0;
-    o[132] = 0x40;
-    for (int k = 133; k < 164; k++) o[k] = 0;
+// delta, delta2 are fixed: their multiples j*16^i*delta (i < 64, 1 <= j <= 15) are tabulated at init, so k*delta is at most
+// 64 mixed additions and no doubling. The work of one proof is spread over three launches x several roles (blockIdx.y)
+// so that the longest serial chain is one 254-bit double-and-add instead of six.
+
+static const int FB_WINDOWS = 64, FB_ENTRIES = 15;
+
+// tab[i*15 + (j-1)] = j * 16^i * base  (affine). One thread per window.
+template <class C>
+__global__ void fixed_base_table_kernel(typename C::A base, typename C::A* __restrict__ tab) {
+    typedef typename C::X X;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= FB_WINDOWS) return;
+    X b = X::from_affine(base);
+    for (int d = 0; d < 4 * i; d++) b = b.dbl();
+    X acc = b;
+    tab[i * FB_ENTRIES] = acc.to_affine();
+    for (int j = 1; j < FB_ENTRIES; j++) {
+        acc.add(b);
+        tab[i * FB_ENTRIES + j] = acc.to_affine();
+    }
+}
+template <class C>
+FD typename C::X fixed_base_mul(const typename C::A* __restrict__ tab, Scalar256 k) {
+    typename C::X acc = C::X::inf();
+#pragma unroll
+    for (int wi = 0; wi < 8; wi++) {
+        uint32_t word = k.w[wi];
+#pragma unroll 1
+        for (int j = 0; j < 8; j++) {
+            uint32_t nib = (word >> (4 * j)) & 15u;
+            if (nib) acc.madd(tab[(wi * 8 + j) * FB_ENTRIES + (nib - 1)], false);
+        }
+    }
+    return acc;
+}
+FD Scalar256 scalar_of(const Fr& k) {
+    Scalar256 s;
+    for (int i = 0; i < 8; i++) s.w[i] = k.l[i];
+    return s;
 }
 
-// gathers wire indices: out[j] = index of the j-th wire with flag[w] == 0   (host builds these; kept for reference)
+// rs: canonical limbs, r at [2i], s at [2i+1].
+// phase 1, role (blockIdx.y) 0: Ar ; 1: Bs1 ; 2: Bs (compressed straight into the proof)
+__global__ void __launch_bounds__(64)
+assemble_phase1_kernel(AssemblyKeys keys, uint32_t n, const G1XYZZ* __restrict__ mA, const G1XYZZ* __restrict__ mB1,
+                       const G2XYZZ* __restrict__ mB2, const Fr* __restrict__ rs, G1XYZZ* __restrict__ Ar_out,
+                       G1XYZZ* __restrict__ Bs1_out, uint8_t* __restrict__ out, size_t out_stride) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t role = blockIdx.y;
+    if (role == 0) {
+        G1XYZZ v = fixed_base_mul<G1>(keys.delta_tab, scalar_of(rs[2 * i]));
+        v.add(mA[i]);
+        v.madd(keys.alpha, false);
+        Ar_out[i] = v;
+    } else if (role == 1) {
+        G1XYZZ v = fixed_base_mul<G1>(keys.delta_tab, scalar_of(rs[2 * i + 1]));
+        v.add(mB1[i]);
+        v.madd(keys.beta, false);
+        Bs1_out[i] = v;
+    } else {
+        G2XYZZ v = fixed_base_mul<G2>(keys.delta2_tab, scalar_of(rs[2 * i + 1]));
+        v.add(mB2[i]);
+        v.madd(keys.beta2, false);
+        g2_compress(v.to_affine(), out + (size_t)i * out_stride + 32);
+    }
+}
+// phase 2, role 0: s*Ar ; 1: r*Bs1
+__global__ void __launch_bounds__(64)
+assemble_phase2_kernel(uint32_t n, const G1XYZZ* __restrict__ Ar, const G1XYZZ* __restrict__ Bs1, const Fr* __restrict__ rs,
+                       G1XYZZ* __restrict__ sAr, G1XYZZ* __restrict__ rBs1) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (blockIdx.y == 0) sAr[i] = scalar_mul(Ar[i], scalar_of(rs[2 * i + 1]));
+    else rBs1[i] = scalar_mul(Bs1[i], scalar_of(rs[2 * i]));
+}
+// phase 3: Krs, compression of Ar and Krs, trailer of Proof.WriteTo without commitments (Appendix C)
+__global__ void __launch_bounds__(64)
+assemble_phase3_kernel(AssemblyKeys keys, uint32_t n, const G1XYZZ* __restrict__ mK, const G1XYZZ* __restrict__ mZ,
+                       const G1XYZZ* __restrict__ Ar, const G1XYZZ* __restrict__ sAr, const G1XYZZ* __restrict__ rBs1,
+                       const Fr* __restrict__ rs, uint8_t* __restrict__ out, size_t out_stride) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t* o = out + (size_t)i * out_stride;
+    if (blockIdx.y == 1) {
+        g1_compress(Ar[i].to_affine(), o);
+        o[128] = 0; o[129] = 0; o[130] = 0; o[131] = 0;
+        o[132] = 0x40;
+        for (int k = 133; k < 164; k++) o[k] = 0;
+        return;
+    }
+    Fr r = rs[2 * i], s = rs[2 * i + 1];
+    Fr rsm = (r.to_mont() * s.to_mont()).from_mont();
+    G1XYZZ Krs = fixed_base_mul<G1>(keys.delta_tab, scalar_of(rsm)).neg();
+    Krs.add(mK[i]);
+    Krs.add(mZ[i]);
+    Krs.add(sAr[i]);
+    Krs.add(rBs1[i]);
+    g1_compress(Krs.to_affine(), o + 96);
+}
 
 }  // namespace g16

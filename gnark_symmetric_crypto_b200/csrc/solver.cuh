@@ -1,0 +1,190 @@
+// Batched R1CS witness solver: many independent witnesses of the SAME constraint system solved in lock-step.
+// Replaces: gnark v0.11.0 constraint/bn254 (*system).Solve system.go:72-99, (*solver).run
+// solver.go:439-509, processInstruction :390-418, solveR1C :540-586, solveWithHint :205-229, accumulateInto :177-195,
+// blueprints blueprint_r1cs.go:36-59 / blueprint_hint.go:10-30 / blueprint_logderivlookup.go:30-69 and the hint
+// std/math/bits.nBits — reached from libraries/prover/impl/provers.go:148,216 (groth16.Prove -> r1cs.Solve).
+//
+// Mapping: warp = one instruction x 32 witnesses (lanes). All lanes run the same instruction, so control flow is uniform;
+// the calldata of the instruction is read once per warp through the uniform path. Linear expressions are walked four
+// terms at a time: the four wire loads and the four coefficient products are independent, only the final additions
+// chain (the 33-bit adder recompositions of the ChaCha circuit have 130-term expressions, and they bound the level time).
+#pragma once
+#include "prover_api.hpp"
+
+namespace g16 {
+
+static const int SOLVER_UNROLL = 4;
+
+// acc += sum of `nt` terms starting at calldata[pos]; terms on `skip_wire` (the wire this instruction solves) are not
+// evaluated: their coefficients are summed into ucoef instead.
+// W points at this witness' column of the wire-major array: wire k is W[k * ws].
+__device__ __forceinline__ void acc_terms(const SolverProgram& sp, const Fr* __restrict__ W, size_t ws, uint32_t pos,
+                                          uint32_t nt, uint32_t skip_wire, Fr& acc, Fr& ucoef) {
+    for (uint32_t t0 = 0; t0 < nt; t0 += SOLVER_UNROLL) {
+        uint32_t cid[SOLVER_UNROLL], wid[SOLVER_UNROLL];
+        Fr w[SOLVER_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SOLVER_UNROLL; u++) {
+            bool ok = t0 + u < nt;
+            cid[u] = ok ? sp.calldata[pos + 2 * (t0 + u)] : 0u;
+            wid[u] = ok ? sp.calldata[pos + 2 * (t0 + u) + 1] : SOLVE_WIRE_NONE - 1;   // sentinel: "no term"
+        }
+#pragma unroll
+        for (int u = 0; u < SOLVER_UNROLL; u++) {
+            bool is_wire = wid[u] < sp.n_wires && wid[u] != skip_wire;
+            w[u] = is_wire ? W[(size_t)wid[u] * ws] : Fr::zero();
+        }
+        // products first (independent), sums afterwards
+        Fr term[SOLVER_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SOLVER_UNROLL; u++) {
+            term[u] = Fr::zero();
+            if (wid[u] == SOLVE_WIRE_NONE - 1) continue;                       // past the end
+            if (wid[u] == WIRE_CONST) { term[u] = sp.coeffs[cid[u]]; continue; }   // constant term
+            if (wid[u] == skip_wire) continue;
+            if (sp.fast_coeffs && cid[u] <= 4) {   // warp-uniform: 0, +1, +2, -1, -2
+                switch (cid[u]) {
+                    case 0: break;
+                    case 1: term[u] = w[u]; break;
+                    case 2: term[u] = w[u].dbl(); break;
+                    case 3: term[u] = w[u].neg(); break;
+                    default: term[u] = w[u].dbl().neg(); break;
+                }
+            } else {
+                // bit-valued wires dominate these circuits (every ChaCha wire is 0, 1 or -1): c*0 and c*1 need no product.
+                // Exact for any value: the Montgomery product runs whenever a lane holds something else.
+                const Fr c = sp.coeffs[cid[u]];
+                if (w[u].is_zero()) term[u] = Fr::zero();
+                else if (w[u] == Fr::one()) term[u] = c;
+                else term[u] = c * w[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SOLVER_UNROLL; u++) {
+            if (wid[u] == skip_wire && skip_wire != SOLVE_WIRE_NONE) ucoef = ucoef + sp.coeffs[cid[u]];
+            else acc = acc + term[u];
+        }
+    }
+}
+__device__ __forceinline__ Fr eval_le(const SolverProgram& sp, const Fr* __restrict__ W, size_t ws, uint32_t& pos) {
+    uint32_t nt = sp.calldata[pos++];
+    Fr acc = Fr::zero(), dummy = Fr::zero();
+    acc_terms(sp, W, ws, pos, nt, SOLVE_WIRE_NONE, acc, dummy);
+    pos += 2 * nt;
+    return acc;
+}
+
+// executes instruction `ins` for one witness. status bits: 1 unsatisfied constraint, 2 division by zero, 4 unsupported
+__device__ __forceinline__ void solve_instruction(const SolverProgram& sp, uint32_t ins, Fr* __restrict__ W, size_t ws,
+                                                  Fr* __restrict__ A, Fr* __restrict__ B, Fr* __restrict__ C,
+                                                  uint32_t* status) {
+    const InsMeta m = sp.meta[ins];
+    uint32_t kind = m.kind & 0xFF;
+    uint32_t base = m.cd_start;
+    if (kind == 0) {
+        uint32_t nL = sp.calldata[base + 1], nR = sp.calldata[base + 2], nO = sp.calldata[base + 3];
+        uint32_t uside = (m.kind >> 8) & 0xFF;
+        bool solves = m.solve_wire != SOLVE_WIRE_NONE;
+        Fr sL = Fr::zero(), sR = Fr::zero(), sO = Fr::zero(), ucoef = Fr::zero(), unused = Fr::zero();
+        uint32_t pos = base + 4;
+        acc_terms(sp, W, ws, pos, nL, (solves && uside == 0) ? m.solve_wire : SOLVE_WIRE_NONE, sL, (uside == 0) ? ucoef : unused);
+        pos += 2 * nL;
+        acc_terms(sp, W, ws, pos, nR, (solves && uside == 1) ? m.solve_wire : SOLVE_WIRE_NONE, sR, (uside == 1) ? ucoef : unused);
+        pos += 2 * nR;
+        acc_terms(sp, W, ws, pos, nO, (solves && uside == 2) ? m.solve_wire : SOLVE_WIRE_NONE, sO, (uside == 2) ? ucoef : unused);
+        if (solves) {
+            Fr w;
+            Fr kinv = sp.ucoef_inv[ins];
+            if (uside == 2) {
+                w = (sL * sR - sO) * kinv;
+                sO = sO + ucoef * w;
+            } else if (uside == 0) {
+                if (sR.is_zero()) { atomicOr(status, 2u); w = Fr::zero(); }
+                else w = (sO * sR.inv() - sL) * kinv;
+                sL = sL + ucoef * w;
+            } else {
+                if (sL.is_zero()) { atomicOr(status, 2u); w = Fr::zero(); }
+                else w = (sO * sL.inv() - sR) * kinv;
+                sR = sR + ucoef * w;
+            }
+            W[(size_t)m.solve_wire * ws] = w;
+        } else if (sL * sR != sO) {
+            atomicOr(status, 1u);
+        }
+        A[m.cons_off] = sL;
+        B[m.cons_off] = sR;
+        C[m.cons_off] = sO;
+    } else if (kind == 1) {
+        uint32_t hid = sp.calldata[base + 1], nin = sp.calldata[base + 2];
+        uint32_t pos = base + 3;
+        if (hid == HINT_NBITS && nin == 1) {
+            Fr v = eval_le(sp, W, ws, pos).from_mont();
+            uint32_t o0 = sp.calldata[pos], o1 = sp.calldata[pos + 1];
+            const Fr one = Fr::one(), zero = Fr::zero();
+            uint32_t k = 0;
+#pragma unroll
+            for (int wi = 0; wi < 8; wi++) {   // static limb index: no local-memory array
+                uint32_t word = v.l[wi];
+                for (int b = 0; b < 32 && k < o1 - o0; b++, k++) W[(size_t)(o0 + k) * ws] = ((word >> b) & 1u) ? one : zero;
+            }
+            for (; k < o1 - o0; k++) W[(size_t)(o0 + k) * ws] = zero;
+        } else {
+            atomicOr(status, 4u);
+        }
+    } else {
+        // lookup: [len, nbEntries, nIn, inputs...] -> W[wire_off + k] = table[value(input k)]
+        uint32_t nent = sp.calldata[base + 1], nin = sp.calldata[base + 2];
+        uint32_t pos = base + 3;
+        const Fr* tab = sp.lookup_tabs + (size_t)m.lookup_tab * 256;
+        for (uint32_t k = 0; k < nin; k++) {
+            Fr v = eval_le(sp, W, ws, pos).from_mont();
+            uint32_t hi = v.l[1] | v.l[2] | v.l[3] | v.l[4] | v.l[5] | v.l[6] | v.l[7];
+            if (hi || v.l[0] >= nent || v.l[0] >= 256) { atomicOr(status, 1u); W[(size_t)(m.wire_off + k) * ws] = Fr::zero(); }
+            else W[(size_t)(m.wire_off + k) * ws] = tab[v.l[0]];
+        }
+    }
+}
+
+// One launch per level of the r1cs schedule (instructions inside a level are independent, level l
+// only reads wires of levels < l). grid.x covers the instructions of the level, grid.y the groups of 32 witnesses.
+__global__ void __launch_bounds__(32 * SOLVER_WARPS)
+solver_level_kernel(SolverProgram sp, uint32_t lo, uint32_t hi, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C,
+                    uint32_t* status) {
+    uint32_t inst = blockIdx.y * 32 + threadIdx.x;
+    uint32_t k = lo + blockIdx.x * blockDim.y + threadIdx.y;
+    if (inst >= batch || k >= hi) return;
+    solve_instruction(sp, sp.level_instr[k], W + inst, w_stride, A + (size_t)inst * sp.n_dom,
+                      B + (size_t)inst * sp.n_dom, C + (size_t)inst * sp.n_dom, status);
+}
+
+// per instruction: 1 / (sum of coefficients of the wire it solves)   (init-time)
+__global__ void solver_ucoef_kernel(SolverProgram sp, uint32_t n_instr, Fr* __restrict__ out) {
+    uint32_t ins = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ins >= n_instr) return;
+    const InsMeta m = sp.meta[ins];
+    Fr r = Fr::one();
+    if ((m.kind & 0xFF) == 0 && m.solve_wire != SOLVE_WIRE_NONE) {
+        uint32_t base = m.cd_start;
+        uint32_t n[3] = {sp.calldata[base + 1], sp.calldata[base + 2], sp.calldata[base + 3]};
+        uint32_t pos = base + 4, uside = (m.kind >> 8) & 0xFF;
+        Fr uc = Fr::zero();
+        for (int side = 0; side < 3; side++)
+            for (uint32_t t = 0; t < n[side]; t++) {
+                uint32_t cid = sp.calldata[pos], wid = sp.calldata[pos + 1];
+                pos += 2;
+                if (wid == m.solve_wire && (uint32_t)side == uside) uc = uc + sp.coeffs[cid];
+            }
+        r = uc.inv();
+    }
+    out[ins] = r;
+}
+// flag = 1 iff coefficient ids 0..4 are 0, 1, 2, -1, -2
+__global__ void solver_check_coeffs_kernel(const Fr* __restrict__ coeffs, uint32_t ncoef, uint32_t* __restrict__ flag) {
+    if (threadIdx.x || blockIdx.x) return;
+    Fr one = Fr::one(), two = one + one;
+    bool ok = ncoef >= 5 && coeffs[0].is_zero() && coeffs[1] == one && coeffs[2] == two && coeffs[3] == one.neg() &&
+              coeffs[4] == two.neg();
+    *flag = ok ? 1u : 0u;
+}
+
+}  // namespace g16

@@ -320,4 +320,6 @@ def ntt_bench(n: int, batch: int, iters: int):
 def imad_peak():
     a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
     _check(_lib.load().g16_imad_peak(C.byref(a), C.byref(b), C.byref(c)))
-    return {"imad_per_s": a.value, "imad_wide_per_s": b.value, "modmul_per_s": c.value}
+    d = C.c_double(0)
+    _check(_lib.load().g16_imad_chain_rate(C.byref(d)))
+    return {"imad_per_s": a.value, "imad_wide_per_s": b.value, "modmul_per_s": c.value, "imad_wide_carry_per_s": d.value}

@@ -126,6 +126,9 @@ int g16_prove_witness_detail(g16_ctx* ctx, const uint64_t* witness, size_t n_wit
 /* integer-multiply microbenchmark: sustained 32-bit IMAD and IMAD.WIDE rates of this GPU (ops/s), the roofline
  * denominator the MSM numbers are quoted against (not in MEASURED_PEAKS.json). */
 int g16_imad_peak(double* imad_per_s, double* imad_wide_per_s, double* modmul_per_s);
+/* rate of carry-chained wide MADs (IMAD.WIDE.U32.X, the instruction the Montgomery product is made of) measured by the
+ * last g16_imad_peak call; 0 before */
+int g16_imad_chain_rate(double* wide_carry_mads_per_s);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * (1) outer ABI: byte-compatible with the cgo exports of libraries/prover/libprove.go
