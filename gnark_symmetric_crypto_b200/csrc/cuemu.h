@@ -138,6 +138,7 @@ static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new CuEmuEvent{
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = 0);
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)((b->t - a->t) * 1e3); return 0; }
 
 #define G16_LAUNCH(kernel, grid, block, smem, stream, sync, ...) \

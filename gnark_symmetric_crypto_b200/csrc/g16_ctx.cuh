@@ -52,8 +52,11 @@ struct Ctx {
     DevBuf<uint8_t> d_keys, d_nonces, d_inputs, d_rs_be, d_ct, d_proofs;
     DevBuf<uint32_t> d_counters, d_status;
     DevBuf<Fr> d_rs, d_witness, W, Aev, Bev, Cev;
-    MsmWorkspace<G1> ws1;
-    MsmWorkspace<G2> ws2;
+    MsmWorkspace<G1> ws1;    // Z query, main stream
+    MsmWorkspace<G1> ws1b;   // A / B1 / K queries, side stream
+    MsmWorkspace<G2> ws2;    // B2 query, side stream
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevBuf<G1XYZZ> resA, resB1, resK, resZ;
     DevBuf<G2XYZZ> resB2;
     StageTimer timer;
@@ -64,6 +67,9 @@ struct Ctx {
     bool tables_ready = false;
 
     ~Ctx() {
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (stream2) cudaStreamDestroy(stream2);
         if (stream) cudaStreamDestroy(stream);
     }
     size_t proof_bytes() const { return 164; }
@@ -100,6 +106,9 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     cx->device = device;
     G16_CUDA(cudaSetDevice(device));
     G16_CUDA(cudaStreamCreate(&cx->stream));
+    G16_CUDA(cudaStreamCreate(&cx->stream2));
+    G16_CUDA(cudaEventCreate(&cx->ev_fork));
+    G16_CUDA(cudaEventCreate(&cx->ev_join));
     cudaStream_t st = cx->stream;
     cx->sub_batch = (uint32_t)env_int("G16_SUBBATCH", 256);
     if (cx->sub_batch == 0) cx->sub_batch = 1;
@@ -328,11 +337,11 @@ static void ctx_ensure_batch(Ctx& cx, size_t n) {
     cx.d_rs.ensure(2 * n);
 }
 
-static void run_query_g1(Ctx& cx, const PrecompQuery& q, const Fr* scalars, size_t row_stride, size_t elem_stride, bool use_map,
-                         uint32_t rows, G1XYZZ* out, StageTimer* tm) {
+static void run_query_g1(MsmWorkspace<G1>& ws, cudaStream_t st, const PrecompQuery& q, const Fr* scalars, size_t row_stride,
+                         size_t elem_stride, bool use_map, uint32_t rows, G1XYZZ* out, StageTimer* tm) {
     MsmShape sh = msm_make_shape(q.n, rows, q.c, 1);
-    msm_run_g1(cx.ws1, sh, q.table.p, scalars, row_stride, elem_stride, use_map ? q.map.p : nullptr, 1, cx.stream, tm);
-    G16_CUDA(cudaMemcpyAsync(out, cx.ws1.result.p, (size_t)rows * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, cx.stream));
+    msm_run_g1(ws, sh, q.table.p, scalars, row_stride, elem_stride, use_map ? q.map.p : nullptr, 1, st, tm);
+    G16_CUDA(cudaMemcpyAsync(out, ws.result.p, (size_t)rows * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
 }
 
 // returns device ms (sum over stages). Leaves proofs in d_proofs. Throws on unsatisfied witness.
@@ -343,9 +352,10 @@ static float ctx_run_batch(Ctx& cx, size_t n, bool chacha) {
     ctx_ensure_batch(cx, n);
     StageTimer& tm = cx.timer;
     tm.reset();
-    size_t l0 = cx.ws1.launches + cx.ws2.launches + cx.dom.launches;
+    size_t l0 = cx.ws1.launches + cx.ws1b.launches + cx.ws2.launches + cx.dom.launches;
     size_t own = 0;
     cx.ws1.log_reset();
+    cx.ws1b.log_reset();
     cx.ws2.log_reset();
     tm.mark(ST_SOLVE, st);
     G16_CUDA(cudaMemsetAsync(cx.d_status.p, 0, 4, st));
@@ -361,6 +371,11 @@ static float ctx_run_batch(Ctx& cx, size_t n, bool chacha) {
     // W is wire-major: wire k of proof i at W[k*n + i]
     own += 2 + launch_solver(cx.sp, cx.h_level_off.data(), (uint32_t)n, cx.W.p, n, cx.Aev.p, cx.Bev.p, cx.Cev.p,
                              cx.d_status.p, st);
+    // The witness is complete: the wire-driven queries (A, B1, K on G1, B on G2 — short, latency-bound kernels) run on
+    // a side stream and fill the SM slots that the long H / Z kernels of the main stream leave idle.
+    cudaStream_t st2 = cx.stream2;
+    G16_CUDA(cudaEventRecord(cx.ev_fork, st));
+    G16_CUDA(cudaStreamWaitEvent(st2, cx.ev_fork, 0));
     for (size_t sb = 0; sb < n; sb += cx.sub_batch) {
         uint32_t rows = (uint32_t)((n - sb) < cx.sub_batch ? (n - sb) : cx.sub_batch);
         Fr* a = cx.Aev.p + sb * cx.n_dom;
@@ -370,16 +385,18 @@ static float ctx_run_batch(Ctx& cx, size_t n, bool chacha) {
         tm.mark(ST_H, st);
         compute_h_run(cx.dom, a, b, c, cx.n_dom, rows, st);
         // h (gnark order) pairs index-for-index with G1.Z; the other queries read wire values through their maps
-        run_query_g1(cx, cx.qZ, a, cx.n_dom, 1, false, rows, cx.resZ.p + sb, &tm);
-        run_query_g1(cx, cx.qA, w, 1, n, true, rows, cx.resA.p + sb, &tm);
-        run_query_g1(cx, cx.qB, w, 1, n, true, rows, cx.resB1.p + sb, &tm);
-        run_query_g1(cx, cx.qK, w, 1, n, true, rows, cx.resK.p + sb, &tm);
+        run_query_g1(cx.ws1, st, cx.qZ, a, cx.n_dom, 1, false, rows, cx.resZ.p + sb, &tm);
+        run_query_g1(cx.ws1b, st2, cx.qA, w, 1, n, true, rows, cx.resA.p + sb, nullptr);
+        run_query_g1(cx.ws1b, st2, cx.qB, w, 1, n, true, rows, cx.resB1.p + sb, nullptr);
+        run_query_g1(cx.ws1b, st2, cx.qK, w, 1, n, true, rows, cx.resK.p + sb, nullptr);
         {
             MsmShape sh = msm_make_shape(cx.nB2, rows, cx.cB2, 1);
-            msm_run_g2(cx.ws2, sh, cx.tabB2.p, w, 1, n, cx.qB.map.p, 1, st, &tm);
-            G16_CUDA(cudaMemcpyAsync(cx.resB2.p + sb, cx.ws2.result.p, (size_t)rows * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st));
+            msm_run_g2(cx.ws2, sh, cx.tabB2.p, w, 1, n, cx.qB.map.p, 1, st2, nullptr);
+            G16_CUDA(cudaMemcpyAsync(cx.resB2.p + sb, cx.ws2.result.p, (size_t)rows * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st2));
         }
     }
+    G16_CUDA(cudaEventRecord(cx.ev_join, st2));
+    G16_CUDA(cudaStreamWaitEvent(st, cx.ev_join, 0));
     tm.mark(ST_ASSEMBLE, st);
     own += launch_assemble(cx.keys, cx.asm_scratch, (uint32_t)n, cx.resA.p, cx.resB1.p, cx.resK.p, cx.resZ.p, cx.resB2.p,
                            cx.d_rs.p, cx.d_proofs.p, cx.proof_bytes(), st);
@@ -391,11 +408,13 @@ static float ctx_run_batch(Ctx& cx, size_t n, bool chacha) {
     float total = tm.finish(per);
     for (int i = 0; i < ST_COUNT; i++) cx.stage_ms[i] = per[i];
     cx.stage_ms[6] = total;
-    cx.launches = own + (cx.ws1.launches + cx.ws2.launches + cx.dom.launches - l0);
+    cx.launches = own + (cx.ws1.launches + cx.ws1b.launches + cx.ws2.launches + cx.dom.launches - l0);
     cx.stage_ms[7] = (float)cx.launches;
-    cx.counters[0] = cx.ws1.log_sum(st);   // G1 mixed additions performed by the accumulate kernel
-    cx.counters[1] = cx.ws2.log_sum(st);   // G2 mixed additions
-    cx.counters[2] = cx.ws1.log_n;         // G1 accumulate launches
+    G16_CUDA(cudaStreamSynchronize(st2));
+    cx.counters[0] = cx.ws1.log_sum(st) + cx.ws1b.log_sum(st2);   // G1 mixed additions performed by the accumulate kernel
+    cx.counters[6] = cx.ws1.log_sum(st);                          // ... of which on the main stream (Z query)
+    cx.counters[1] = cx.ws2.log_sum(st2);   // G2 mixed additions
+    cx.counters[2] = cx.ws1.log_n + cx.ws1b.log_n;   // G1 accumulate launches
     cx.counters[3] = cx.ws2.log_n;
     cx.counters[4] = cx.launches;
     cx.counters[5] = n;
