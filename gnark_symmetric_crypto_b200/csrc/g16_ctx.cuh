@@ -63,7 +63,7 @@ struct Ctx {
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     size_t launches = 0;
     uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    uint32_t sub_batch = 256;
+    uint32_t sub_batch = 512;
     bool tables_ready = false;
 
     ~Ctx() {
@@ -110,7 +110,7 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     G16_CUDA(cudaEventCreate(&cx->ev_fork));
     G16_CUDA(cudaEventCreate(&cx->ev_join));
     cudaStream_t st = cx->stream;
-    cx->sub_batch = (uint32_t)env_int("G16_SUBBATCH", 256);
+    cx->sub_batch = (uint32_t)env_int("G16_SUBBATCH", 512);
     if (cx->sub_batch == 0) cx->sub_batch = 1;
 
     PkFile pk = parse_pk(pk_bytes, pk_len);
@@ -198,7 +198,7 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
 
     // ---- fixed-base tables (built now, or on the first prove when G16_LAZY_TABLES=1 — gnark's icicle backend also
     //      defers its device set-up to the first Prove)
-    cx->qZ.c = env_int("G16_C_Z", 16);
+    cx->qZ.c = env_int("G16_C_Z", 15);
     cx->qA.c = env_int("G16_C_A", 13);
     cx->qB.c = env_int("G16_C_B", 13);
     cx->qK.c = env_int("G16_C_K", 13);

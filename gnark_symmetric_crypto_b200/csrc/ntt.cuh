@@ -68,12 +68,16 @@ ntt_pass_kernel(Fr* __restrict__ data, size_t vec_stride, NttPass p, const Fr* _
             uint32_t gi = ntt_global_index(p, tile, e0);
             uint32_t tidx = (gi & ((1u << bit) - 1u)) << (p.k - 1 - bit);
             Fr a = sm_load(sm, tile_elems, e0), b = sm_load(sm, tile_elems, e1);
-            Fr w = tw[tidx];
-            if (p.dif) {
+            if (bit == 0) {   // span-1 stage: every twiddle is w^0 = 1 (uniform across the grid): no product
+                sm_store(sm, tile_elems, e0, a + b);
+                sm_store(sm, tile_elems, e1, a - b);
+            } else if (p.dif) {
+                Fr w = tw[tidx];
                 Fr d = a - b;
                 sm_store(sm, tile_elems, e0, a + b);
                 sm_store(sm, tile_elems, e1, d * w);
             } else {
+                Fr w = tw[tidx];
                 Fr t = b * w;
                 sm_store(sm, tile_elems, e0, a + t);
                 sm_store(sm, tile_elems, e1, a - t);

@@ -197,7 +197,7 @@ class Groth16Context:
     def counters(self) -> dict:
         c = np.zeros(8, dtype=np.uint64)
         _check(self._L.g16_last_counters(self._h, _p64(c)))
-        names = ["g1_madds", "g2_madds", "g1_acc_launches", "g2_acc_launches", "launches", "proofs"]
+        names = ["g1_madds", "g2_madds", "g1_acc_launches", "g2_acc_launches", "launches", "proofs", "g1_madds_main_stream"]
         return {k: int(v) for k, v in zip(names, c)}
 
     # ---- stage-level

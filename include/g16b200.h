@@ -77,7 +77,8 @@ int g16_chacha_batch_fetch(g16_ctx* ctx, uint8_t* proofs_out, uint8_t* ct_out);
  * 2 MSM scalar prep + sort, 3 MSM bucket accumulation, 4 MSM reductions, 5 proof assembly, 6 total, 7 kernel launches */
 int g16_last_stage_ms(const g16_ctx* ctx, float ms[8]);
 /* work counters of the last run: 0 G1 mixed additions done by the bucket-accumulation kernel (= sorted entries),
- * 1 G2 mixed additions, 2 G1 accumulate launches, 3 G2 accumulate launches, 4 kernel launches, 5 proofs */
+ * 1 G2 mixed additions, 2 G1 accumulate launches, 3 G2 accumulate launches, 4 kernel launches, 5 proofs,
+ * 6 the part of [0] done on the main stream (Z query; the stage timers bracket the main stream only) */
 int g16_last_counters(const g16_ctx* ctx, uint64_t out[8]);
 
 /* ------------------------------------------------------------------------------------------------------------------
