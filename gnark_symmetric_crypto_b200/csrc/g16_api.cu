@@ -85,15 +85,30 @@ static void random_scalars_be(uint8_t* out, size_t count) {
     }
 }
 
+// rs: per proof r | s (2 x 32 B big-endian) followed, for circuits with a hints.Randomize wire (AES), by the 32-byte
+// commitment mask: 64 or 96 bytes per proof. NULL = draw everything from the OS CSPRNG.
+static size_t rs_bytes_per_proof(const Ctx& c) { return c.has_randomize ? 96 : 64; }
+static void stage_masks(Ctx& c, size_t n, const uint8_t* masks_be) {
+    c.d_mask_be.upload(masks_be, 32 * n, c.stream);
+    c.d_mask.ensure(n);
+    fr_be_to_mont(c.d_mask_be.p, (uint32_t)n, c.d_mask.p, c.stream);
+}
 static void stage_rs(Ctx& c, size_t n, const uint8_t* rs) {
-    std::vector<uint8_t> tmp;
+    const size_t per = rs_bytes_per_proof(c);
+    std::vector<uint8_t> tmp, rs64(64 * n), masks;
     if (!rs) {
-        tmp.resize(64 * n);
-        random_scalars_be(tmp.data(), 2 * n);
+        tmp.resize(per * n);
+        random_scalars_be(tmp.data(), per / 32 * n);
         rs = tmp.data();
     }
-    c.d_rs_be.upload(rs, 64 * n, c.stream);
-    G16_CUDA(cudaStreamSynchronize(c.stream));   // tmp must outlive the copy
+    for (size_t i = 0; i < n; i++) memcpy(&rs64[64 * i], rs + per * i, 64);
+    c.d_rs_be.upload(rs64.data(), 64 * n, c.stream);
+    if (c.has_randomize) {
+        masks.resize(32 * n);
+        for (size_t i = 0; i < n; i++) memcpy(&masks[32 * i], rs + per * i + 64, 32);
+        stage_masks(c, n, masks.data());
+    }
+    G16_CUDA(cudaStreamSynchronize(c.stream));   // host temporaries must outlive the copies
 }
 
 static void prove_witness_impl(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, const uint8_t* rs,
@@ -107,8 +122,8 @@ static void prove_witness_impl(g16_ctx* ctx, const uint64_t* witness, size_t n_w
     c.d_witness.upload((const Fr*)witness, n_witness, c.stream);
     stage_rs(c, 1, rs);
     c.staged = 1;
-    c.staged_is_chacha = false;
-    ctx_run_batch(c, 1, false);
+    c.staged_kind = 0;
+    ctx_run_batch(c, 1, 0);
     c.d_proofs.download(proof_out, c.proof_bytes(), c.stream);
     if (proof_len) *proof_len = c.proof_bytes();
     if (msm_g1_out) {
@@ -191,7 +206,7 @@ int g16_chacha_batch_stage(g16_ctx* ctx, size_t n, const uint8_t* keys, const ui
         c.d_inputs.upload(inputs, 64 * n, c.stream);
         stage_rs(c, n, rs);
         c.staged = n;
-        c.staged_is_chacha = true;
+        c.staged_kind = 1;
     });
 }
 int g16_chacha_batch_run(g16_ctx* ctx, float* ms) {
@@ -199,9 +214,9 @@ int g16_chacha_batch_run(g16_ctx* ctx, float* ms) {
         REQUIRE(ctx, "NULL argument");
         std::lock_guard<std::mutex> lk(ctx->mu);
         Ctx& c = *ctx->cx;
-        REQUIRE(c.staged > 0 && c.staged_is_chacha, "no staged ChaCha batch");
+        REQUIRE(c.staged > 0 && c.staged_kind != 0, "no staged request batch");
         G16_CUDA(cudaSetDevice(c.device));
-        float t = ctx_run_batch(c, c.staged, true);
+        float t = ctx_run_batch(c, c.staged, c.staged_kind);
         if (ms) *ms = t;
     });
 }
@@ -220,6 +235,34 @@ int g16_chacha_batch_fetch(g16_ctx* ctx, uint8_t* proofs_out, uint8_t* ct_out) {
 int g16_prove_chacha_batch(g16_ctx* ctx, size_t n, const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters,
                            const uint8_t* inputs, const uint8_t* rs, uint8_t* proofs_out, uint8_t* ct_out) {
     int rc = g16_chacha_batch_stage(ctx, n, keys, nonces, counters, inputs, rs);
+    if (rc) return rc;
+    rc = g16_chacha_batch_run(ctx, nullptr);
+    if (rc) return rc;
+    return g16_chacha_batch_fetch(ctx, proofs_out, ct_out);
+}
+int g16_aes_batch_stage(g16_ctx* ctx, size_t n, const uint8_t* keys, size_t key_len, const uint8_t* nonces,
+                        const uint32_t* counters, const uint8_t* inputs, const uint8_t* rsm) {
+    return guarded([&] {
+        REQUIRE(ctx && keys && nonces && counters && inputs, "NULL argument");
+        REQUIRE(n > 0 && n <= (1u << 20), "batch size out of range");
+        REQUIRE(key_len == 16 || key_len == 32, "key length must be 16 or 32");
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        Ctx& c = *ctx->cx;
+        REQUIRE(c.n_public == 142 && c.n_secret == key_len, "context does not hold the AES circuit for this key length");
+        G16_CUDA(cudaSetDevice(c.device));
+        c.d_keys.upload(keys, key_len * n, c.stream);
+        c.d_nonces.upload(nonces, 12 * n, c.stream);
+        c.d_counters.upload(counters, n, c.stream);
+        c.d_inputs.upload(inputs, 64 * n, c.stream);
+        stage_rs(c, n, rsm);
+        c.staged = n;
+        c.staged_kind = 2;
+        c.staged_key_len = (uint32_t)key_len;
+    });
+}
+int g16_prove_aes_batch(g16_ctx* ctx, size_t n, const uint8_t* keys, size_t key_len, const uint8_t* nonces,
+                        const uint32_t* counters, const uint8_t* inputs, const uint8_t* rsm, uint8_t* proofs_out, uint8_t* ct_out) {
+    int rc = g16_aes_batch_stage(ctx, n, keys, key_len, nonces, counters, inputs, rsm);
     if (rc) return rc;
     rc = g16_chacha_batch_run(ctx, nullptr);
     if (rc) return rc;
@@ -248,24 +291,27 @@ int g16_prove_witness_detail(g16_ctx* ctx, const uint64_t* witness, size_t n_wit
     return guarded([&] { prove_witness_impl(ctx, witness, n_witness, rs, proof_out, proof_len, msm_g1_out, msm_g2_out, h_out); });
 }
 
-int g16_solve(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, size_t batch, uint64_t* W, uint64_t* A, uint64_t* B,
-              uint64_t* C) {
+int g16_solve_ex(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, size_t batch, const uint8_t* masks_be, uint64_t* W,
+                 uint64_t* A, uint64_t* B, uint64_t* C) {
     return guarded([&] {
         REQUIRE(ctx && witness && batch > 0, "bad argument");
         std::lock_guard<std::mutex> lk(ctx->mu);
         Ctx& c = *ctx->cx;
         REQUIRE(n_witness == (size_t)c.n_public - 1 + c.n_secret, "witness length must be nbPublic-1+nbSecret");
         if (!c.solver_supported) throw std::runtime_error("unsupported circuit: " + c.solver_unsupported_reason);
+        REQUIRE(masks_be || !c.has_randomize, "this circuit has a hints.Randomize wire: masks are required");
         G16_CUDA(cudaSetDevice(c.device));
         cudaStream_t st = c.stream;
+        if (c.n_commit) ctx_build_tables(c);
         ctx_ensure_batch(c, batch);
         c.d_witness.upload((const Fr*)witness, n_witness * batch, st);
+        if (c.has_randomize) stage_masks(c, batch, masks_be);
         G16_CUDA(cudaMemsetAsync(c.d_status.p, 0, 4, st));
         G16_CUDA(cudaMemsetAsync(c.Aev.p, 0, batch * c.n_dom * sizeof(Fr), st));
         G16_CUDA(cudaMemsetAsync(c.Bev.p, 0, batch * c.n_dom * sizeof(Fr), st));
         G16_CUDA(cudaMemsetAsync(c.Cev.p, 0, batch * c.n_dom * sizeof(Fr), st));
         launch_witness_copy(c.d_witness.p, (uint32_t)n_witness, (uint32_t)batch, c.W.p, batch, st);
-        launch_solver(c.sp, c.h_level_off.data(), (uint32_t)batch, c.W.p, batch, c.Aev.p, c.Bev.p, c.Cev.p, c.d_status.p, st);
+        ctx_solve(c, batch, nullptr);
         uint32_t status = 0;
         c.d_status.download(&status, 1, st);
         DevBuf<Fr> rows;
@@ -283,6 +329,10 @@ int g16_solve(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, size_t ba
         if (status & 4u) throw std::runtime_error("solver: unsupported hint");
         if (status & 3u) throw std::domain_error("witness does not satisfy the constraint system");
     });
+}
+int g16_solve(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, size_t batch, uint64_t* W, uint64_t* A, uint64_t* B,
+              uint64_t* C) {
+    return g16_solve_ex(ctx, witness, n_witness, batch, nullptr, W, A, B, C);
 }
 
 int g16_compute_h(g16_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c_in, uint64_t* h_out) {

@@ -28,7 +28,7 @@ struct Ctx {
     uint32_t nA = 0, nB = 0, nZ = 0, nK = 0, nB2 = 0;
     uint32_t nb_wires = 0, n_public = 0, n_secret = 0, n_constraints = 0, n_instr = 0, nlevels = 0, n_commit = 0;
     // key material
-    DevBuf<G1Affine> A, B, Z, K;
+    DevBuf<G1Affine> A, B, Z, K, ped_basis, ped_basis_sigma;
     DevBuf<G2Affine> B2;
     PrecompQuery qA, qB, qZ, qK;
     DevBuf<G2Affine> tabB2;
@@ -46,9 +46,18 @@ struct Ctx {
     std::vector<uint32_t> h_level_off;
     bool solver_supported = true;
     std::string solver_unsupported_reason;
+    // BSB22 commitment (AES circuits): at most one commitment is supported
+    PrecompQuery qPed, qPedSigma;       // Pedersen Basis / BasisExpSigma over the private-committed wires
+    uint32_t commit_wire = 0, bsb_level = 0, bsb_ins = 0xFFFFFFFFu;
+    bool has_randomize = false;
+    DevBuf<G1XYZZ> resCommit, resPok;
+    DevBuf<G1Affine> commit_aff;
+    DevBuf<Fr> d_mask;
+    DevBuf<uint8_t> d_mask_be;
     // batch state
     size_t staged = 0;
-    bool staged_is_chacha = false;
+    int staged_kind = 0;   // 0 generic witness, 1 chacha requests, 2 aes requests
+    uint32_t staged_key_len = 0;
     DevBuf<uint8_t> d_keys, d_nonces, d_inputs, d_rs_be, d_ct, d_proofs;
     DevBuf<uint32_t> d_counters, d_status;
     DevBuf<Fr> d_rs, d_witness, W, Aev, Bev, Cev;
@@ -72,7 +81,7 @@ struct Ctx {
         if (stream2) cudaStreamDestroy(stream2);
         if (stream) cudaStreamDestroy(stream);
     }
-    size_t proof_bytes() const { return 164; }
+    size_t proof_bytes() const { return n_commit ? 196 : 164; }
 };
 
 static inline int env_int(const char* name, int dflt) {
@@ -86,6 +95,17 @@ static void ctx_build_tables(Ctx& cx) {
     if (cx.tables_ready) return;
     cudaStream_t st = cx.stream;
     auto nwin = [](int c) { return (254 + c - 1) / c; };
+    if (cx.qA.table.n) {   // rebuild after the Pedersen bases arrived: only those are missing
+        if (cx.qPed.n && !cx.qPed.table.n) {
+            cx.qPed.table.alloc((size_t)cx.qPed.n * nwin(cx.qPed.c));
+            cx.qPedSigma.table.alloc((size_t)cx.qPedSigma.n * nwin(cx.qPedSigma.c));
+            msm_precompute_g1(cx.ped_basis.p, cx.qPed.n, nwin(cx.qPed.c), cx.qPed.c, cx.qPed.table.p, st);
+            msm_precompute_g1(cx.ped_basis_sigma.p, cx.qPedSigma.n, nwin(cx.qPedSigma.c), cx.qPedSigma.c, cx.qPedSigma.table.p, st);
+            G16_CUDA(cudaStreamSynchronize(st));
+        }
+        cx.tables_ready = true;
+        return;
+    }
     cx.qA.table.alloc((size_t)cx.nA * nwin(cx.qA.c));
     cx.qB.table.alloc((size_t)cx.nB * nwin(cx.qB.c));
     cx.qZ.table.alloc((size_t)cx.nZ * nwin(cx.qZ.c));
@@ -96,6 +116,12 @@ static void ctx_build_tables(Ctx& cx) {
     msm_precompute_g1(cx.Z.p, cx.nZ, nwin(cx.qZ.c), cx.qZ.c, cx.qZ.table.p, st);
     msm_precompute_g1(cx.K.p, cx.nK, nwin(cx.qK.c), cx.qK.c, cx.qK.table.p, st);
     msm_precompute_g2(cx.B2.p, cx.nB2, nwin(cx.cB2), cx.cB2, cx.tabB2.p, st);
+    if (cx.qPed.n) {
+        cx.qPed.table.alloc((size_t)cx.qPed.n * nwin(cx.qPed.c));
+        cx.qPedSigma.table.alloc((size_t)cx.qPedSigma.n * nwin(cx.qPedSigma.c));
+        msm_precompute_g1(cx.ped_basis.p, cx.qPed.n, nwin(cx.qPed.c), cx.qPed.c, cx.qPed.table.p, st);
+        msm_precompute_g1(cx.ped_basis_sigma.p, cx.qPedSigma.n, nwin(cx.qPedSigma.c), cx.qPedSigma.c, cx.qPedSigma.table.p, st);
+    }
     G16_CUDA(cudaStreamSynchronize(st));
     cx.tables_ready = true;
 }
@@ -264,9 +290,14 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
                 uint32_t o0 = cd[pos], o1 = cd[pos + 1];
                 if (o1 < o0 || o1 > cx->nb_wires) throw ParseError("r1cs: hint output range out of bounds");
                 for (uint32_t w = o0; w < o1; w++) solved[w] = 1;
-                if (hid != HINT_NBITS) {
+                if (hid == HINT_RANDOMIZE) cx->has_randomize = true;
+                else if (hid == HINT_BSB22) {
+                    if (cx->bsb_ins != 0xFFFFFFFFu) { cx->solver_supported = false; cx->solver_unsupported_reason = "more than one BSB22 commitment"; }
+                    cx->bsb_ins = (uint32_t)i;
+                    cx->commit_wire = o0;
+                } else if (hid != HINT_NBITS && hid != HINT_COUNT) {
                     cx->solver_supported = false;
-                    cx->solver_unsupported_reason = "hint id " + std::to_string(hid) + " (commitment / log-derivative hints) is not implemented on the device yet";
+                    cx->solver_unsupported_reason = "hint id " + std::to_string(hid) + " is not implemented on the device";
                 }
             } else {
                 uint32_t nin = cd[s0 + 2];
@@ -279,6 +310,7 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
         for (auto& lv : cs.levels) {
             for (uint32_t id : lv) {
                 if (id >= cs.n_instr()) throw ParseError("r1cs: level references unknown instruction");
+                if (id == cx->bsb_ins) cx->bsb_level = (uint32_t)(lvl_off.size() - 1);
                 lvl_instr.push_back(id);
             }
             lvl_off.push_back((uint32_t)lvl_instr.size());
@@ -312,12 +344,34 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
         sp.level_off = cx->d_level_off.p; sp.coeffs = cx->d_coeffs.p; sp.ucoef_inv = cx->d_ucoef_inv.p;
         sp.lookup_tabs = cx->d_lookup_tabs.p; sp.nlevels = cx->nlevels; sp.n_wires = cx->nb_wires;
         sp.n_dom = (uint32_t)cx->n_dom; sp.fast_coeffs = 0;
+        sp.randomize = nullptr; sp.bsb_ins = cx->bsb_ins;
         G16_CUDA(cudaStreamSynchronize(st));   // host vectors above must outlive the copies
         sp.fast_coeffs = launch_solver_init(sp, (uint32_t)cs.n_instr(), (uint32_t)(cs.coeffs.size() / 4), cx->d_ucoef_inv.p, st);
     }
-    if (cx->n_commit) {
+    if (cx->n_commit > 1 || (cx->n_commit == 1 && (cx->bsb_ins == 0xFFFFFFFFu || pk.ped.size() != 1))) {
         cx->solver_supported = false;
-        if (cx->solver_unsupported_reason.empty()) cx->solver_unsupported_reason = "circuits with BSB22 commitments are not supported yet";
+        if (cx->solver_unsupported_reason.empty()) cx->solver_unsupported_reason = "only circuits with at most one BSB22 commitment are supported";
+    }
+    if (cx->n_commit == 1 && cx->solver_supported) {
+        const CommitmentInfo& ci = cs.commitments[0];
+        if (ci.commitment_index != cx->commit_wire) throw ParseError("r1cs: commitment wire does not match the Bsb22 hint output");
+        if (ci.private_committed.size() != pk.ped[0].n_basis) throw ParseError("pk: Pedersen basis size does not match the committed wires");
+        if (!ci.public_and_commitment_committed.empty()) throw ParseError("public-committed wires are not supported");
+        DevBuf<G1Affine> basis, basis_sigma;
+        decompress1(pk.ped[0].basis, pk.ped[0].n_basis, basis);
+        decompress1(pk.ped[0].basis_sigma, pk.ped[0].n_sigma, basis_sigma);
+        uint32_t herr2 = 0;
+        err.download(&herr2, 1, st);
+        G16_CUDA(cudaStreamSynchronize(st));
+        if (herr2) throw ParseError("pk: Pedersen basis decompression failed");
+        cx->ped_basis = std::move(basis);
+        cx->ped_basis_sigma = std::move(basis_sigma);
+        cx->qPed.n = cx->qPedSigma.n = pk.ped[0].n_basis;
+        cx->qPed.c = cx->qPedSigma.c = env_int("G16_C_PED", 16);
+        cx->qPed.map.upload(ci.private_committed.data(), ci.private_committed.size(), st);
+        cx->qPedSigma.map.upload(ci.private_committed.data(), ci.private_committed.size(), st);
+        G16_CUDA(cudaStreamSynchronize(st));
+        if (cx->tables_ready) { cx->tables_ready = false; ctx_build_tables(*cx); }
     }
     cx->d_status.alloc(1);
     return cx;
@@ -335,6 +389,7 @@ static void ctx_ensure_batch(Ctx& cx, size_t n) {
     cx.d_proofs.ensure(n * cx.proof_bytes());
     cx.d_ct.ensure(n * 64);
     cx.d_rs.ensure(2 * n);
+    if (cx.n_commit) { cx.resCommit.ensure(n); cx.resPok.ensure(n); cx.commit_aff.ensure(n); }
 }
 
 static void run_query_g1(MsmWorkspace<G1>& ws, cudaStream_t st, const PrecompQuery& q, const Fr* scalars, size_t row_stride,
@@ -344,8 +399,31 @@ static void run_query_g1(MsmWorkspace<G1>& ws, cudaStream_t st, const PrecompQue
     G16_CUDA(cudaMemcpyAsync(out, ws.result.p, (size_t)rows * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
 }
 
+// Solves all witnesses of the batch (W wire-major, stride n). With a BSB22 commitment the level schedule is cut after
+// the level that holds the commitment hint: Pedersen MSM over the committed wires -> hash to field -> challenge wire
+// (gnark prove.go:84-108 overrides the hint the same way), then the remaining levels run.
+static size_t ctx_solve(Ctx& cx, size_t n, StageTimer* tm) {
+    cudaStream_t st = cx.stream;
+    SolverProgram sp = cx.sp;
+    sp.randomize = cx.has_randomize ? cx.d_mask.p : nullptr;
+    if (!cx.n_commit)
+        return launch_solver(sp, cx.h_level_off.data(), 0, cx.nlevels, (uint32_t)n, cx.W.p, n, cx.Aev.p, cx.Bev.p, cx.Cev.p,
+                             cx.d_status.p, st);
+    size_t launches = launch_solver(sp, cx.h_level_off.data(), 0, cx.bsb_level + 1, (uint32_t)n, cx.W.p, n, cx.Aev.p, cx.Bev.p,
+                                    cx.Cev.p, cx.d_status.p, st);
+    for (size_t sb = 0; sb < n; sb += cx.sub_batch) {
+        uint32_t rows = (uint32_t)((n - sb) < cx.sub_batch ? (n - sb) : cx.sub_batch);
+        run_query_g1(cx.ws1b, st, cx.qPed, cx.W.p + sb, 1, n, true, rows, cx.resCommit.p + sb, nullptr);
+    }
+    launch_bsb22_challenge(cx.resCommit.p, (uint32_t)n, cx.W.p, n, cx.commit_wire, cx.commit_aff.p, st);
+    launches += 1 + launch_solver(sp, cx.h_level_off.data(), cx.bsb_level + 1, cx.nlevels, (uint32_t)n, cx.W.p, n, cx.Aev.p,
+                                  cx.Bev.p, cx.Cev.p, cx.d_status.p, st);
+    (void)tm;
+    return launches;
+}
+
 // returns device ms (sum over stages). Leaves proofs in d_proofs. Throws on unsatisfied witness.
-static float ctx_run_batch(Ctx& cx, size_t n, bool chacha) {
+static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     if (!cx.solver_supported) throw std::runtime_error("unsupported circuit: " + cx.solver_unsupported_reason);
     cudaStream_t st = cx.stream;
     ctx_build_tables(cx);
@@ -362,15 +440,17 @@ static float ctx_run_batch(Ctx& cx, size_t n, bool chacha) {
     G16_CUDA(cudaMemsetAsync(cx.Aev.p, 0, n * cx.n_dom * sizeof(Fr), st));
     G16_CUDA(cudaMemsetAsync(cx.Bev.p, 0, n * cx.n_dom * sizeof(Fr), st));
     G16_CUDA(cudaMemsetAsync(cx.Cev.p, 0, n * cx.n_dom * sizeof(Fr), st));
-    if (chacha) {
+    if (kind == 1) {
         launch_chacha_witness(cx.d_keys.p, cx.d_nonces.p, cx.d_counters.p, cx.d_inputs.p, (uint32_t)n, cx.W.p, n, cx.d_ct.p, st);
+    } else if (kind == 2) {
+        launch_aes_witness(cx.d_keys.p, cx.staged_key_len, cx.d_nonces.p, cx.d_counters.p, cx.d_inputs.p, (uint32_t)n, cx.W.p, n,
+                           cx.d_ct.p, st);
     } else {
         launch_witness_copy(cx.d_witness.p, cx.n_public - 1 + cx.n_secret, (uint32_t)n, cx.W.p, n, st);
     }
     launch_scalars_from_be(cx.d_rs_be.p, (uint32_t)(2 * n), cx.d_rs.p, st);
     // W is wire-major: wire k of proof i at W[k*n + i]
-    own += 2 + launch_solver(cx.sp, cx.h_level_off.data(), (uint32_t)n, cx.W.p, n, cx.Aev.p, cx.Bev.p, cx.Cev.p,
-                             cx.d_status.p, st);
+    own += 2 + ctx_solve(cx, n, &tm);
     // The witness is complete: the wire-driven queries (A, B1, K on G1, B on G2 — short, latency-bound kernels) run on
     // a side stream and fill the SM slots that the long H / Z kernels of the main stream leave idle.
     cudaStream_t st2 = cx.stream2;
@@ -394,12 +474,18 @@ static float ctx_run_batch(Ctx& cx, size_t n, bool chacha) {
             msm_run_g2(cx.ws2, sh, cx.tabB2.p, w, 1, n, cx.qB.map.p, 1, st2, nullptr);
             G16_CUDA(cudaMemcpyAsync(cx.resB2.p + sb, cx.ws2.result.p, (size_t)rows * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st2));
         }
+        if (cx.n_commit)   // proof of knowledge of the commitment: same scalars over BasisExpSigma
+            run_query_g1(cx.ws1b, st2, cx.qPedSigma, w, 1, n, true, rows, cx.resPok.p + sb, nullptr);
     }
     G16_CUDA(cudaEventRecord(cx.ev_join, st2));
     G16_CUDA(cudaStreamWaitEvent(st, cx.ev_join, 0));
     tm.mark(ST_ASSEMBLE, st);
-    own += launch_assemble(cx.keys, cx.asm_scratch, (uint32_t)n, cx.resA.p, cx.resB1.p, cx.resK.p, cx.resZ.p, cx.resB2.p,
-                           cx.d_rs.p, cx.d_proofs.p, cx.proof_bytes(), st);
+    own += launch_assemble(cx.keys, cx.asm_scratch, cx.n_commit != 0, (uint32_t)n, cx.resA.p, cx.resB1.p, cx.resK.p, cx.resZ.p,
+                           cx.resB2.p, cx.d_rs.p, cx.d_proofs.p, cx.proof_bytes(), st);
+    if (cx.n_commit) {
+        launch_assemble_commitment(cx.commit_aff.p, cx.resPok.p, (uint32_t)n, cx.d_proofs.p, cx.proof_bytes(), st);
+        own += 1;
+    }
     tm.mark(-1, st);
     uint32_t status = 0;
     cx.d_status.download(&status, 1, st);

@@ -43,6 +43,17 @@ PkFile parse_pk(const uint8_t* data, size_t len) {
     pk.inf_a = r.take(pk.nb_wires, "InfinityA");
     pk.inf_b = r.take(pk.nb_wires, "InfinityB");
     pk.n_commit_keys = r.be32("len(CommitmentKeys)");
+    if (pk.n_commit_keys > 16) throw ParseError("pk: implausible number of commitment keys");
+    for (uint32_t k = 0; k < pk.n_commit_keys; k++) {
+        PkFile::Ped ped;
+        ped.n_basis = r.be32("len(Pedersen.Basis)");
+        ped.basis = r.take((size_t)ped.n_basis * 32, "Pedersen.Basis");
+        ped.n_sigma = r.be32("len(Pedersen.BasisExpSigma)");
+        ped.basis_sigma = r.take((size_t)ped.n_sigma * 32, "Pedersen.BasisExpSigma");
+        if (ped.n_basis != ped.n_sigma) throw ParseError("pk: Pedersen basis sizes differ");
+        pk.ped.push_back(ped);
+    }
+    if (r.off != len) throw ParseError("pk: trailing bytes");
     if (pk.nZ + 1 != pk.n) throw ParseError("pk: len(G1.Z) != n-1");
     if (pk.nB != pk.nB2) throw ParseError("pk: len(G1.B) != len(G2.B)");
     if (pk.nA + pk.nb_inf_a != pk.nb_wires || pk.nB + pk.nb_inf_b != pk.nb_wires) throw ParseError("pk: infinity counts inconsistent");

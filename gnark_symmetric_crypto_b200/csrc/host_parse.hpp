@@ -30,6 +30,10 @@ struct PkFile {
     const uint8_t* inf_a = nullptr;
     const uint8_t* inf_b = nullptr;
     uint32_t n_commit_keys = 0;
+    // per BSB22 commitment: Pedersen Basis and BasisExpSigma (compressed G1, 32 B each); layout recalled from
+    // gnark-crypto fr/pedersen ProvingKey.WriteTo, self-consistent with oracle/setup.py (no reference key exists)
+    struct Ped { const uint8_t* basis; uint32_t n_basis; const uint8_t* basis_sigma; uint32_t n_sigma; };
+    std::vector<Ped> ped;
 };
 PkFile parse_pk(const uint8_t* data, size_t len);
 

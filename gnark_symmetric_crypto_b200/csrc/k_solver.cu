@@ -4,11 +4,12 @@
 
 namespace g16 {
 
-size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, uint32_t batch, Fr* W, size_t w_stride, Fr* A,
-                     Fr* B, Fr* C, uint32_t* status, cudaStream_t st) {
+size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, uint32_t lev_begin, uint32_t lev_end, uint32_t batch,
+                     Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C, uint32_t* status, cudaStream_t st) {
     const uint32_t groups = div_up(batch, 32);
     size_t launches = 0;
-    for (uint32_t lev = 0; lev < sp.nlevels; lev++) {
+    if (lev_end > sp.nlevels) lev_end = sp.nlevels;
+    for (uint32_t lev = lev_begin; lev < lev_end; lev++) {
         uint32_t lo = h_level_off[lev], hi = h_level_off[lev + 1];
         if (hi == lo) continue;
         dim3 grid(div_up(hi - lo, SOLVER_WARPS), groups);

@@ -195,7 +195,10 @@ std::string prove_impl(const uint8_t* params, size_t len) {
         if (ip.key.size() != 32 && ip.key.size() != 16) throw Panic("key length must be 16 or 32: " + std::to_string(ip.key.size()));   // provers.go:174-176
         if (ip.nonce.size() != 12) throw Panic("nonce length must be 12: " + std::to_string(ip.nonce.size()));
         if (ip.input.size() != 64) throw Panic("plaintext length must be 64: " + std::to_string(ip.input.size()));
-        throw Panic("AES-CTR proving (BSB22 commitment path) is not implemented in this build of libg16b200");
+        int rc = g16_prove_aes_batch(ctx, 1, ip.key.data(), ip.key.size(), ip.nonce.data(), &ip.counter, ip.input.data(), nullptr,
+                                     proof.data(), ct.data());
+        if (rc) throw Panic(std::string("groth16 prove failed: ") + g16_last_error());
+        proof.resize(196);
     }
     return "{\"proof\":{\"proofJson\":\"" + b64encode(proof.data(), proof.size()) + "\"},\"publicSignals\":\"" +
            b64encode(ct.data(), ct.size()) + "\"}";

@@ -32,6 +32,8 @@ struct SolverProgram {
     uint32_t n_wires;
     uint32_t n_dom;                // stride of the A/B/C vectors (domain size)
     int fast_coeffs;               // coefficient ids 1,2,3,4 are +1,+2,-1,-2 (verified on the device at init)
+    const Fr* randomize;           // per witness: value of the hints.Randomize wire (Montgomery), or null
+    uint32_t bsb_ins;              // instruction id of the Bsb22 commitment hint (executed by the host pipeline), or ~0
 };
 
 struct AssemblyKeys {
@@ -52,16 +54,27 @@ void launch_chacha_witness(const uint8_t* keys, const uint8_t* nonces, const uin
                            uint32_t n, Fr* W, size_t w_stride, uint8_t* ct_out, cudaStream_t st);
 void launch_witness_copy(const Fr* witness, uint32_t n_witness, uint32_t batch, Fr* W, size_t w_stride, cudaStream_t st);
 // h_level_off: host copy of the level offsets (nlevels + 1). Returns the number of kernel launches.
-size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, uint32_t batch, Fr* W, size_t w_stride, Fr* A,
-                     Fr* B, Fr* C, uint32_t* status, cudaStream_t st);
+// runs levels [lev_begin, lev_end)
+size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, uint32_t lev_begin, uint32_t lev_end, uint32_t batch,
+                     Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C, uint32_t* status, cudaStream_t st);
 // fills ucoef_inv (n_instr entries) and returns whether coefficient ids 0..4 are 0,1,2,-1,-2 (synchronises the stream)
 int launch_solver_init(const SolverProgram& sp, uint32_t n_instr, uint32_t n_coeffs, Fr* ucoef_inv, cudaStream_t st);
 // builds the 64 x 15 fixed-base tables of delta / delta2 (device buffers owned by the caller)
 void launch_fixed_base_tables(const AssemblyKeys& keys, G1Affine* tab1, G2Affine* tab2, cudaStream_t st);
 // three launches; returns the launch count
-size_t launch_assemble(const AssemblyKeys& keys, AssemblyScratch& sc, uint32_t n, const G1XYZZ* mA, const G1XYZZ* mB1,
+size_t launch_assemble(const AssemblyKeys& keys, AssemblyScratch& sc, bool with_commitment, uint32_t n, const G1XYZZ* mA, const G1XYZZ* mB1,
                        const G1XYZZ* mK, const G1XYZZ* mZ, const G2XYZZ* mB2, const Fr* rs, uint8_t* out, size_t out_stride,
                        cudaStream_t st);
+// AES-CTR witness (provers.go:172-227): key_len 16 or 32; W wire-major
+void launch_aes_witness(const uint8_t* keys, uint32_t key_len, const uint8_t* nonces, const uint32_t* counters,
+                        const uint8_t* inputs, uint32_t n, Fr* W, size_t w_stride, uint8_t* ct_out, cudaStream_t st);
+// BSB22: commitment point (XYZZ per proof) -> challenge = hash_to_field(X||Y, "bsb22-commitment") written to the commitment
+// wire; the affine commitment is kept for the proof
+void launch_bsb22_challenge(const G1XYZZ* commit, uint32_t n, Fr* W, size_t w_stride, uint32_t commit_wire, G1Affine* commit_aff,
+                            cudaStream_t st);
+// proof trailer with one commitment: u32 1 | C | PoK (Appendix C) at byte 128 of each proof
+void launch_assemble_commitment(const G1Affine* commit_aff, const G1XYZZ* pok, uint32_t n, uint8_t* out, size_t out_stride,
+                                cudaStream_t st);
 void launch_wires_to_rows(const Fr* W, size_t w_stride, uint32_t batch, uint32_t nb_wires, Fr* out, cudaStream_t st);
 // stage-level test entry points
 void launch_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, cudaStream_t st);

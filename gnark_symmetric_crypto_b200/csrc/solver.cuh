@@ -128,6 +128,50 @@ __device__ __forceinline__ void solve_instruction(const SolverProgram& sp, uint3
                 for (int b = 0; b < 32 && k < o1 - o0; b++, k++) W[(size_t)(o0 + k) * ws] = ((word >> b) & 1u) ? one : zero;
             }
             for (; k < o1 - o0; k++) W[(size_t)(o0 + k) * ws] = zero;
+        } else if (hid == HINT_RANDOMIZE) {
+            // hints.Randomize: one uniformly random field element (the blinding mask of the BSB22 commitment)
+            for (uint32_t k = 0; k < nin; k++) eval_le(sp, W, ws, pos);   // (no inputs in these circuits)
+            uint32_t o0 = sp.calldata[pos];
+            if (sp.randomize) W[(size_t)o0 * ws] = sp.randomize[0];
+            else atomicOr(status, 4u);
+        } else if (hid == HINT_BSB22) {
+            // executed between two level ranges by the host pipeline (MSM + hash): nothing to do here
+            if (ins != sp.bsb_ins) atomicOr(status, 4u);
+        } else if (hid == HINT_COUNT) {
+            // logderivarg.countHint: inputs [nbRows, rowWidth, nbRows x rowWidth table values, queries (rowWidth each)];
+            // output k = number of queries equal to row k. Rows carry their own index in column 0 (logderivlookup tables),
+            // so a query can only match the row named by its first value.
+            uint32_t nrows = eval_le(sp, W, ws, pos).from_mont().l[0];
+            uint32_t width = eval_le(sp, W, ws, pos).from_mont().l[0];
+            uint32_t o_pos;
+            if (nrows > 256 || width != 2 || nin < 2 + nrows * width) { atomicOr(status, 4u); return; }
+            uint16_t cnt[256];
+            for (uint32_t k = 0; k < 256; k++) cnt[k] = 0;
+            // position of every table row in calldata: rows are single constant terms in these circuits, but walk them anyway
+            uint32_t row_pos0 = pos;
+            uint32_t p2 = pos;
+            for (uint32_t k = 0; k < nrows * width; k++) { uint32_t nt = sp.calldata[p2]; p2 += 1 + 2 * nt; }
+            uint32_t row_stride_words = nrows ? (p2 - row_pos0) / nrows : 0;   // uniform rows (checked below)
+            uint32_t nq = (nin - 2 - nrows * width) / width;
+            pos = p2;
+            for (uint32_t q = 0; q < nq; q++) {
+                Fr qi = eval_le(sp, W, ws, pos);
+                Fr qv = eval_le(sp, W, ws, pos);
+                Fr qc = qi.from_mont();
+                uint32_t hi = qc.l[1] | qc.l[2] | qc.l[3] | qc.l[4] | qc.l[5] | qc.l[6] | qc.l[7];
+                if (hi || qc.l[0] >= nrows) continue;
+                uint32_t rp = row_pos0 + qc.l[0] * row_stride_words;
+                Fr ri = eval_le(sp, W, ws, rp);
+                Fr rv = eval_le(sp, W, ws, rp);
+                if (ri == qi && rv == qv) cnt[qc.l[0]]++;
+            }
+            o_pos = pos;
+            uint32_t o0 = sp.calldata[o_pos], o1 = sp.calldata[o_pos + 1];
+            for (uint32_t k = 0; k < o1 - o0; k++) {
+                Fr v = Fr::zero();
+                v.l[0] = k < 256 ? cnt[k] : 0;
+                W[(size_t)(o0 + k) * ws] = v.to_mont();
+            }
         } else {
             atomicOr(status, 4u);
         }
@@ -153,6 +197,7 @@ solver_level_kernel(SolverProgram sp, uint32_t lo, uint32_t hi, uint32_t batch, 
     uint32_t inst = blockIdx.y * 32 + threadIdx.x;
     uint32_t k = lo + blockIdx.x * blockDim.y + threadIdx.y;
     if (inst >= batch || k >= hi) return;
+    if (sp.randomize) sp.randomize += inst;   // sp is a by-value kernel parameter: per-thread view of the mask array
     solve_instruction(sp, sp.level_instr[k], W + inst, w_stride, A + (size_t)inst * sp.n_dom,
                       B + (size_t)inst * sp.n_dom, C + (size_t)inst * sp.n_dom, status);
 }

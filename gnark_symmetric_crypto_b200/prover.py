@@ -175,6 +175,33 @@ class Groth16Context:
         pb = self.proof_bytes
         return [proofs[j * pb:(j + 1) * pb].tobytes() for j in range(n)], [cts[j * 64:(j + 1) * 64].tobytes() for j in range(n)]
 
+    def prove_aes_batch(self, keys, nonces, counters, inputs, rsm=None):
+        """cipher "aes-128-ctr" / "aes-256-ctr": -> (list of 196-byte proofs, list of 64-byte ciphertexts).
+        rsm: per proof r | s | mask (3 x 32-byte big-endian) or None for fresh randomness."""
+        n = len(counters)
+        key_len = len(keys[0])
+        if key_len not in (16, 32):
+            raise ValueError(f"key length must be 16 or 32: {key_len}")
+        k = np.frombuffer(b"".join(keys), dtype=np.uint8).copy()
+        no = np.frombuffer(b"".join(nonces), dtype=np.uint8).copy()
+        i = np.frombuffer(b"".join(inputs), dtype=np.uint8).copy()
+        c = np.asarray(counters, dtype=np.uint32).copy()
+        if no.size != 12 * n:
+            raise ValueError(f"nonce length must be 12: {no.size // max(n, 1)}")
+        if i.size != 64 * n:
+            raise ValueError(f"plaintext length must be 64: {i.size // max(n, 1)}")
+        r = None
+        if rsm is not None:
+            r = np.frombuffer(b"".join(rsm), dtype=np.uint8).copy()
+            if r.size != 96 * n:
+                raise ValueError("rsm must hold 96 bytes per proof")
+        proofs = np.zeros(n * self.proof_bytes, dtype=np.uint8)
+        cts = np.zeros(n * 64, dtype=np.uint8)
+        _check(self._L.g16_prove_aes_batch(self._h, n, _p8(k), key_len, _p8(no), c.ctypes.data_as(u32p), _p8(i),
+                                           _p8(r) if r is not None else None, _p8(proofs), _p8(cts)))
+        pb = self.proof_bytes
+        return [proofs[j * pb:(j + 1) * pb].tobytes() for j in range(n)], [cts[j * 64:(j + 1) * 64].tobytes() for j in range(n)]
+
     # phase-split variant for benchmarks (arrays already packed by the caller)
     def stage(self, k, no, c, i, r):
         _check(self._L.g16_chacha_batch_stage(self._h, len(c), _p8(k), _p8(no), c.ctypes.data_as(u32p), _p8(i),
@@ -201,14 +228,19 @@ class Groth16Context:
         return {k: int(v) for k, v in zip(names, c)}
 
     # ---- stage-level
-    def solve(self, witness: np.ndarray, batch: int = 1):
+    def solve(self, witness: np.ndarray, batch: int = 1, masks=None):
+        """masks: list of ints (one per witness) for circuits with a hints.Randomize wire"""
         w = np.ascontiguousarray(witness, dtype=np.uint64).reshape(batch, -1, 4)
         nw = w.shape[1]
         W = np.zeros((batch, self.nb_wires, 4), dtype=np.uint64)
         A = np.zeros((batch, self.nb_constraints, 4), dtype=np.uint64)
         B = np.zeros_like(A)
         Cc = np.zeros_like(A)
-        _check(self._L.g16_solve(self._h, _p64(w), nw, batch, _p64(W), _p64(A), _p64(B), _p64(Cc)))
+        mb = None
+        if masks is not None:
+            mb = np.frombuffer(b"".join(int(m).to_bytes(32, "big") for m in masks), dtype=np.uint8).copy()
+        _check(self._L.g16_solve_ex(self._h, _p64(w), nw, batch, _p8(mb) if mb is not None else None, _p64(W), _p64(A),
+                                    _p64(B), _p64(Cc)))
         return W, A, B, Cc
 
     def compute_h(self, a, b, c) -> np.ndarray:

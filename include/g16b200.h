@@ -55,8 +55,9 @@ void g16_free(g16_ctx* ctx);
 int g16_info(const g16_ctx* ctx, uint64_t info[16]);
 
 /* gnark-shaped entry: `witness` = the nbPublic-1 public then nbSecret secret assignments (what frontend.NewWitness
- * yields, provers.go:144), Montgomery limbs. rs = r|s as 2 x 32-byte big-endian canonical scalars, or NULL to draw them
- * from the OS CSPRNG (gnark draws from crypto/rand). proof_out must hold g16_info()[13] bytes. */
+ * yields, provers.go:144), Montgomery limbs. rs = r|s as 2 x 32-byte big-endian canonical scalars (followed by the 32-byte
+ * commitment mask for circuits with a hints.Randomize wire, i.e. AES: 96 bytes), or NULL to draw them from the OS CSPRNG
+ * (gnark draws from crypto/rand). proof_out must hold g16_info()[13] bytes. */
 int g16_prove_witness(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, const uint8_t* rs, uint8_t* proof_out,
                       size_t* proof_len);
 
@@ -72,6 +73,15 @@ int g16_chacha_batch_stage(g16_ctx* ctx, size_t n, const uint8_t* keys, const ui
                            const uint8_t* inputs, const uint8_t* rs);
 int g16_chacha_batch_run(g16_ctx* ctx, float* ms);
 int g16_chacha_batch_fetch(g16_ctx* ctx, uint8_t* proofs_out, uint8_t* ct_out);
+
+/* library-shaped batch entry for "aes-128-ctr" / "aes-256-ctr" (provers.go:172-227): key_len 16 or 32. rsm = n x 96 bytes
+ * (r | s | commitment mask, 32-byte big-endian each) or NULL for CSPRNG values. proofs n*196 (one BSB22 commitment),
+ * ciphertexts n*64. g16_aes_batch_stage + g16_chacha_batch_run + g16_chacha_batch_fetch split it into phases. */
+int g16_prove_aes_batch(g16_ctx* ctx, size_t n, const uint8_t* keys, size_t key_len, const uint8_t* nonces,
+                        const uint32_t* counters, const uint8_t* inputs, const uint8_t* rsm, uint8_t* proofs_out,
+                        uint8_t* ct_out);
+int g16_aes_batch_stage(g16_ctx* ctx, size_t n, const uint8_t* keys, size_t key_len, const uint8_t* nonces,
+                        const uint32_t* counters, const uint8_t* inputs, const uint8_t* rsm);
 
 /* per-stage timings of the last g16_chacha_batch_run, milliseconds: 0 witness+solve, 1 compute_h (7 NTT + pointwise),
  * 2 MSM scalar prep + sort, 3 MSM bucket accumulation, 4 MSM reductions, 5 proof assembly, 6 total, 7 kernel launches */
@@ -119,6 +129,9 @@ int g16_compute_h(g16_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint
  * witness: batch x n_witness. Outputs (any may be NULL): W batch x nbWires, A/B/C batch x nbConstraints. */
 int g16_solve(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, size_t batch, uint64_t* W, uint64_t* A,
               uint64_t* B, uint64_t* C);
+/* same, for circuits with a hints.Randomize wire (AES): masks_be = batch x 32-byte big-endian commitment masks */
+int g16_solve_ex(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, size_t batch, const uint8_t* masks_be,
+                 uint64_t* W, uint64_t* A, uint64_t* B, uint64_t* C);
 /* the five MSM results of one proof before assembly: affine msmA, msmB1, msmK, msmZ (G1) and msmB2 (G2) */
 int g16_prove_witness_detail(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, const uint8_t* rs,
                              uint8_t* proof_out, size_t* proof_len, uint64_t* msm_g1_out /* 4 x 8 */,
