@@ -42,6 +42,8 @@ EXPORTS = {
     "g16_prove_aes_batch": (C.c_int, [C.c_void_p, C.c_size_t, u8p, C.c_size_t, u8p, u32p, u8p, u8p, u8p, u8p]),
     "g16_aes_batch_stage": (C.c_int, [C.c_void_p, C.c_size_t, u8p, C.c_size_t, u8p, u32p, u8p, u8p]),
     "g16_solve_ex": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_size_t, u8p, u64p, u64p, u64p, u64p]),
+    "g16_aes_witness": (C.c_int, [u8p, C.c_size_t, u8p, u32p, u8p, C.c_size_t, u8p, u64p]),
+    "g16_bsb22_challenge": (C.c_int, [u64p, C.c_size_t, u64p]),
     "g16_last_stage_ms": (C.c_int, [C.c_void_p, f32p]),
     "g16_last_counters": (C.c_int, [C.c_void_p, u64p]),
     "g16_field_op": (C.c_int, [C.c_int, C.c_int, u64p, u64p, u64p, C.c_size_t]),

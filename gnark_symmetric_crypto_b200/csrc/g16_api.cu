@@ -335,6 +335,41 @@ int g16_solve(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, size_t ba
     return g16_solve_ex(ctx, witness, n_witness, batch, nullptr, W, A, B, C);
 }
 
+int g16_aes_witness(const uint8_t* keys, size_t key_len, const uint8_t* nonces, const uint32_t* counters, const uint8_t* inputs,
+                    size_t n, uint8_t* ct_out, uint64_t* witness_out) {
+    return guarded([&] {
+        REQUIRE(keys && nonces && counters && inputs && n > 0 && n <= (1u << 20), "bad argument");
+        REQUIRE(key_len == 16 || key_len == 32, "key length must be 16 or 32");
+        require_device();
+        const uint32_t nw = 142 + (uint32_t)key_len;   // ONE | Nonce[12] | Counter | Plaintext[64] | Ciphertext[64] | Key
+        DevBuf<uint8_t> dk, dn, di, dct(64 * n);
+        DevBuf<uint32_t> dc;
+        DevBuf<Fr> W((size_t)nw * n), rows((size_t)nw * n);
+        dk.upload(keys, key_len * n); dn.upload(nonces, 12 * n); dc.upload(counters, n); di.upload(inputs, 64 * n);
+        launch_aes_witness(dk.p, (uint32_t)key_len, dn.p, dc.p, di.p, (uint32_t)n, W.p, n, dct.p, 0);
+        if (ct_out) dct.download(ct_out, 64 * n);
+        if (witness_out) {
+            launch_wires_to_rows(W.p, n, (uint32_t)n, nw, rows.p, 0);
+            rows.download((Fr*)witness_out, (size_t)nw * n);
+        }
+        G16_CUDA(cudaDeviceSynchronize());
+    });
+}
+int g16_bsb22_challenge(const uint64_t* commitments, size_t n, uint64_t* challenges_out) {
+    return guarded([&] {
+        REQUIRE(commitments && challenges_out && n > 0 && n <= (1u << 20), "bad argument");
+        require_device();
+        DevBuf<G1Affine> aff, aff2(n);
+        DevBuf<G1XYZZ> xy(n);
+        DevBuf<Fr> out(n);
+        aff.upload((const G1Affine*)commitments, n);
+        launch_g1_affine_to_xyzz(aff.p, (uint32_t)n, xy.p, 0);
+        launch_bsb22_challenge(xy.p, (uint32_t)n, out.p, n, 0, aff2.p, 0);   // "wire 0" of an n-wide witness = out[i]
+        out.download((Fr*)challenges_out, n);
+        G16_CUDA(cudaDeviceSynchronize());
+    });
+}
+
 int g16_compute_h(g16_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c_in, uint64_t* h_out) {
     return guarded([&] {
         REQUIRE(ctx && a && b && c_in && h_out, "NULL argument");

@@ -112,6 +112,10 @@ void launch_bsb22_challenge(const G1XYZZ* commit, uint32_t n, Fr* W, size_t w_st
     G16_LAUNCH(bsb22_challenge_kernel, div_up(n, 64), 64, 0, st, false, commit, n, W, w_stride, commit_wire, commit_aff);
     G16_CHECK_LAUNCH();
 }
+void launch_g1_affine_to_xyzz(const G1Affine* in, uint32_t n, G1XYZZ* out, cudaStream_t st) {
+    G16_LAUNCH(g1_affine_to_xyzz_kernel, div_up(n, 128), 128, 0, st, false, in, n, out);
+    G16_CHECK_LAUNCH();
+}
 void launch_assemble_commitment(const G1Affine* commit_aff, const G1XYZZ* pok, uint32_t n, uint8_t* out, size_t out_stride,
                                 cudaStream_t st) {
     G16_LAUNCH(assemble_commitment_kernel, div_up(n, 64), 64, 0, st, false, commit_aff, pok, n, out, out_stride);

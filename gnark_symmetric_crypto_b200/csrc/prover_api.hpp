@@ -75,6 +75,7 @@ void launch_bsb22_challenge(const G1XYZZ* commit, uint32_t n, Fr* W, size_t w_st
 // proof trailer with one commitment: u32 1 | C | PoK (Appendix C) at byte 128 of each proof
 void launch_assemble_commitment(const G1Affine* commit_aff, const G1XYZZ* pok, uint32_t n, uint8_t* out, size_t out_stride,
                                 cudaStream_t st);
+void launch_g1_affine_to_xyzz(const G1Affine* in, uint32_t n, G1XYZZ* out, cudaStream_t st);
 void launch_wires_to_rows(const Fr* W, size_t w_stride, uint32_t batch, uint32_t nb_wires, Fr* out, cudaStream_t st);
 // stage-level test entry points
 void launch_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, cudaStream_t st);

@@ -265,13 +265,17 @@ __global__ void aes_witness_kernel(const uint8_t* __restrict__ keys, uint32_t ke
     aes_expand_key(key, nk, rk);
     uint8_t ct[64];
     uint32_t ctr = counters[i];
+    // cipher.NewCTR increments the whole 16-byte block as one big-endian integer: a counter within 3 of 2^32 carries into
+    // the nonce bytes. (The circuit then rejects the witness, aes128.go:49-50 AssertIsLessOrEqual(counter, MaxUint32),
+    // exactly as groth16.Prove fails in the reference.)
+    uint8_t blk[16];
+    for (int k = 0; k < 12; k++) blk[k] = nonce[k];
+    blk[12] = (uint8_t)(ctr >> 24); blk[13] = (uint8_t)(ctr >> 16); blk[14] = (uint8_t)(ctr >> 8); blk[15] = (uint8_t)ctr;
     for (int b = 0; b < 4; b++) {
-        uint8_t blk[16], ks[16];
-        for (int k = 0; k < 12; k++) blk[k] = nonce[k];
-        uint32_t c = ctr + (uint32_t)b;
-        blk[12] = (uint8_t)(c >> 24); blk[13] = (uint8_t)(c >> 16); blk[14] = (uint8_t)(c >> 8); blk[15] = (uint8_t)c;
+        uint8_t ks[16];
         aes_encrypt_block(rk, nk + 6, blk, ks);
         for (int k = 0; k < 16; k++) ct[16 * b + k] = in[16 * b + k] ^ ks[k];
+        for (int k = 15; k >= 0; k--) if (++blk[k] != 0) break;
     }
     for (int k = 0; k < 64; k++) ct_out[(size_t)i * 64 + k] = ct[k];
     Fr* w = W + i;
@@ -359,6 +363,11 @@ __global__ void bsb22_challenge_kernel(const G1XYZZ* __restrict__ commit, uint32
         acc = acc + bv;
     }
     W[(size_t)commit_wire * w_stride + i] = acc.to_mont();
+}
+// stage-level test entry (g16_bsb22_challenge): affine points -> the XYZZ form bsb22_challenge_kernel consumes
+__global__ void g1_affine_to_xyzz_kernel(const G1Affine* __restrict__ in, uint32_t n, G1XYZZ* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = G1XYZZ::from_affine(in[i]);
 }
 __global__ void assemble_commitment_kernel(const G1Affine* __restrict__ commit_aff, const G1XYZZ* __restrict__ pok, uint32_t n,
                                            uint8_t* __restrict__ out, size_t out_stride) {

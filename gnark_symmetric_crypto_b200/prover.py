@@ -286,6 +286,30 @@ def decompress(group: int, raw: bytes) -> np.ndarray:
     return out
 
 
+def aes_witness(keys, nonces, counters, inputs, with_witness: bool = True):
+    """provers.go:172-227 witness assignment on the device: -> (ciphertexts [n] bytes, witness [n, 142+key_len, 4] u64
+    Montgomery in solver order ONE | Nonce | Counter | Plaintext | Ciphertext | Key)."""
+    n = len(counters)
+    key_len = len(keys[0])
+    k = np.frombuffer(b"".join(keys), dtype=np.uint8).copy()
+    no = np.frombuffer(b"".join(nonces), dtype=np.uint8).copy()
+    i = np.frombuffer(b"".join(inputs), dtype=np.uint8).copy()
+    c = np.asarray(counters, dtype=np.uint32).copy()
+    cts = np.zeros(n * 64, dtype=np.uint8)
+    wit = np.zeros((n, 142 + key_len, 4), dtype=np.uint64) if with_witness else None
+    _check(_lib.load().g16_aes_witness(_p8(k), key_len, _p8(no), c.ctypes.data_as(u32p), _p8(i), n, _p8(cts),
+                                       _p64(wit) if with_witness else None))
+    return [cts[j * 64:(j + 1) * 64].tobytes() for j in range(n)], wit
+
+
+def bsb22_challenge(commitments: np.ndarray) -> np.ndarray:
+    """gnark prove.go:84-108 commitment hash: affine G1 points [n, 8] u64 Montgomery -> challenges [n, 4] u64 Montgomery"""
+    pts = np.ascontiguousarray(commitments, dtype=np.uint64).reshape(-1, 8)
+    out = np.zeros((len(pts), 4), dtype=np.uint64)
+    _check(_lib.load().g16_bsb22_challenge(_p64(pts), len(pts), _p64(out)))
+    return out
+
+
 def msm(group: int, points: np.ndarray, scalars: np.ndarray, scalars_mont: bool = False, window: int = 0):
     """-> (affine result, [total, accumulate, sort, reduce] ms)"""
     w = 8 if group == 1 else 16

@@ -132,6 +132,14 @@ int g16_solve(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, size_t ba
 /* same, for circuits with a hints.Randomize wire (AES): masks_be = batch x 32-byte big-endian commitment masks */
 int g16_solve_ex(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, size_t batch, const uint8_t* masks_be,
                  uint64_t* W, uint64_t* A, uint64_t* B, uint64_t* C);
+/* AES-CTR witness assignment alone (provers.go:172-227: crypto/aes + cipher.NewCTR for the ciphertext, then the
+ * byte-valued witness): ct_out n x 64; witness_out (may be NULL) n x (142 + key_len) field elements, Montgomery, in
+ * solver order ONE | Nonce[12] | Counter | Plaintext[64] | Ciphertext[64] | Key[key_len]. */
+int g16_aes_witness(const uint8_t* keys, size_t key_len, const uint8_t* nonces, const uint32_t* counters,
+                    const uint8_t* inputs, size_t n, uint8_t* ct_out, uint64_t* witness_out);
+/* BSB22 commitment challenge alone (gnark prove.go:84-108 -> gnark-crypto fr.Hash / hash_to_field, RFC 9380
+ * expand_message_xmd with SHA-256, DST "bsb22-commitment"): n affine G1 commitments (Montgomery x|y) -> n Fr, Montgomery */
+int g16_bsb22_challenge(const uint64_t* commitments, size_t n, uint64_t* challenges_out);
 /* the five MSM results of one proof before assembly: affine msmA, msmB1, msmK, msmZ (G1) and msmB2 (G2) */
 int g16_prove_witness_detail(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, const uint8_t* rs,
                              uint8_t* proof_out, size_t* proof_len, uint64_t* msm_g1_out /* 4 x 8 */,

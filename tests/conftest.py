@@ -47,6 +47,50 @@ def oracle_vk(oracle, vk_bytes):
     return oracle.VerifyingKeyOracle(vk_bytes)
 
 
+def aes_keys(bits: int):
+    """(pk, vk, r1cs) for AES-128/256. The reference ships no pk.aes* (.MISSING_LARGE_BLOBS), so the keys come from the
+    oracle's Setup restatement on the reference's r1cs.aes*, toxic waste from the seed "g16-b200-aes<bits>" (SURVEY §8d
+    config 2/3). Cached under tests/golden/_gen (git-ignored; regenerated in ~30 s when absent)."""
+    from oracle import oracle as O, setup as S
+    r1 = (GOLDEN / f"r1cs.aes{bits}").read_bytes()
+    gen = GOLDEN / "_gen"
+    pkp, vkp = gen / f"pk.aes{bits}", gen / f"vk.aes{bits}"
+    if not (pkp.exists() and vkp.exists()):
+        gen.mkdir(exist_ok=True)
+        pk, vk = S.setup(O.CircuitOracle(r1).r, f"g16-b200-aes{bits}".encode())
+        tmp = gen / f".pk.aes{bits}.{os.getpid()}"
+        tmp.write_bytes(pk); tmp.replace(pkp)
+        tmp.write_bytes(vk); tmp.replace(vkp)
+    return pkp.read_bytes(), vkp.read_bytes(), r1
+
+
+@pytest.fixture(scope="session")
+def aes128_oracle(oracle):
+    from oracle import setup as S
+    pk, vk, r1 = aes_keys(128)
+    return S.AESOracleProver(r1, b"", keys=(pk, vk))
+
+
+@pytest.fixture(scope="session")
+def aes256_oracle(oracle):
+    from oracle import setup as S
+    pk, vk, r1 = aes_keys(256)
+    return S.AESOracleProver(r1, b"", keys=(pk, vk))
+
+
+# libraries/core_test.go:265 / :275 — the reference's AES benchmark inputs (BASELINE configs 2, 3); fixed r, s, mask
+AES_KAT = {
+    128: dict(key=bytes([2]) * 16, nonce=bytes([3]) * 12, counter=2,
+              input=bytes([183, 4, 206, 60, 254, 21, 117, 9, 150, 227, 246, 245, 71, 101, 56, 67, 79, 93, 44, 163, 22, 89, 128, 55, 214,
+                           254, 228, 214, 89, 253, 176, 112, 138, 115, 93, 140, 194, 222, 104, 252, 49, 144, 91, 252]) + bytes(20)),
+    256: dict(key=bytes([2]) * 32, nonce=bytes([3]) * 12, counter=10,
+              input=bytes([189, 250, 225, 242, 6, 46, 173, 203, 7, 166, 62, 139, 67, 150, 1, 155, 64, 122, 211, 198, 184, 203, 124, 194,
+                           99, 34, 127, 29, 236, 17, 232, 214, 154, 146, 78, 217, 254, 224, 208, 196, 55, 200, 23, 93, 90, 175, 240, 31,
+                           31, 225, 26, 15, 219, 156, 123, 21, 103, 98, 205, 87, 197, 22, 245, 158])),
+}
+AES_RSM = (int("11" * 20, 16), int("22" * 20, 16), int("33" * 20, 16))
+
+
 @pytest.fixture(scope="session")
 def emu():
     """TEST-ONLY host-emulation build of the product sources (tests/emu). Never reachable through the package API."""

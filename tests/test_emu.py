@@ -203,3 +203,29 @@ def test_libprove_json_layer(emu):
     assert "not initialized" in prove(b'{"cipher":"chacha20","key":"AAEC","nonce":[],"counter":1,"input":[]}')
     assert isinstance(prove(b"{not json"), str)
     assert "counter" in prove(b'{"cipher":"chacha20","counter":[0,1]}')   # core_test.go:122 passes an array: unmarshal error
+
+
+def test_aes_witness_and_bsb22_hash(emu, oracle):
+    """provers.go:184-210 (AES-CTR keystream, byte-valued witness) and the BSB22 commitment hash (RFC 9380
+    expand_message_xmd / SHA-256 -> Fr) as the device kernels compute them, against the oracle."""
+    from oracle import setup as S
+    rng = np.random.default_rng(11)
+    for klen in (16, 32):
+        n = 5
+        keys = [rng.bytes(klen) for _ in range(n)]; nonces = [rng.bytes(12) for _ in range(n)]
+        ctrs = [0, 0xFFFFFFFC, 0xFFFFFFFE, 7, 1 << 31]; ins = [rng.bytes(64) for _ in range(n)]
+        nonces[2] = bytes([0xFF]) * 12   # cipher.NewCTR carries the counter overflow into the nonce bytes
+        k = np.frombuffer(b"".join(keys), dtype=np.uint8).copy(); no = np.frombuffer(b"".join(nonces), dtype=np.uint8).copy()
+        i = np.frombuffer(b"".join(ins), dtype=np.uint8).copy(); c = np.asarray(ctrs, dtype=np.uint32)
+        cts = np.zeros(64 * n, dtype=np.uint8); wit = np.zeros((n, 142 + klen, 4), dtype=np.uint64)
+        ok(emu, emu.g16_aes_witness(p8(k), klen, p8(no), c.ctypes.data_as(_lib.u32p), p8(i), n, p8(cts), p64(wit)))
+        for j in range(n):
+            a, ct = S.aes_assignment(keys[j], nonces[j], ctrs[j], ins[j])
+            assert cts[64 * j:64 * j + 64].tobytes() == ct, (klen, j)
+            assert np.array_equal(wit[j], oracle.to_mont(1, oracle.ints_to_limbs(a)))
+    assert emu.g16_aes_witness(p8(k), 24, p8(no), c.ctypes.data_as(_lib.u32p), p8(i), n, p8(cts), None) == 1   # AES-192: bad argument
+    pts = oracle.g1_fixed_base(oracle.rand_field(rng, 1, 9)); pts[4] = 0
+    out = np.zeros((9, 4), dtype=np.uint64)
+    ok(emu, emu.g16_bsb22_challenge(p64(pts), 9, p64(out)))
+    ref = oracle.to_mont(1, oracle.ints_to_limbs([S.hash_to_fr(S.g1_uncompressed(p), b"bsb22-commitment") for p in pts]))
+    assert np.array_equal(out, ref)
