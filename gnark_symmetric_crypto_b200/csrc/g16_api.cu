@@ -268,6 +268,16 @@ int g16_prove_aes_batch(g16_ctx* ctx, size_t n, const uint8_t* keys, size_t key_
     if (rc) return rc;
     return g16_chacha_batch_fetch(ctx, proofs_out, ct_out);
 }
+int g16_set_schedule(g16_ctx* ctx, int pipeline, int sub_batch) {
+    return guarded([&] {
+        REQUIRE(ctx, "NULL argument");
+        REQUIRE(sub_batch >= 0 && sub_batch <= (1 << 16), "sub-batch out of range");
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        Ctx& c = *ctx->cx;
+        c.pipeline = pipeline ? 1 : 0;
+        if (sub_batch > 0) c.sub_batch = (uint32_t)sub_batch;
+    });
+}
 int g16_last_stage_ms(const g16_ctx* ctx, float ms[8]) {
     return guarded([&] {
         REQUIRE(ctx && ms, "NULL argument");
@@ -311,7 +321,7 @@ int g16_solve_ex(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, size_t
         G16_CUDA(cudaMemsetAsync(c.Bev.p, 0, batch * c.n_dom * sizeof(Fr), st));
         G16_CUDA(cudaMemsetAsync(c.Cev.p, 0, batch * c.n_dom * sizeof(Fr), st));
         launch_witness_copy(c.d_witness.p, (uint32_t)n_witness, (uint32_t)batch, c.W.p, batch, st);
-        ctx_solve(c, batch, nullptr);
+        ctx_solve(c, batch, 0, (uint32_t)batch, st, c.ws1b);
         uint32_t status = 0;
         c.d_status.download(&status, 1, st);
         DevBuf<Fr> rows;

@@ -61,11 +61,15 @@ struct Ctx {
     DevBuf<uint8_t> d_keys, d_nonces, d_inputs, d_rs_be, d_ct, d_proofs;
     DevBuf<uint32_t> d_counters, d_status;
     DevBuf<Fr> d_rs, d_witness, W, Aev, Bev, Cev;
-    MsmWorkspace<G1> ws1;    // Z query, main stream
+    MsmWorkspace<G1> ws1;    // Z query, main stream (lane 0)
+    MsmWorkspace<G1> ws1c;   // Z query of lane 1 (pipelined schedule)
     MsmWorkspace<G1> ws1b;   // A / B1 / K queries, side stream
     MsmWorkspace<G2> ws2;    // B2 query, side stream
     cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream3 = nullptr;   // lane 1 of the pipelined schedule
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    std::vector<cudaEvent_t> ev_solved;   // one per sub-batch: witness complete
+    int pipeline = 0;                 // 1: sub-batches alternate between two lanes (streams); 0: one main stream, stage timers
     DevBuf<G1XYZZ> resA, resB1, resK, resZ;
     DevBuf<G2XYZZ> resB2;
     StageTimer timer;
@@ -78,6 +82,11 @@ struct Ctx {
     ~Ctx() {
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
+        if (ev_join3) cudaEventDestroy(ev_join3);
+        if (ev_t0) cudaEventDestroy(ev_t0);
+        if (ev_t1) cudaEventDestroy(ev_t1);
+        for (auto e : ev_solved) cudaEventDestroy(e);
+        if (stream3) cudaStreamDestroy(stream3);
         if (stream2) cudaStreamDestroy(stream2);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -135,7 +144,15 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     G16_CUDA(cudaStreamCreate(&cx->stream2));
     G16_CUDA(cudaEventCreate(&cx->ev_fork));
     G16_CUDA(cudaEventCreate(&cx->ev_join));
+    G16_CUDA(cudaStreamCreate(&cx->stream3));
+    G16_CUDA(cudaEventCreate(&cx->ev_join3));
+    G16_CUDA(cudaEventCreate(&cx->ev_t0));
+    G16_CUDA(cudaEventCreate(&cx->ev_t1));
     cudaStream_t st = cx->stream;
+    // Measured on B200 (1024 ChaCha proofs): single stream 189.9 ms; two lanes 191.3 / 198.6 / 214.9 ms at sub-batch
+    // 512 / 256 / 128. The bucket-accumulation and NTT kernels fill every SM's register file, so kernels of the other
+    // lane only time-slice with them; the pipelined schedule stays available (G16_PIPELINE=1) but is not the default.
+    cx->pipeline = env_int("G16_PIPELINE", 0);
     cx->sub_batch = (uint32_t)env_int("G16_SUBBATCH", 512);
     if (cx->sub_batch == 0) cx->sub_batch = 1;
 
@@ -399,27 +416,40 @@ static void run_query_g1(MsmWorkspace<G1>& ws, cudaStream_t st, const PrecompQue
     G16_CUDA(cudaMemcpyAsync(out, ws.result.p, (size_t)rows * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
 }
 
-// Solves all witnesses of the batch (W wire-major, stride n). With a BSB22 commitment the level schedule is cut after
-// the level that holds the commitment hint: Pedersen MSM over the committed wires -> hash to field -> challenge wire
-// (gnark prove.go:84-108 overrides the hint the same way), then the remaining levels run.
-static size_t ctx_solve(Ctx& cx, size_t n, StageTimer* tm) {
-    cudaStream_t st = cx.stream;
+// Solves witnesses [sb, sb + rows) of the batch (W wire-major, stride n) on stream st. With a BSB22 commitment the level
+// schedule is cut after the level that holds the commitment hint: Pedersen MSM over the committed wires -> hash to field ->
+// challenge wire (gnark prove.go:84-108 overrides the hint the same way), then the remaining levels run. wsc: the MSM
+// workspace the commitment may use on this stream.
+static size_t ctx_solve(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaStream_t st, MsmWorkspace<G1>& wsc) {
     SolverProgram sp = cx.sp;
-    sp.randomize = cx.has_randomize ? cx.d_mask.p : nullptr;
+    sp.randomize = cx.has_randomize ? cx.d_mask.p + sb : nullptr;
+    Fr* W = cx.W.p + sb;
+    Fr* A = cx.Aev.p + sb * cx.n_dom;
+    Fr* B = cx.Bev.p + sb * cx.n_dom;
+    Fr* C = cx.Cev.p + sb * cx.n_dom;
     if (!cx.n_commit)
-        return launch_solver(sp, cx.h_level_off.data(), 0, cx.nlevels, (uint32_t)n, cx.W.p, n, cx.Aev.p, cx.Bev.p, cx.Cev.p,
-                             cx.d_status.p, st);
-    size_t launches = launch_solver(sp, cx.h_level_off.data(), 0, cx.bsb_level + 1, (uint32_t)n, cx.W.p, n, cx.Aev.p, cx.Bev.p,
-                                    cx.Cev.p, cx.d_status.p, st);
-    for (size_t sb = 0; sb < n; sb += cx.sub_batch) {
-        uint32_t rows = (uint32_t)((n - sb) < cx.sub_batch ? (n - sb) : cx.sub_batch);
-        run_query_g1(cx.ws1b, st, cx.qPed, cx.W.p + sb, 1, n, true, rows, cx.resCommit.p + sb, nullptr);
+        return launch_solver(sp, cx.h_level_off.data(), 0, cx.nlevels, rows, W, n, A, B, C, cx.d_status.p, st);
+    size_t launches = launch_solver(sp, cx.h_level_off.data(), 0, cx.bsb_level + 1, rows, W, n, A, B, C, cx.d_status.p, st);
+    for (size_t o = 0; o < rows; o += cx.sub_batch) {
+        uint32_t r = (uint32_t)((rows - o) < cx.sub_batch ? (rows - o) : cx.sub_batch);
+        run_query_g1(wsc, st, cx.qPed, W + o, 1, n, true, r, cx.resCommit.p + sb + o, nullptr);
     }
-    launch_bsb22_challenge(cx.resCommit.p, (uint32_t)n, cx.W.p, n, cx.commit_wire, cx.commit_aff.p, st);
-    launches += 1 + launch_solver(sp, cx.h_level_off.data(), cx.bsb_level + 1, cx.nlevels, (uint32_t)n, cx.W.p, n, cx.Aev.p,
-                                  cx.Bev.p, cx.Cev.p, cx.d_status.p, st);
-    (void)tm;
+    launch_bsb22_challenge(cx.resCommit.p + sb, rows, W, n, cx.commit_wire, cx.commit_aff.p + sb, st);
+    launches += 1 + launch_solver(sp, cx.h_level_off.data(), cx.bsb_level + 1, cx.nlevels, rows, W, n, A, B, C, cx.d_status.p, st);
     return launches;
+}
+
+// the wire-driven queries of one sub-batch (A, B1, K on G1, B on G2, the commitment PoK): short, latency-bound kernels
+static void ctx_wire_queries(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaStream_t st2) {
+    const Fr* w = cx.W.p + sb;   // column offset into the wire-major array
+    run_query_g1(cx.ws1b, st2, cx.qA, w, 1, n, true, rows, cx.resA.p + sb, nullptr);
+    run_query_g1(cx.ws1b, st2, cx.qB, w, 1, n, true, rows, cx.resB1.p + sb, nullptr);
+    run_query_g1(cx.ws1b, st2, cx.qK, w, 1, n, true, rows, cx.resK.p + sb, nullptr);
+    MsmShape sh = msm_make_shape(cx.nB2, rows, cx.cB2, 1);
+    msm_run_g2(cx.ws2, sh, cx.tabB2.p, w, 1, n, cx.qB.map.p, 1, st2, nullptr);
+    G16_CUDA(cudaMemcpyAsync(cx.resB2.p + sb, cx.ws2.result.p, (size_t)rows * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st2));
+    if (cx.n_commit)   // proof of knowledge of the commitment: same scalars over BasisExpSigma
+        run_query_g1(cx.ws1b, st2, cx.qPedSigma, w, 1, n, true, rows, cx.resPok.p + sb, nullptr);
 }
 
 // returns device ms (sum over stages). Leaves proofs in d_proofs. Throws on unsatisfied witness.
@@ -430,12 +460,14 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     ctx_ensure_batch(cx, n);
     StageTimer& tm = cx.timer;
     tm.reset();
-    size_t l0 = cx.ws1.launches + cx.ws1b.launches + cx.ws2.launches + cx.dom.launches;
+    size_t l0 = cx.ws1.launches + cx.ws1c.launches + cx.ws1b.launches + cx.ws2.launches + cx.dom.launches;
     size_t own = 0;
     cx.ws1.log_reset();
+    cx.ws1c.log_reset();
     cx.ws1b.log_reset();
     cx.ws2.log_reset();
-    tm.mark(ST_SOLVE, st);
+    const bool piped = cx.pipeline && n > cx.sub_batch;
+    tm.mark(piped ? ST_COUNT : ST_SOLVE, st);   // pipelined: one interval that only counts towards the total
     G16_CUDA(cudaMemsetAsync(cx.d_status.p, 0, 4, st));
     G16_CUDA(cudaMemsetAsync(cx.Aev.p, 0, n * cx.n_dom * sizeof(Fr), st));
     G16_CUDA(cudaMemsetAsync(cx.Bev.p, 0, n * cx.n_dom * sizeof(Fr), st));
@@ -449,33 +481,49 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
         launch_witness_copy(cx.d_witness.p, cx.n_public - 1 + cx.n_secret, (uint32_t)n, cx.W.p, n, st);
     }
     launch_scalars_from_be(cx.d_rs_be.p, (uint32_t)(2 * n), cx.d_rs.p, st);
+    own += 2;
     // W is wire-major: wire k of proof i at W[k*n + i]
-    own += 2 + ctx_solve(cx, n, &tm);
-    // The witness is complete: the wire-driven queries (A, B1, K on G1, B on G2 — short, latency-bound kernels) run on
-    // a side stream and fill the SM slots that the long H / Z kernels of the main stream leave idle.
     cudaStream_t st2 = cx.stream2;
-    G16_CUDA(cudaEventRecord(cx.ev_fork, st));
-    G16_CUDA(cudaStreamWaitEvent(st2, cx.ev_fork, 0));
-    for (size_t sb = 0; sb < n; sb += cx.sub_batch) {
-        uint32_t rows = (uint32_t)((n - sb) < cx.sub_batch ? (n - sb) : cx.sub_batch);
-        Fr* a = cx.Aev.p + sb * cx.n_dom;
-        Fr* b = cx.Bev.p + sb * cx.n_dom;
-        Fr* c = cx.Cev.p + sb * cx.n_dom;
-        const Fr* w = cx.W.p + sb;   // column offset into the wire-major array
-        tm.mark(ST_H, st);
-        compute_h_run(cx.dom, a, b, c, cx.n_dom, rows, st);
-        // h (gnark order) pairs index-for-index with G1.Z; the other queries read wire values through their maps
-        run_query_g1(cx.ws1, st, cx.qZ, a, cx.n_dom, 1, false, rows, cx.resZ.p + sb, &tm);
-        run_query_g1(cx.ws1b, st2, cx.qA, w, 1, n, true, rows, cx.resA.p + sb, nullptr);
-        run_query_g1(cx.ws1b, st2, cx.qB, w, 1, n, true, rows, cx.resB1.p + sb, nullptr);
-        run_query_g1(cx.ws1b, st2, cx.qK, w, 1, n, true, rows, cx.resK.p + sb, nullptr);
-        {
-            MsmShape sh = msm_make_shape(cx.nB2, rows, cx.cB2, 1);
-            msm_run_g2(cx.ws2, sh, cx.tabB2.p, w, 1, n, cx.qB.map.p, 1, st2, nullptr);
-            G16_CUDA(cudaMemcpyAsync(cx.resB2.p + sb, cx.ws2.result.p, (size_t)rows * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st2));
+    if (!piped) {
+        // one main stream with stage timers: solve everything, then per sub-batch H and the Z query; the wire-driven
+        // queries run on a side stream and fill the SM slots that the long H / Z kernels leave idle.
+        own += ctx_solve(cx, n, 0, (uint32_t)n, st, cx.ws1b);
+        G16_CUDA(cudaEventRecord(cx.ev_fork, st));
+        G16_CUDA(cudaStreamWaitEvent(st2, cx.ev_fork, 0));
+        for (size_t sb = 0; sb < n; sb += cx.sub_batch) {
+            uint32_t rows = (uint32_t)((n - sb) < cx.sub_batch ? (n - sb) : cx.sub_batch);
+            Fr* a = cx.Aev.p + sb * cx.n_dom;
+            tm.mark(ST_H, st);
+            compute_h_run(cx.dom, a, cx.Bev.p + sb * cx.n_dom, cx.Cev.p + sb * cx.n_dom, cx.n_dom, rows, st);
+            // h (gnark order) pairs index-for-index with G1.Z; the other queries read wire values through their maps
+            run_query_g1(cx.ws1, st, cx.qZ, a, cx.n_dom, 1, false, rows, cx.resZ.p + sb, &tm);
+            ctx_wire_queries(cx, n, sb, rows, st2);
         }
-        if (cx.n_commit)   // proof of knowledge of the commitment: same scalars over BasisExpSigma
-            run_query_g1(cx.ws1b, st2, cx.qPedSigma, w, 1, n, true, rows, cx.resPok.p + sb, nullptr);
+    } else {
+        // Pipelined schedule: sub-batch k runs its whole chain (solve -> H -> Z query) on lane k % 2, so the latency-bound
+        // phases of one sub-batch (solver levels, bucket sort, reduction trees) overlap the integer-multiply-bound phases
+        // (NTT, bucket accumulation) of the other lane; the wire-driven queries follow on the side stream as soon as the
+        // sub-batch's witness is complete. Stage timers are meaningless here: only the total is measured.
+        cudaStream_t lane[2] = {st, cx.stream3};
+        MsmWorkspace<G1>* wsz[2] = {&cx.ws1, &cx.ws1c};
+        G16_CUDA(cudaEventRecord(cx.ev_fork, st));
+        G16_CUDA(cudaStreamWaitEvent(lane[1], cx.ev_fork, 0));
+        size_t k = 0;
+        for (size_t sb = 0; sb < n; sb += cx.sub_batch, k++) {
+            uint32_t rows = (uint32_t)((n - sb) < cx.sub_batch ? (n - sb) : cx.sub_batch);
+            cudaStream_t s = lane[k & 1];
+            MsmWorkspace<G1>& wz = *wsz[k & 1];
+            own += ctx_solve(cx, n, sb, rows, s, wz);
+            if (cx.ev_solved.size() <= k) { cudaEvent_t e; G16_CUDA(cudaEventCreate(&e)); cx.ev_solved.push_back(e); }
+            G16_CUDA(cudaEventRecord(cx.ev_solved[k], s));
+            G16_CUDA(cudaStreamWaitEvent(st2, cx.ev_solved[k], 0));
+            ctx_wire_queries(cx, n, sb, rows, st2);
+            Fr* a = cx.Aev.p + sb * cx.n_dom;
+            compute_h_run(cx.dom, a, cx.Bev.p + sb * cx.n_dom, cx.Cev.p + sb * cx.n_dom, cx.n_dom, rows, s);
+            run_query_g1(wz, s, cx.qZ, a, cx.n_dom, 1, false, rows, cx.resZ.p + sb, nullptr);
+        }
+        G16_CUDA(cudaEventRecord(cx.ev_join3, lane[1]));
+        G16_CUDA(cudaStreamWaitEvent(st, cx.ev_join3, 0));
     }
     G16_CUDA(cudaEventRecord(cx.ev_join, st2));
     G16_CUDA(cudaStreamWaitEvent(st, cx.ev_join, 0));
@@ -494,16 +542,18 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     float total = tm.finish(per);
     for (int i = 0; i < ST_COUNT; i++) cx.stage_ms[i] = per[i];
     cx.stage_ms[6] = total;
-    cx.launches = own + (cx.ws1.launches + cx.ws1b.launches + cx.ws2.launches + cx.dom.launches - l0);
+    cx.launches = own + (cx.ws1.launches + cx.ws1c.launches + cx.ws1b.launches + cx.ws2.launches + cx.dom.launches - l0);
     cx.stage_ms[7] = (float)cx.launches;
     G16_CUDA(cudaStreamSynchronize(st2));
-    cx.counters[0] = cx.ws1.log_sum(st) + cx.ws1b.log_sum(st2);   // G1 mixed additions performed by the accumulate kernel
-    cx.counters[6] = cx.ws1.log_sum(st);                          // ... of which on the main stream (Z query)
+    G16_CUDA(cudaStreamSynchronize(cx.stream3));
+    cx.counters[6] = cx.ws1.log_sum(st) + cx.ws1c.log_sum(cx.stream3);   // G1 mixed additions of the Z query (lanes)
+    cx.counters[0] = cx.counters[6] + cx.ws1b.log_sum(st2);               // ... of all G1 queries
     cx.counters[1] = cx.ws2.log_sum(st2);   // G2 mixed additions
-    cx.counters[2] = cx.ws1.log_n + cx.ws1b.log_n;   // G1 accumulate launches
+    cx.counters[2] = cx.ws1.log_n + cx.ws1c.log_n + cx.ws1b.log_n;   // G1 accumulate launches
     cx.counters[3] = cx.ws2.log_n;
     cx.counters[4] = cx.launches;
     cx.counters[5] = n;
+    cx.counters[7] = (uint64_t)cx.sub_batch | ((uint64_t)(piped ? 1 : 0) << 32);
     if (status & 4u) throw std::runtime_error("solver: unsupported hint");
     if (status & 3u) throw std::domain_error("witness does not satisfy the constraint system");
     return total;

@@ -215,6 +215,11 @@ class Groth16Context:
     def fetch(self, proofs: np.ndarray, cts: np.ndarray):
         _check(self._L.g16_chacha_batch_fetch(self._h, _p8(proofs), _p8(cts)))
 
+    def set_schedule(self, pipeline: bool, sub_batch: int = 0):
+        """pipeline=True: sub-batches alternate between two streams (throughput schedule, total time only);
+        False: one main stream with per-stage timers. Results are identical."""
+        _check(self._L.g16_set_schedule(self._h, int(bool(pipeline)), int(sub_batch)))
+
     def stage_ms(self) -> dict:
         ms = np.zeros(8, dtype=np.float32)
         _check(self._L.g16_last_stage_ms(self._h, ms.ctypes.data_as(f32p)))
@@ -225,7 +230,10 @@ class Groth16Context:
         c = np.zeros(8, dtype=np.uint64)
         _check(self._L.g16_last_counters(self._h, _p64(c)))
         names = ["g1_madds", "g2_madds", "g1_acc_launches", "g2_acc_launches", "launches", "proofs", "g1_madds_main_stream"]
-        return {k: int(v) for k, v in zip(names, c)}
+        out = {k: int(v) for k, v in zip(names, c)}
+        out["sub_batch"] = int(c[7]) & 0xFFFFFFFF
+        out["pipelined"] = bool(int(c[7]) >> 32)
+        return out
 
     # ---- stage-level
     def solve(self, witness: np.ndarray, batch: int = 1, masks=None):
