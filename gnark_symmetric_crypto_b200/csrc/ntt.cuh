@@ -4,8 +4,8 @@
 // difFFT, ditFFT, kerDIF*/kerDIT*) and gnark v0.11.0 backend/groth16/bn254/prove.go:359-384 (computeH), reached from
 // libraries/prover/impl/provers.go:148,216.
 //
-// A transform of size n = 2^k is run as 1 + ceil((k-11)/8) passes; each pass stages a tile of up to 2048 elements
-// (64 KiB) in shared memory and performs all radix-2 stages whose butterfly bit lies inside the tile, so a 2^15 vector
+// A transform of size n = 2^k is run as 1 + ceil((k-T)/8) passes (T = NTT_TILE_LG = 10); each pass stages a tile of up to
+// 2^T elements (32 KiB) in shared memory and performs all radix-2 stages whose butterfly bit lies inside the tile, so a 2^15 vector
 // crosses HBM/L2 twice per transform. DIF (natural -> bit-reversed) and DIT (bit-reversed -> natural) are paired exactly
 // as gnark pairs them, which removes every bit-reversal permutation from compute_h; the 1/n and coset factors g^(+-i)
 // are folded into the pass that touches the bit-reversed side. `batch` vectors are transformed per launch (grid.y).
@@ -13,6 +13,13 @@
 #include "ntt_api.hpp"
 
 namespace g16 {
+
+#ifndef NTT_MINB
+#define NTT_MINB 4   // resident CTAs per SM the pass kernel is compiled for (32 KiB tiles: 4 x 256 threads x 64 registers)
+#endif
+#ifndef NTT_ILP
+#define NTT_ILP 1   // independent butterflies in flight per thread (see ntt_api.hpp for the measurements)
+#endif
 
 // tile-local index -> index in the vector
 FD uint32_t ntt_global_index(const NttPass& p, uint32_t tile, uint32_t e) {
@@ -40,7 +47,7 @@ FD Fr sm_load(const uint4* sm, uint32_t tile_elems, uint32_t e) {
 
 // One pass over `batch` vectors. tw = table of w^i, i < n/2 (w = the root used by this direction).
 // scale (optional) multiplies element at vector index i by scale[i]: on load for DIT, on store for DIF.
-__global__ void __launch_bounds__(NTT_THREADS)
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MINB)
 ntt_pass_kernel(Fr* __restrict__ data, size_t vec_stride, NttPass p, const Fr* __restrict__ tw,
                 const Fr* __restrict__ scale) {
 #if defined(G16_EMU)
@@ -62,25 +69,40 @@ ntt_pass_kernel(Fr* __restrict__ data, size_t vec_stride, NttPass p, const Fr* _
     for (int s = 0; s < p.m; s++) {
         int bit = p.dif ? (p.b_lo + p.m - 1 - s) : (p.b_lo + s);   // butterfly bit in the vector index
         int lb = bit - p.b_lo + (p.b_lo == 0 ? 0 : p.q);           // same bit in the tile-local index
-        for (uint32_t u = threadIdx.x; u < half; u += blockDim.x) {
-            uint32_t e0 = ((u >> lb) << (lb + 1)) | (u & ((1u << lb) - 1u));
-            uint32_t e1 = e0 | (1u << lb);
-            uint32_t gi = ntt_global_index(p, tile, e0);
-            uint32_t tidx = (gi & ((1u << bit) - 1u)) << (p.k - 1 - bit);
-            Fr a = sm_load(sm, tile_elems, e0), b = sm_load(sm, tile_elems, e1);
-            if (bit == 0) {   // span-1 stage: every twiddle is w^0 = 1 (uniform across the grid): no product
-                sm_store(sm, tile_elems, e0, a + b);
-                sm_store(sm, tile_elems, e1, a - b);
-            } else if (p.dif) {
-                Fr w = tw[tidx];
-                Fr d = a - b;
-                sm_store(sm, tile_elems, e0, a + b);
-                sm_store(sm, tile_elems, e1, d * w);
-            } else {
-                Fr w = tw[tidx];
-                Fr t = b * w;
-                sm_store(sm, tile_elems, e0, a + t);
-                sm_store(sm, tile_elems, e1, a - t);
+        // NTT_ILP butterflies per thread are loaded, computed and stored together: their Montgomery products are independent
+        // carry chains that ptxas interleaves (one chain per warp leaves the multiplier waiting on its own carries)
+        for (uint32_t u0 = threadIdx.x; u0 < half; u0 += blockDim.x * NTT_ILP) {
+            Fr a[NTT_ILP], b[NTT_ILP], w[NTT_ILP];
+            uint32_t e0[NTT_ILP];
+#pragma unroll
+            for (int j = 0; j < NTT_ILP; j++) {
+                uint32_t u = u0 + (uint32_t)j * blockDim.x;
+                if (u >= half) { e0[j] = 0xFFFFFFFFu; continue; }
+                e0[j] = ((u >> lb) << (lb + 1)) | (u & ((1u << lb) - 1u));
+                a[j] = sm_load(sm, tile_elems, e0[j]);
+                b[j] = sm_load(sm, tile_elems, e0[j] | (1u << lb));
+                if (bit != 0) {
+                    uint32_t gi = ntt_global_index(p, tile, e0[j]);
+                    w[j] = tw[(gi & ((1u << bit) - 1u)) << (p.k - 1 - bit)];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NTT_ILP; j++) {
+                if (e0[j] == 0xFFFFFFFFu) continue;
+                Fr lo, hi;
+                if (bit == 0) {   // span-1 stage: every twiddle is w^0 = 1 (uniform across the grid): no product
+                    lo = a[j] + b[j];
+                    hi = a[j] - b[j];
+                } else if (p.dif) {
+                    lo = a[j] + b[j];
+                    hi = (a[j] - b[j]) * w[j];
+                } else {
+                    Fr t = b[j] * w[j];
+                    lo = a[j] + t;
+                    hi = a[j] - t;
+                }
+                sm_store(sm, tile_elems, e0[j], lo);
+                sm_store(sm, tile_elems, e0[j] | (1u << lb), hi);
             }
         }
         __syncthreads();

@@ -207,6 +207,10 @@ class Groth16Context:
         _check(self._L.g16_chacha_batch_stage(self._h, len(c), _p8(k), _p8(no), c.ctypes.data_as(u32p), _p8(i),
                                               _p8(r) if r is not None else None))
 
+    def stage_aes(self, k, key_len, no, c, i, r):
+        _check(self._L.g16_aes_batch_stage(self._h, len(c), _p8(k), key_len, _p8(no), c.ctypes.data_as(u32p), _p8(i),
+                                           _p8(r) if r is not None else None))
+
     def run(self) -> float:
         ms = C.c_float(0)
         _check(self._L.g16_chacha_batch_run(self._h, C.byref(ms)))
