@@ -96,10 +96,14 @@ void launch_wires_to_rows(const Fr* W, size_t w_stride, uint32_t batch, uint32_t
     G16_CHECK_LAUNCH();
 }
 void launch_fixed_base_tables(const AssemblyKeys& keys, G1Affine* tab1, G2Affine* tab2, cudaStream_t st) {
-    auto k1 = fixed_base_table_kernel<G1>;
+    launch_fixed_base_table_g1(keys.delta, tab1, st);
     auto k2 = fixed_base_table_kernel<G2>;
-    G16_LAUNCH(k1, 1, 64, 0, st, false, keys.delta, tab1);
-    G16_LAUNCH(k2, 1, 64, 0, st, false, keys.delta2, tab2);
+    G16_LAUNCH(k2, 1, FB_WINDOWS, 0, st, false, keys.delta2, tab2);
+    G16_CHECK_LAUNCH();
+}
+void launch_assemble_g2(const AssemblyKeys& keys, uint32_t n, const G2XYZZ* mB2, const Fr* rs, uint8_t* out, size_t out_stride,
+                        cudaStream_t st) {
+    G16_LAUNCH(assemble_g2_kernel, n, FB_WINDOWS, 0, st, true, keys, n, mB2, rs, out, out_stride);
     G16_CHECK_LAUNCH();
 }
 void launch_aes_witness(const uint8_t* keys, uint32_t key_len, const uint8_t* nonces, const uint32_t* counters,
@@ -121,18 +125,4 @@ void launch_assemble_commitment(const G1Affine* commit_aff, const G1XYZZ* pok, u
     G16_LAUNCH(assemble_commitment_kernel, div_up(n, 64), 64, 0, st, false, commit_aff, pok, n, out, out_stride);
     G16_CHECK_LAUNCH();
 }
-size_t launch_assemble(const AssemblyKeys& keys, AssemblyScratch& sc, bool with_commitment, uint32_t n, const G1XYZZ* mA, const G1XYZZ* mB1,
-                       const G1XYZZ* mK, const G1XYZZ* mZ, const G2XYZZ* mB2, const Fr* rs, uint8_t* out, size_t out_stride,
-                       cudaStream_t st) {
-    sc.Ar.ensure(n); sc.Bs1.ensure(n); sc.sAr.ensure(n); sc.rBs1.ensure(n);
-    const unsigned gx = div_up(n, 64);
-    G16_LAUNCH(assemble_phase1_kernel, dim3(gx, 3), 64, 0, st, false, keys, n, mA, mB1, mB2, rs, sc.Ar.p, sc.Bs1.p, out, out_stride);
-    G16_LAUNCH(assemble_phase2_kernel, dim3(gx, 2), 64, 0, st, false, n, (const G1XYZZ*)sc.Ar.p, (const G1XYZZ*)sc.Bs1.p, rs,
-               sc.sAr.p, sc.rBs1.p);
-    G16_LAUNCH(assemble_phase3_kernel, dim3(gx, 2), 64, 0, st, false, keys, n, with_commitment ? 1 : 0, mK, mZ, (const G1XYZZ*)sc.Ar.p,
-               (const G1XYZZ*)sc.sAr.p, (const G1XYZZ*)sc.rBs1.p, rs, out, out_stride);
-    G16_CHECK_LAUNCH();
-    return 3;
-}
-
 }  // namespace g16

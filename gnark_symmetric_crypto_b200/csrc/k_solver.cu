@@ -1,6 +1,7 @@
 // Hot translation unit: the batched R1CS solver (solver.cuh) with the Montgomery product inlined, so that the four
 // independent coefficient products of an unrolled term group overlap.
 #include "solver.cuh"
+#include <cstdlib>
 
 namespace g16 {
 
@@ -9,12 +10,27 @@ size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, uint3
     const uint32_t groups = div_up(batch, 32);
     size_t launches = 0;
     if (lev_end > sp.nlevels) lev_end = sp.nlevels;
+#if !defined(G16_EMU)
+    // few witnesses: lanes split the terms of an instruction instead of the witnesses (G16_SOLVER_SMALL = largest such batch)
+    static const uint32_t small_max = [] { const char* v = getenv("G16_SOLVER_SMALL"); return (uint32_t)(v && *v ? atoi(v) : 8); }();
+    const bool small = batch <= small_max;
+#else
+    const bool small = false;
+#endif
     for (uint32_t lev = lev_begin; lev < lev_end; lev++) {
         uint32_t lo = h_level_off[lev], hi = h_level_off[lev + 1];
         if (hi == lo) continue;
-        dim3 grid(div_up(hi - lo, SOLVER_WARPS), groups);
-        G16_LAUNCH(solver_level_kernel, grid, dim3(32, SOLVER_WARPS), 0, st, false, sp, lo, hi, batch, W, w_stride, A, B, C,
-                   status);
+        if (small) {
+#if !defined(G16_EMU)
+            dim3 grid(div_up(hi - lo, SOLVER_WARPS), batch);
+            G16_LAUNCH(solver_level_small_kernel, grid, dim3(32, SOLVER_WARPS), 0, st, false, sp, lo, hi, batch, W, w_stride, A, B,
+                       C, status);
+#endif
+        } else {
+            dim3 grid(div_up(hi - lo, SOLVER_WARPS), groups);
+            G16_LAUNCH(solver_level_kernel, grid, dim3(32, SOLVER_WARPS), 0, st, false, sp, lo, hi, batch, W, w_stride, A, B, C,
+                       status);
+        }
         launches++;
     }
     G16_CHECK_LAUNCH();

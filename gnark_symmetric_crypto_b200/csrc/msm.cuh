@@ -298,18 +298,19 @@ msm_merge_final_kernel(const uint32_t* __restrict__ total_entries, int L, int le
 // Node = (R, V): R = sum of the B_k below it, V = sum (k - base)*B_k. Leaves are the buckets (weight 1..g inside a
 // level-1 node), upper levels use 0-based child weights:  V = sum_i V_i + span_child * sum_i i*R_i.
 // Segment = one (row, window) bucket set of `n_in` items; thread = one output node.
-template <class C, int LEVEL1>
+template <class C, int LEVEL1, int LOG_G>
 __global__ void __launch_bounds__(128)
 msm_tree_kernel(const typename C::X* __restrict__ in_R, const typename C::X* __restrict__ in_V, uint32_t n_in,
                 uint32_t n_out, uint32_t segs, int log_span_child, typename C::X* __restrict__ out_R,
                 typename C::X* __restrict__ out_V) {
     typedef typename C::X X;
+    const uint32_t G = 1u << LOG_G;
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)segs * n_out) return;
     uint32_t seg = (uint32_t)(gid / n_out), node = (uint32_t)(gid % n_out);
     const X* R = in_R + (size_t)seg * n_in;
-    uint32_t lo = node * MSM_TREE_G;
-    uint32_t hi = lo + MSM_TREE_G < n_in ? lo + MSM_TREE_G : n_in;   // children [lo, hi)
+    uint32_t lo = node * G;
+    uint32_t hi = lo + G < n_in ? lo + G : n_in;   // children [lo, hi)
     X run = X::inf(), tot = X::inf();
     if (LEVEL1) {
         // weights 1..g: tot accumulates run after every add
@@ -330,6 +331,17 @@ msm_tree_kernel(const typename C::X* __restrict__ in_R, const typename C::X* __r
     }
     out_R[gid] = run;
     out_V[gid] = tot;
+}
+template <class C, int LOG_G>
+static void msm_tree_launch(bool level1, size_t nodes, cudaStream_t stream, const typename C::X* inR, const typename C::X* inV,
+                            uint32_t n_in, uint32_t n_out, uint32_t segs, int log_span, typename C::X* outR, typename C::X* outV) {
+    if (level1) {
+        auto k = msm_tree_kernel<C, 1, LOG_G>;
+        G16_LAUNCH(k, div_up(nodes, 128), 128, 0, stream, false, inR, inV, n_in, n_out, segs, log_span, outR, outV);
+    } else {
+        auto k = msm_tree_kernel<C, 0, LOG_G>;
+        G16_LAUNCH(k, div_up(nodes, 128), 128, 0, stream, false, inR, inV, n_in, n_out, segs, log_span, outR, outV);
+    }
 }
 
 // Horner over windows: out[row] = sum_w 2^(c*w) * S[row][w]   (S = the V of the tree roots)
@@ -451,30 +463,30 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     }
     G16_CUDA(cudaMemcpyAsync(ws.entry_log.p + ws.log_n, ws.total.p, 4, cudaMemcpyDeviceToDevice, stream));
     ws.log_n++;
-    // reduction tree
+    // reduction tree. Arity 32 minimises the work (2 + 3/32 additions per bucket) and is used whenever its first level
+    // has enough nodes to fill the machine; a small problem (a single proof: 16384 buckets -> 512 nodes) is bound by the
+    // serial chain inside a node instead (2 x arity additions per level), so it gets arity 4 and more, shorter levels.
     const uint32_t segs = sh.rows * sh.segs_per_row();
     uint32_t n_in = (uint32_t)sh.nbk;
+    const int log_g = ((size_t)segs * ((n_in + MSM_TREE_G - 1) / MSM_TREE_G) < (size_t)148 * 256) ? MSM_TREE_LOG_G_SMALL : MSM_TREE_LOG_G;
     const X* inR = ws.buckets.p;
     const X* inV = nullptr;
     int level = 1, log_span = 0, pp = 0;
     while (true) {
-        uint32_t n_out = (n_in + MSM_TREE_G - 1) / MSM_TREE_G;
+        uint32_t n_out = (n_in + (1u << log_g) - 1) >> log_g;
         ws.lvlR[pp].ensure((size_t)segs * n_out);
         ws.lvlV[pp].ensure((size_t)segs * n_out);
-        if (level == 1) {
-            auto k = msm_tree_kernel<C, 1>;
-            G16_LAUNCH(k, div_up((size_t)segs * n_out, 128), 128, 0, stream, false, inR, inV, n_in, n_out, segs, log_span,
-                       ws.lvlR[pp].p, ws.lvlV[pp].p);
-        } else {
-            auto k = msm_tree_kernel<C, 0>;
-            G16_LAUNCH(k, div_up((size_t)segs * n_out, 128), 128, 0, stream, false, inR, inV, n_in, n_out, segs, log_span,
-                       ws.lvlR[pp].p, ws.lvlV[pp].p);
-        }
+        if (log_g == MSM_TREE_LOG_G)
+            msm_tree_launch<C, MSM_TREE_LOG_G>(level == 1, (size_t)segs * n_out, stream, inR, inV, n_in, n_out, segs, log_span,
+                                               ws.lvlR[pp].p, ws.lvlV[pp].p);
+        else
+            msm_tree_launch<C, MSM_TREE_LOG_G_SMALL>(level == 1, (size_t)segs * n_out, stream, inR, inV, n_in, n_out, segs, log_span,
+                                                     ws.lvlR[pp].p, ws.lvlV[pp].p);
         ws.launches++;
         inR = ws.lvlR[pp].p;
         inV = ws.lvlV[pp].p;
         n_in = n_out;
-        log_span += 5;   // log2(MSM_TREE_G)
+        log_span += log_g;
         level++;
         pp ^= 1;
         if (n_out == 1) break;

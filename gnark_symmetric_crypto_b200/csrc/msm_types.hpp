@@ -17,7 +17,8 @@ struct MsmShape {
 };
 
 static const uint32_t MSM_INVALID = 0xFFFFFFFFu;
-static const int MSM_TREE_G = 32;   // arity of the bucket-reduction tree
+static const int MSM_TREE_LOG_G = 5, MSM_TREE_G = 1 << MSM_TREE_LOG_G;   // arity of the bucket-reduction tree (throughput)
+static const int MSM_TREE_LOG_G_SMALL = 2;                              // arity for small problems (latency)
 
 template <class C>
 struct MsmWorkspace {

@@ -43,7 +43,7 @@ struct AssemblyKeys {
     const G2Affine* delta2_tab;   // device: j*16^i*delta2
 };
 struct AssemblyScratch {
-    DevBuf<G1XYZZ> Ar, Bs1, sAr, rBs1;
+    DevBuf<G1XYZZ> Ar, Bs1, nrsd, win_tab;   // win_tab: 15 window multiples per variable-base product (2 per proof)
 };
 
 // all pointers are device pointers
@@ -61,10 +61,14 @@ size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, uint3
 int launch_solver_init(const SolverProgram& sp, uint32_t n_instr, uint32_t n_coeffs, Fr* ucoef_inv, cudaStream_t st);
 // builds the 64 x 15 fixed-base tables of delta / delta2 (device buffers owned by the caller)
 void launch_fixed_base_tables(const AssemblyKeys& keys, G1Affine* tab1, G2Affine* tab2, cudaStream_t st);
-// three launches; returns the launch count
-size_t launch_assemble(const AssemblyKeys& keys, AssemblyScratch& sc, bool with_commitment, uint32_t n, const G1XYZZ* mA, const G1XYZZ* mB1,
-                       const G1XYZZ* mK, const G1XYZZ* mZ, const G2XYZZ* mB2, const Fr* rs, uint8_t* out, size_t out_stride,
+void launch_fixed_base_table_g1(const G1Affine& base, G1Affine* tab, cudaStream_t st);   // k_assemble.cu
+// G1 half of the assembly (Ar, Krs, trailer): two launches; returns the launch count. The G2 element Bs is written by
+// launch_assemble_g2, which only needs the G2 MSM result and may run on another stream.
+size_t launch_assemble(const AssemblyKeys& keys, AssemblyScratch& sc, bool with_commitment, uint32_t n, const G1XYZZ* mA,
+                       const G1XYZZ* mB1, const G1XYZZ* mK, const G1XYZZ* mZ, const Fr* rs, uint8_t* out, size_t out_stride,
                        cudaStream_t st);
+void launch_assemble_g2(const AssemblyKeys& keys, uint32_t n, const G2XYZZ* mB2, const Fr* rs, uint8_t* out, size_t out_stride,
+                        cudaStream_t st);
 // AES-CTR witness (provers.go:172-227): key_len 16 or 32; W wire-major
 void launch_aes_witness(const uint8_t* keys, uint32_t key_len, const uint8_t* nonces, const uint32_t* counters,
                         const uint8_t* inputs, uint32_t n, Fr* W, size_t w_stride, uint8_t* ct_out, cudaStream_t st);

@@ -2,29 +2,15 @@
 //   * point decompression of the proving key            (replaces gnark marshal.go:311-348 ProvingKey.readFrom — a19)
 //   * ChaCha20 witness assignment                        (replaces provers.go:79-142 + utils/bytes.go:11-47 — a3..a6)
 //   (the batched R1CS solver lives in solver.cuh / k_solver.cu)
-//   * proof assembly + serialisation                     (replaces prove.go:174-295 tail, marshal.go:32-59 — a16, a18)
+//   (proof assembly + serialisation live in assemble.cuh / k_assemble.cu, a hot translation unit)
 #pragma once
+#include "fixed_base.cuh"
 #include "prover_api.hpp"
+#include "serialize.cuh"
 
 namespace g16 {
 
 // ------------------------------------------------------------------------------------------------ decompression
-FD Fp fp_from_be32(const uint8_t* b, bool mask_flags) {
-    Fp v;
-    for (int i = 0; i < 8; i++) {
-        const uint8_t* q = b + 28 - 4 * i;
-        v.l[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
-    }
-    if (mask_flags) v.l[7] &= 0x3FFFFFFFu;
-    return v.to_mont();
-}
-FD void fp_to_be32(const Fp& m, uint8_t* b) {
-    Fp c = m.from_mont();
-    for (int i = 0; i < 8; i++) {
-        uint8_t* q = b + 28 - 4 * i;
-        q[0] = (uint8_t)(c.l[i] >> 24); q[1] = (uint8_t)(c.l[i] >> 16); q[2] = (uint8_t)(c.l[i] >> 8); q[3] = (uint8_t)c.l[i];
-    }
-}
 FD Fp fp_three() { Fp o = Fp::one(); return o + o + o; }
 FD Fp2 g2_coeff_b() {   // 3/(9+u)
     Fp o = Fp::one();
@@ -95,18 +81,6 @@ __global__ void decompress_g2_kernel(const uint8_t* __restrict__ in, uint32_t n,
     bool want_largest = flag == 0xC0;
     if (y.lex_largest() != want_largest) y = y.neg();
     out[i] = {x, y};
-}
-
-FD void g1_compress(const G1Affine& p, uint8_t* out) {
-    if (p.is_inf()) { for (int i = 0; i < 32; i++) out[i] = 0; out[0] = 0x40; return; }
-    fp_to_be32(p.x, out);
-    out[0] |= p.y.lex_largest() ? 0xC0 : 0x80;
-}
-FD void g2_compress(const G2Affine& p, uint8_t* out) {
-    if (p.is_inf()) { for (int i = 0; i < 64; i++) out[i] = 0; out[0] = 0x40; return; }
-    fp_to_be32(p.x.a1, out);
-    fp_to_be32(p.x.a0, out + 32);
-    out[0] |= p.y.lex_largest() ? 0xC0 : 0x80;
 }
 
 // big-endian 32-byte canonical scalars -> Fr canonical limbs (NOT Montgomery)
@@ -379,6 +353,21 @@ __global__ void assemble_commitment_kernel(const G1Affine* __restrict__ commit_a
     g1_compress(pok[i].to_affine(), o + 164);
 }
 
+// G2 proof element: Bs = msmB2 + beta2 + s*delta2, compressed straight into bytes [32, 96) of the proof (Appendix C, F.1).
+// grid n, block 64 (the fixed-base product is a depth-6 tree, see fixed_base.cuh). Runs on the side stream, right behind
+// the G2 MSM it consumes, so it is off the critical path of the G1 assembly.
+__global__ void __launch_bounds__(FB_WINDOWS)
+assemble_g2_kernel(AssemblyKeys keys, uint32_t n, const G2XYZZ* __restrict__ mB2, const Fr* __restrict__ rs,
+                   uint8_t* __restrict__ out, size_t out_stride) {
+    __shared__ G2XYZZ sm[FB_WINDOWS];
+    const uint32_t i = blockIdx.x;
+    G2XYZZ v = fixed_base_mul_block<G2>(keys.delta2_tab, rs[2 * i + 1], sm);
+    if (threadIdx.x) return;
+    v.add(mB2[i]);
+    v.madd(keys.beta2, false);
+    g2_compress(v.to_affine(), out + (size_t)i * out_stride + 32);
+}
+
 // wire-major W -> one row of nb_wires values per witness (test / gnark-shaped output only)
 __global__ void wires_to_rows_kernel(const Fr* __restrict__ W, size_t w_stride, uint32_t batch, uint32_t nb_wires,
                                      Fr* __restrict__ out) {
@@ -386,113 +375,6 @@ __global__ void wires_to_rows_kernel(const Fr* __restrict__ W, size_t w_stride, 
     if (gid >= (size_t)batch * nb_wires) return;
     uint32_t i = (uint32_t)(gid % batch), k = (uint32_t)(gid / batch);
     out[(size_t)i * nb_wires + k] = W[(size_t)k * w_stride + i];
-}
-
-// ------------------------------------------------------------------------------------------------ proof assembly
-// 
-//   Ar  = msmA + alpha + r*delta          Bs1 = msmB1 + beta + s*delta        Bs = msmB2 + beta2 + s*delta2
-//   Krs = msmK + msmZ + s*Ar + r*Bs1 - (r*s)*delta
-// delta, delta2 are fixed: their multiples j*16^i*delta (i < 64, 1 <= j <= 15) are tabulated at init, so k*delta is at most
-// 64 mixed additions and no doubling. The work of one proof is spread over three launches x several roles (blockIdx.y)
-// so that the longest serial chain is one 254-bit double-and-add instead of six.
-
-static const int FB_WINDOWS = 64, FB_ENTRIES = 15;
-
-// tab[i*15 + (j-1)] = j * 16^i * base  (affine). One thread per window.
-template <class C>
-__global__ void fixed_base_table_kernel(typename C::A base, typename C::A* __restrict__ tab) {
-    typedef typename C::X X;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= FB_WINDOWS) return;
-    X b = X::from_affine(base);
-    for (int d = 0; d < 4 * i; d++) b = b.dbl();
-    X acc = b;
-    tab[i * FB_ENTRIES] = acc.to_affine();
-    for (int j = 1; j < FB_ENTRIES; j++) {
-        acc.add(b);
-        tab[i * FB_ENTRIES + j] = acc.to_affine();
-    }
-}
-template <class C>
-FD typename C::X fixed_base_mul(const typename C::A* __restrict__ tab, Scalar256 k) {
-    typename C::X acc = C::X::inf();
-#pragma unroll
-    for (int wi = 0; wi < 8; wi++) {
-        uint32_t word = k.w[wi];
-#pragma unroll 1
-        for (int j = 0; j < 8; j++) {
-            uint32_t nib = (word >> (4 * j)) & 15u;
-            if (nib) acc.madd(tab[(wi * 8 + j) * FB_ENTRIES + (nib - 1)], false);
-        }
-    }
-    return acc;
-}
-FD Scalar256 scalar_of(const Fr& k) {
-    Scalar256 s;
-    for (int i = 0; i < 8; i++) s.w[i] = k.l[i];
-    return s;
-}
-
-// rs: canonical limbs, r at [2i], s at [2i+1].
-// phase 1, role (blockIdx.y) 0: Ar ; 1: Bs1 ; 2: Bs (compressed straight into the proof)
-__global__ void __launch_bounds__(64)
-assemble_phase1_kernel(AssemblyKeys keys, uint32_t n, const G1XYZZ* __restrict__ mA, const G1XYZZ* __restrict__ mB1,
-                       const G2XYZZ* __restrict__ mB2, const Fr* __restrict__ rs, G1XYZZ* __restrict__ Ar_out,
-                       G1XYZZ* __restrict__ Bs1_out, uint8_t* __restrict__ out, size_t out_stride) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t role = blockIdx.y;
-    if (role == 0) {
-        G1XYZZ v = fixed_base_mul<G1>(keys.delta_tab, scalar_of(rs[2 * i]));
-        v.add(mA[i]);
-        v.madd(keys.alpha, false);
-        Ar_out[i] = v;
-    } else if (role == 1) {
-        G1XYZZ v = fixed_base_mul<G1>(keys.delta_tab, scalar_of(rs[2 * i + 1]));
-        v.add(mB1[i]);
-        v.madd(keys.beta, false);
-        Bs1_out[i] = v;
-    } else {
-        G2XYZZ v = fixed_base_mul<G2>(keys.delta2_tab, scalar_of(rs[2 * i + 1]));
-        v.add(mB2[i]);
-        v.madd(keys.beta2, false);
-        g2_compress(v.to_affine(), out + (size_t)i * out_stride + 32);
-    }
-}
-// phase 2, role 0: s*Ar ; 1: r*Bs1
-__global__ void __launch_bounds__(64)
-assemble_phase2_kernel(uint32_t n, const G1XYZZ* __restrict__ Ar, const G1XYZZ* __restrict__ Bs1, const Fr* __restrict__ rs,
-                       G1XYZZ* __restrict__ sAr, G1XYZZ* __restrict__ rBs1) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (blockIdx.y == 0) sAr[i] = scalar_mul(Ar[i], scalar_of(rs[2 * i + 1]));
-    else rBs1[i] = scalar_mul(Bs1[i], scalar_of(rs[2 * i]));
-}
-// phase 3: Krs, compression of Ar and Krs, trailer of Proof.WriteTo without commitments (Appendix C)
-__global__ void __launch_bounds__(64)
-assemble_phase3_kernel(AssemblyKeys keys, uint32_t n, int with_commitment, const G1XYZZ* __restrict__ mK,
-                       const G1XYZZ* __restrict__ mZ, const G1XYZZ* __restrict__ Ar, const G1XYZZ* __restrict__ sAr,
-                       const G1XYZZ* __restrict__ rBs1, const Fr* __restrict__ rs, uint8_t* __restrict__ out, size_t out_stride) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint8_t* o = out + (size_t)i * out_stride;
-    if (blockIdx.y == 1) {
-        g1_compress(Ar[i].to_affine(), o);
-        if (!with_commitment) {   // u32 0 commitments | infinity PoK
-            o[128] = 0; o[129] = 0; o[130] = 0; o[131] = 0;
-            o[132] = 0x40;
-            for (int k = 133; k < 164; k++) o[k] = 0;
-        }
-        return;
-    }
-    Fr r = rs[2 * i], s = rs[2 * i + 1];
-    Fr rsm = (r.to_mont() * s.to_mont()).from_mont();
-    G1XYZZ Krs = fixed_base_mul<G1>(keys.delta_tab, scalar_of(rsm)).neg();
-    Krs.add(mK[i]);
-    Krs.add(mZ[i]);
-    Krs.add(sAr[i]);
-    Krs.add(rBs1[i]);
-    g1_compress(Krs.to_affine(), o + 96);
 }
 
 }  // namespace g16

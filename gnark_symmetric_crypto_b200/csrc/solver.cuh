@@ -74,6 +74,36 @@ __device__ __forceinline__ Fr eval_le(const SolverProgram& sp, const Fr* __restr
     return acc;
 }
 
+// Tail of an R1C once the three linear expressions are known without the solved wire's terms (their coefficients are
+// summed in ucoef): solve for the wire (solver.go:540-586), or check L*R == O, and emit the constraint's A/B/C values.
+__device__ __forceinline__ void r1c_finish(const SolverProgram& sp, const InsMeta& m, uint32_t ins, Fr sL, Fr sR, Fr sO,
+                                           const Fr& ucoef, Fr* __restrict__ W, size_t ws, Fr* __restrict__ A,
+                                           Fr* __restrict__ B, Fr* __restrict__ C, uint32_t* status) {
+    uint32_t uside = (m.kind >> 8) & 0xFF;
+    if (m.solve_wire != SOLVE_WIRE_NONE) {
+        Fr w;
+        Fr kinv = sp.ucoef_inv[ins];
+        if (uside == 2) {
+            w = (sL * sR - sO) * kinv;
+            sO = sO + ucoef * w;
+        } else if (uside == 0) {
+            if (sR.is_zero()) { atomicOr(status, 2u); w = Fr::zero(); }
+            else w = (sO * sR.inv() - sL) * kinv;
+            sL = sL + ucoef * w;
+        } else {
+            if (sL.is_zero()) { atomicOr(status, 2u); w = Fr::zero(); }
+            else w = (sO * sL.inv() - sR) * kinv;
+            sR = sR + ucoef * w;
+        }
+        W[(size_t)m.solve_wire * ws] = w;
+    } else if (sL * sR != sO) {
+        atomicOr(status, 1u);
+    }
+    A[m.cons_off] = sL;
+    B[m.cons_off] = sR;
+    C[m.cons_off] = sO;
+}
+
 // executes instruction `ins` for one witness. status bits: 1 unsatisfied constraint, 2 division by zero, 4 unsupported
 __device__ __forceinline__ void solve_instruction(const SolverProgram& sp, uint32_t ins, Fr* __restrict__ W, size_t ws,
                                                   Fr* __restrict__ A, Fr* __restrict__ B, Fr* __restrict__ C,
@@ -92,28 +122,7 @@ __device__ __forceinline__ void solve_instruction(const SolverProgram& sp, uint3
         acc_terms(sp, W, ws, pos, nR, (solves && uside == 1) ? m.solve_wire : SOLVE_WIRE_NONE, sR, (uside == 1) ? ucoef : unused);
         pos += 2 * nR;
         acc_terms(sp, W, ws, pos, nO, (solves && uside == 2) ? m.solve_wire : SOLVE_WIRE_NONE, sO, (uside == 2) ? ucoef : unused);
-        if (solves) {
-            Fr w;
-            Fr kinv = sp.ucoef_inv[ins];
-            if (uside == 2) {
-                w = (sL * sR - sO) * kinv;
-                sO = sO + ucoef * w;
-            } else if (uside == 0) {
-                if (sR.is_zero()) { atomicOr(status, 2u); w = Fr::zero(); }
-                else w = (sO * sR.inv() - sL) * kinv;
-                sL = sL + ucoef * w;
-            } else {
-                if (sL.is_zero()) { atomicOr(status, 2u); w = Fr::zero(); }
-                else w = (sO * sL.inv() - sR) * kinv;
-                sR = sR + ucoef * w;
-            }
-            W[(size_t)m.solve_wire * ws] = w;
-        } else if (sL * sR != sO) {
-            atomicOr(status, 1u);
-        }
-        A[m.cons_off] = sL;
-        B[m.cons_off] = sR;
-        C[m.cons_off] = sO;
+        r1c_finish(sp, m, ins, sL, sR, sO, ucoef, W, ws, A, B, C, status);
     } else if (kind == 1) {
         uint32_t hid = sp.calldata[base + 1], nin = sp.calldata[base + 2];
         uint32_t pos = base + 3;
@@ -201,6 +210,103 @@ solver_level_kernel(SolverProgram sp, uint32_t lo, uint32_t hi, uint32_t batch, 
     solve_instruction(sp, sp.level_instr[k], W + inst, w_stride, A + (size_t)inst * sp.n_dom,
                       B + (size_t)inst * sp.n_dom, C + (size_t)inst * sp.n_dom, status);
 }
+
+#if !defined(G16_EMU)
+// ------------------------------------------------------------------------------------------------ small batches
+// Latency path (a single Prove request): with fewer witnesses than lanes the kernel above leaves
+// 31 lanes idle and walks the 130-term adder expressions serially. Here a warp owns one (instruction, witness) pair and
+// its lanes split the TERMS; the partial sums meet in a shuffle butterfly. Field addition is exact and commutative, so
+// the result is bit-identical to the serial walk.
+__device__ __forceinline__ Fr warp_sum(Fr v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Fr o;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.l[i] = __shfl_xor_sync(0xffffffffu, v.l[i], off);
+        v = v + o;
+    }
+    return v;
+}
+__device__ __forceinline__ Fr term_value(const SolverProgram& sp, const Fr* __restrict__ W, size_t ws, uint32_t cid, uint32_t wid) {
+    if (wid == WIRE_CONST) return sp.coeffs[cid];
+    if (wid >= sp.n_wires) return Fr::zero();
+    Fr w = W[(size_t)wid * ws];
+    if (sp.fast_coeffs && cid <= 4) {
+        switch (cid) {
+            case 0: return Fr::zero();
+            case 1: return w;
+            case 2: return w.dbl();
+            case 3: return w.neg();
+            default: return w.dbl().neg();
+        }
+    }
+    const Fr c = sp.coeffs[cid];
+    if (w.is_zero()) return Fr::zero();
+    if (w == Fr::one()) return c;
+    return c * w;
+}
+// linear expression at calldata[pos] (nt | nt x (cid, wid)), terms split over the lanes; every lane returns the sum
+__device__ __forceinline__ Fr eval_le_warp(const SolverProgram& sp, const Fr* __restrict__ W, size_t ws, uint32_t& pos, uint32_t lane) {
+    uint32_t nt = sp.calldata[pos++];
+    Fr acc = Fr::zero();
+    for (uint32_t t = lane; t < nt; t += 32) acc = acc + term_value(sp, W, ws, sp.calldata[pos + 2 * t], sp.calldata[pos + 2 * t + 1]);
+    pos += 2 * nt;
+    return warp_sum(acc);   // lanes without a term hold zero
+}
+FD uint32_t fr_limb(const Fr& v, uint32_t i) {   // static indexing only (no local-memory array)
+    uint32_t r = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) r = (i == k) ? v.l[k] : r;
+    return r;
+}
+// grid.x covers the instructions of the level (blockDim.y warps per block), grid.y the witnesses
+__global__ void __launch_bounds__(32 * SOLVER_WARPS)
+solver_level_small_kernel(SolverProgram sp, uint32_t lo, uint32_t hi, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B,
+                          Fr* C, uint32_t* status) {
+    const uint32_t lane = threadIdx.x, inst = blockIdx.y;
+    const uint32_t k = lo + blockIdx.x * blockDim.y + threadIdx.y;
+    if (inst >= batch || k >= hi) return;   // warp-uniform
+    if (sp.randomize) sp.randomize += inst;
+    const uint32_t ins = sp.level_instr[k];
+    W += inst;
+    A += (size_t)inst * sp.n_dom; B += (size_t)inst * sp.n_dom; C += (size_t)inst * sp.n_dom;
+    const size_t ws = w_stride;
+    const InsMeta m = sp.meta[ins];
+    const uint32_t kind = m.kind & 0xFF, base = m.cd_start;
+    if (kind == 0) {
+        const uint32_t nL = sp.calldata[base + 1], nR = sp.calldata[base + 2], nO = sp.calldata[base + 3];
+        const uint32_t uside = (m.kind >> 8) & 0xFF;
+        const bool solves = m.solve_wire != SOLVE_WIRE_NONE;
+        Fr sL = Fr::zero(), sR = Fr::zero(), sO = Fr::zero(), ucoef = Fr::zero();
+        const uint32_t total = nL + nR + nO;
+        for (uint32_t t = lane; t < total; t += 32) {
+            const uint32_t side = t < nL ? 0u : (t < nL + nR ? 1u : 2u);
+            const uint32_t cid = sp.calldata[base + 4 + 2 * t], wid = sp.calldata[base + 5 + 2 * t];
+            if (solves && side == uside && wid == m.solve_wire) { ucoef = ucoef + sp.coeffs[cid]; continue; }
+            const Fr v = term_value(sp, W, ws, cid, wid);
+            if (side == 0) sL = sL + v;
+            else if (side == 1) sR = sR + v;
+            else sO = sO + v;
+        }
+        if (nL) sL = warp_sum(sL);
+        if (nR) sR = warp_sum(sR);
+        if (nO) sO = warp_sum(sO);
+        if (solves) ucoef = warp_sum(ucoef);
+        if (lane == 0) r1c_finish(sp, m, ins, sL, sR, sO, ucoef, W, ws, A, B, C, status);
+    } else if (kind == 1 && sp.calldata[base + 1] == HINT_NBITS && sp.calldata[base + 2] == 1) {
+        uint32_t pos = base + 3;
+        const Fr v = eval_le_warp(sp, W, ws, pos, lane).from_mont();
+        const uint32_t o0 = sp.calldata[pos], o1 = sp.calldata[pos + 1];
+        const Fr one = Fr::one(), zero = Fr::zero();
+        for (uint32_t b = lane; b < o1 - o0; b += 32) {
+            const uint32_t word = b < 256 ? fr_limb(v, b >> 5) : 0u;
+            W[(size_t)(o0 + b) * ws] = ((word >> (b & 31)) & 1u) ? one : zero;
+        }
+    } else if (lane == 0) {
+        solve_instruction(sp, ins, W, ws, A, B, C, status);   // lookups, countHint, Randomize: serial on one lane
+    }
+}
+#endif
 
 // per instruction: 1 / (sum of coefficients of the wire it solves)   (init-time)
 __global__ void solver_ucoef_kernel(SolverProgram sp, uint32_t n_instr, Fr* __restrict__ out) {

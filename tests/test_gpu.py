@@ -155,9 +155,15 @@ def test_solver_and_h_match_oracle(G, gpu_ctx, oracle, oracle_prover, kat):
         inputs, _ = oracle.chacha_assignment(k, n, c, i)
         wit.append(oracle.to_mont(1, oracle.ints_to_limbs(inputs[1:])))
         refs.append(oracle_prover.cs.solve(inputs))
+    # batch 4 takes the term-parallel kernel (a warp per instruction and witness, single-request latency path), batch 36
+    # the witness-parallel one (a lane per witness): both must reproduce the oracle's wires and A/B/C evaluations
     W, A, B, Cc = gpu_ctx.solve(np.stack(wit), batch=4)
     for j in range(4):
         for got, ref in zip((W[j], A[j], B[j], Cc[j]), refs[j]):
+            assert np.array_equal(got, ref)
+    W, A, B, Cc = gpu_ctx.solve(np.stack(wit * 9), batch=36)
+    for j in range(36):
+        for got, ref in zip((W[j], A[j], B[j], Cc[j]), refs[j % 4]):
             assert np.array_equal(got, ref)
     n = gpu_ctx.n
     h = gpu_ctx.compute_h(refs[0][1], refs[0][2], refs[0][3])
@@ -167,6 +173,9 @@ def test_solver_and_h_match_oracle(G, gpu_ctx, oracle, oracle_prover, kat):
     with pytest.raises(G.ProverError) as e:
         gpu_ctx.solve(bad, batch=4)
     assert e.value.rc == 4   # G16_ERR_UNSAT
+    with pytest.raises(G.ProverError) as e:
+        gpu_ctx.solve(np.concatenate([bad] * 9), batch=36)
+    assert e.value.rc == 4
 
 
 def test_kat_proof_msm_points_and_h(G, gpu_ctx, oracle, oracle_prover, oracle_vk, kat):
