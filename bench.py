@@ -263,6 +263,20 @@ def run_gpu(args):
     e2e_total_ms, _ = aggregate(e2e_ms, BATCH * args.steps, dev)
     assert np.array_equal(pproofs.numpy(), ref_proofs), "device-resident and end-to-end paths disagree"
 
+    # ---------------- single-request latency (BASELINE config 1: what one libprove Prove call costs), rank 0 only
+    single = None
+    if rank == 0:
+        one = [x[:1] for x in (keys, nonces, ctrs, ins, rs)]
+        for _ in range(3):
+            ctx.prove_chacha_batch(*one)
+        lat = []
+        for _ in range(20):
+            t0 = time.perf_counter(); p1, _c1 = ctx.prove_chacha_batch(*one); lat.append((time.perf_counter() - t0) * 1e3)
+        assert p1[0] == ref_proofs[:ctx.proof_bytes].tobytes(), "single-request and batched paths disagree"
+        single = {"ms_median": statistics.median(lat), "ms_min": min(lat), "stages_ms": ctx.stage_ms(),
+                  "path": "g16_prove_chacha_batch, n = 1, host buffers in, proof bytes out (wall clock)"}
+    barrier()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -312,7 +326,12 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel<G1>", "achieved": achieved, "peak": peak,
-                         "unit": "TIMAD/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "unit": "TIMAD/s", "frac": (achieved / peak) if achieved else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch (Z query of a 512-proof sub-batch) from the
+                         # ncu --set full capture in profiles/ncu_full_r01.txt; algorithmic bytes of that launch: 2.28 GB sorted
+                         # entries + 1.07 GB bucket sums + 1.18 GB chunk-edge partials = 4.5 GB
+                         "traffic": 4.303e9 if (sched["sub_batch"] == 512 and BATCH == 1024) else None,
+                         "traffic_unit": "bytes per launch (profiles/ncu_full_r01.txt)",
                          "note": "achieved = Z-query G1 mixed additions x 2640 algorithmic 32-bit IMAD / accumulate-stage time (CUDA events "
                                  "on the launching stream, sum over launches, same schedule and inputs as the timed region, "
                                  "taken in the steps that follow it); "
@@ -321,6 +340,7 @@ def run_gpu(args):
                          "imad_wide_peak": imad["imad_wide_per_s"] / 1e12, "modmul_per_s": imad["modmul_per_s"]},
             "roofline_ntt": ntt_roof,
             "stages_ms_per_step": {kk: v / args.steps for kk, v in stages.items() if kk != "launches"},
+            "single_request": single,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -43,7 +43,7 @@ struct Ctx {
     DevBuf<InsMeta> d_meta;
     DevBuf<Fr> d_coeffs, d_ucoef_inv, d_lookup_tabs;
     SolverProgram sp;
-    std::vector<uint32_t> h_level_off;
+    std::vector<uint32_t> h_level_off, h_level_split;   // split: first "long" instruction of each level (see ctx_create)
     bool solver_supported = true;
     std::string solver_unsupported_reason;
     // BSB22 commitment (AES circuits): at most one commitment is supported
@@ -323,15 +323,32 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
             }
         }
         for (uint32_t w = 0; w < cx->nb_wires; w++) if (!solved[w]) throw ParseError("r1cs: wire " + std::to_string(w) + " is never defined");
-        std::vector<uint32_t> lvl_instr, lvl_off(1, 0);
+        // Inside a level the instructions are independent, so they may be reordered: those whose linear expressions are
+        // long (the 33-bit adder recompositions of ChaCha: ~130 terms) are moved to the end of their level and solved by the
+        // term-parallel kernel (a warp per instruction and witness), the short ones by the witness-parallel kernel. The
+        // level time is then bounded by a ~16-term chain instead of a 130-term one.
+        const uint32_t long_terms = (uint32_t)env_int("G16_SOLVER_LONG", 24);
+        auto n_terms = [&](uint32_t id) -> uint32_t {
+            uint64_t s0 = cs.start[id];
+            uint8_t kind = cs.bp_kind[cs.bp_id[id]];
+            if (kind == INS_R1C) return cd[s0 + 1] + cd[s0 + 2] + cd[s0 + 3];
+            if (kind == INS_HINT && cd[s0 + 1] == HINT_NBITS && cd[s0 + 2] == 1) return cd[s0 + 3];
+            return 0;   // lookups and the other hints stay on the witness-parallel kernel
+        };
+        std::vector<uint32_t> lvl_instr, lvl_off(1, 0), lvl_split;
         for (auto& lv : cs.levels) {
+            std::vector<uint32_t> longs;
             for (uint32_t id : lv) {
                 if (id >= cs.n_instr()) throw ParseError("r1cs: level references unknown instruction");
                 if (id == cx->bsb_ins) cx->bsb_level = (uint32_t)(lvl_off.size() - 1);
-                lvl_instr.push_back(id);
+                if (n_terms(id) > long_terms) longs.push_back(id);
+                else lvl_instr.push_back(id);
             }
+            lvl_split.push_back((uint32_t)lvl_instr.size());
+            lvl_instr.insert(lvl_instr.end(), longs.begin(), longs.end());
             lvl_off.push_back((uint32_t)lvl_instr.size());
         }
+        cx->h_level_split = lvl_split;
         if (lvl_instr.size() != cs.n_instr()) throw ParseError("r1cs: levels do not cover every instruction exactly once");
         // lookup tables: entry k of table t = coeffs[cid] of the single constant term of that entry (pure gather)
         std::vector<uint64_t> tabs((size_t)(ntab ? ntab : 1) * 256 * 4, 0);
@@ -428,14 +445,14 @@ static size_t ctx_solve(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaStream_
     Fr* B = cx.Bev.p + sb * cx.n_dom;
     Fr* C = cx.Cev.p + sb * cx.n_dom;
     if (!cx.n_commit)
-        return launch_solver(sp, cx.h_level_off.data(), 0, cx.nlevels, rows, W, n, A, B, C, cx.d_status.p, st);
-    size_t launches = launch_solver(sp, cx.h_level_off.data(), 0, cx.bsb_level + 1, rows, W, n, A, B, C, cx.d_status.p, st);
+        return launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), 0, cx.nlevels, rows, W, n, A, B, C, cx.d_status.p, st);
+    size_t launches = launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), 0, cx.bsb_level + 1, rows, W, n, A, B, C, cx.d_status.p, st);
     for (size_t o = 0; o < rows; o += cx.sub_batch) {
         uint32_t r = (uint32_t)((rows - o) < cx.sub_batch ? (rows - o) : cx.sub_batch);
         run_query_g1(wsc, st, cx.qPed, W + o, 1, n, true, r, cx.resCommit.p + sb + o, nullptr);
     }
     launch_bsb22_challenge(cx.resCommit.p + sb, rows, W, n, cx.commit_wire, cx.commit_aff.p + sb, st);
-    launches += 1 + launch_solver(sp, cx.h_level_off.data(), cx.bsb_level + 1, cx.nlevels, rows, W, n, A, B, C, cx.d_status.p, st);
+    launches += 1 + launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), cx.bsb_level + 1, cx.nlevels, rows, W, n, A, B, C, cx.d_status.p, st);
     return launches;
 }
 

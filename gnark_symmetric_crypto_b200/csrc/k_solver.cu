@@ -5,33 +5,38 @@
 
 namespace g16 {
 
-size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, uint32_t lev_begin, uint32_t lev_end, uint32_t batch,
-                     Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C, uint32_t* status, cudaStream_t st) {
+size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, const uint32_t* h_level_split, uint32_t lev_begin,
+                     uint32_t lev_end, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C, uint32_t* status,
+                     cudaStream_t st) {
     const uint32_t groups = div_up(batch, 32);
     size_t launches = 0;
     if (lev_end > sp.nlevels) lev_end = sp.nlevels;
 #if !defined(G16_EMU)
-    // few witnesses: lanes split the terms of an instruction instead of the witnesses (G16_SOLVER_SMALL = largest such batch)
-    static const uint32_t small_max = [] { const char* v = getenv("G16_SOLVER_SMALL"); return (uint32_t)(v && *v ? atoi(v) : 8); }();
+    // few witnesses: every instruction goes to the term-parallel kernel (G16_SOLVER_SMALL = largest such batch)
+    static const uint32_t small_max = [] { const char* v = getenv("G16_SOLVER_SMALL"); return (uint32_t)(v && *v ? atoi(v) : 16); }();
     const bool small = batch <= small_max;
-#else
-    const bool small = false;
 #endif
     for (uint32_t lev = lev_begin; lev < lev_end; lev++) {
         uint32_t lo = h_level_off[lev], hi = h_level_off[lev + 1];
-        if (hi == lo) continue;
-        if (small) {
+        uint32_t split = hi;   // [lo, split) witness-parallel, [split, hi) term-parallel
 #if !defined(G16_EMU)
-            dim3 grid(div_up(hi - lo, SOLVER_WARPS), batch);
-            G16_LAUNCH(solver_level_small_kernel, grid, dim3(32, SOLVER_WARPS), 0, st, false, sp, lo, hi, batch, W, w_stride, A, B,
-                       C, status);
+        if (small) split = lo;
+        else if (h_level_split) split = h_level_split[lev];
 #endif
-        } else {
-            dim3 grid(div_up(hi - lo, SOLVER_WARPS), groups);
-            G16_LAUNCH(solver_level_kernel, grid, dim3(32, SOLVER_WARPS), 0, st, false, sp, lo, hi, batch, W, w_stride, A, B, C,
+        if (split > lo) {
+            dim3 grid(div_up(split - lo, SOLVER_WARPS), groups);
+            G16_LAUNCH(solver_level_kernel, grid, dim3(32, SOLVER_WARPS), 0, st, false, sp, lo, split, batch, W, w_stride, A, B, C,
                        status);
+            launches++;
         }
-        launches++;
+#if !defined(G16_EMU)
+        if (hi > split) {
+            dim3 grid(div_up(hi - split, SOLVER_WARPS), batch);
+            G16_LAUNCH(solver_level_small_kernel, grid, dim3(32, SOLVER_WARPS), 0, st, false, sp, split, hi, batch, W, w_stride, A,
+                       B, C, status);
+            launches++;
+        }
+#endif
     }
     G16_CHECK_LAUNCH();
     return launches;

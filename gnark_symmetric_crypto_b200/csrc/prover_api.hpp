@@ -53,9 +53,11 @@ void launch_scalars_from_be(const uint8_t* in, uint32_t n, Fr* out, cudaStream_t
 void launch_chacha_witness(const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters, const uint8_t* inputs,
                            uint32_t n, Fr* W, size_t w_stride, uint8_t* ct_out, cudaStream_t st);
 void launch_witness_copy(const Fr* witness, uint32_t n_witness, uint32_t batch, Fr* W, size_t w_stride, cudaStream_t st);
-// h_level_off: host copy of the level offsets (nlevels + 1). Returns the number of kernel launches.
+// h_level_off: host copy of the level offsets (nlevels + 1); h_level_split[l] in [off[l], off[l+1]]: instructions from there
+// to the end of level l have long linear expressions (term-parallel kernel). Returns the number of kernel launches.
 // runs levels [lev_begin, lev_end)
-size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, uint32_t lev_begin, uint32_t lev_end, uint32_t batch,
+size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, const uint32_t* h_level_split, uint32_t lev_begin,
+                     uint32_t lev_end, uint32_t batch,
                      Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C, uint32_t* status, cudaStream_t st);
 // fills ucoef_inv (n_instr entries) and returns whether coefficient ids 0..4 are 0,1,2,-1,-2 (synchronises the stream)
 int launch_solver_init(const SolverProgram& sp, uint32_t n_instr, uint32_t n_coeffs, Fr* ucoef_inv, cudaStream_t st);
