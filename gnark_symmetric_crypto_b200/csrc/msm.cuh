@@ -17,6 +17,7 @@
 // Points are read with 128-bit loads (64 B / 128 B affine points are 16-byte aligned).
 #pragma once
 #include "msm_types.hpp"
+#include <cstdlib>
 
 namespace g16 {
 
@@ -397,7 +398,8 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
         // enough chunks to fill the machine a few times over, but not shorter than 8 / longer than 64 entries
         size_t want_threads = 148 * 512 * 4;
         size_t l = max_entries / want_threads;
-        L = l < 8 ? 8 : (l > 64 ? 64 : (int)l);
+        static const int lmax = [] { const char* v = getenv("G16_MSM_LMAX"); return v && *v ? atoi(v) : 64; }();
+        L = l < 8 ? 8 : (l > (size_t)lmax ? lmax : (int)l);
     }
     const size_t max_chunks = (max_entries + L - 1) / L;
     const size_t ntiles = (nbuckets + SCAN_T * SCAN_I - 1) / (SCAN_T * SCAN_I);
