@@ -2,6 +2,8 @@
 // nothing propagates across the ABI. There is no CPU fallback: without a CUDA device these functions return G16_ERR_CUDA.
 #include "../../include/g16b200.h"
 #include "g16_ctx.cuh"
+#include "g16_verify.cuh"
+#include "pairing_api.hpp"
 #include <mutex>
 #include <random>
 
@@ -9,6 +11,11 @@ using namespace g16;
 
 struct g16_ctx {
     std::unique_ptr<Ctx> cx;
+    std::mutex mu;
+};
+
+struct g16_vctx {
+    std::unique_ptr<VCtx> v;
     std::mutex mu;
 };
 
@@ -530,6 +537,58 @@ int g16_msm(int group, const uint64_t* points, const uint64_t* scalars, int scal
     g16_msm_plan_free(p);
     t_last_error = keep;
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ verifier
+int g16_verify_init(const uint8_t* vk, size_t vk_len, int device, g16_vctx** out) {
+    return guarded([&] {
+        REQUIRE(vk && vk_len && out, "NULL argument");
+        *out = nullptr;
+        require_device();
+        std::unique_ptr<g16_vctx> c(new g16_vctx());
+        c->v = vctx_create(vk, vk_len, device);
+        *out = c.release();
+    });
+}
+void g16_verify_free(g16_vctx* ctx) { delete ctx; }
+int g16_verify_info(const g16_vctx* ctx, uint64_t info[4]) {
+    return guarded([&] {
+        REQUIRE(ctx && info, "NULL argument");
+        info[0] = ctx->v->n_public; info[1] = ctx->v->n_commit; info[2] = ctx->v->proof_bytes(); info[3] = ctx->v->nK;
+    });
+}
+int g16_verify_batch(g16_vctx* ctx, size_t n, const uint8_t* proofs, const void* public_inputs, int public_format,
+                     uint8_t* ok_out, float* device_ms) {
+    return guarded([&] {
+        REQUIRE(ctx && proofs && ok_out, "NULL argument");
+        REQUIRE(public_inputs || ctx->v->n_public == 0, "NULL public inputs");
+        REQUIRE(n > 0 && n <= (1u << 20), "batch size out of range");
+        REQUIRE(public_format == 0 || public_format == 1, "public_format must be 0 (Montgomery limbs) or 1 (big-endian bytes)");
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        float ms = vctx_verify_batch(*ctx->v, n, proofs, public_inputs, public_format, ok_out);
+        if (device_ms) *device_ms = ms;
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ stage-level: pairing
+int g16_pairing_check(const uint64_t* g1_points, const uint64_t* g2_points, size_t pairs_per_check, size_t n_checks,
+                      uint8_t* ok_out) {
+    return guarded([&] {
+        REQUIRE(g1_points && g2_points && ok_out, "NULL argument");
+        REQUIRE(pairs_per_check >= 1 && pairs_per_check <= 64 && n_checks >= 1 && pairs_per_check * n_checks <= (1u << 20),
+                "pairing check: sizes out of range");
+        require_device();
+        const size_t np = pairs_per_check * n_checks;
+        DevBuf<G1Affine> P;
+        DevBuf<G2Affine> Q;
+        DevBuf<uint8_t> ok(n_checks);
+        P.upload((const G1Affine*)g1_points, np);
+        Q.upload((const G2Affine*)g2_points, np);
+        PairingWorkspace ws;
+        pairing_check_run(ws, P.p, Q.p, (uint32_t)pairs_per_check, (uint32_t)n_checks, ok.p, 0);
+        ok.download(ok_out, n_checks);
+        G16_CUDA(cudaStreamSynchronize(0));
+    });
 }
 
 // ------------------------------------------------------------------------------------------------ stage-level: NTT

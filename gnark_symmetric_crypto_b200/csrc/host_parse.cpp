@@ -60,6 +60,39 @@ PkFile parse_pk(const uint8_t* data, size_t len) {
     return pk;
 }
 
+VkFile parse_vk(const uint8_t* data, size_t len) {
+    Rd r{data, len};
+    VkFile vk;
+    vk.alpha = r.take(32, "G1.Alpha");
+    vk.beta1 = r.take(32, "G1.Beta");
+    vk.beta2 = r.take(64, "G2.Beta");
+    vk.gamma2 = r.take(64, "G2.Gamma");
+    vk.delta1 = r.take(32, "G1.Delta");
+    vk.delta2 = r.take(64, "G2.Delta");
+    vk.nK = r.be32("len(G1.K)");
+    if (vk.nK == 0 || vk.nK > (1u << 24)) throw ParseError("vk: implausible len(G1.K)");
+    vk.K = r.take((size_t)vk.nK * 32, "G1.K");
+    uint32_t outer = r.be32("len(PublicAndCommitmentCommitted)");
+    if (outer > 16) throw ParseError("vk: implausible number of commitments");
+    for (uint32_t i = 0; i < outer; i++) {
+        uint32_t inner = r.be32("len(PublicAndCommitmentCommitted[i])");
+        if (inner > vk.nK) throw ParseError("vk: implausible committed list");
+        std::vector<uint64_t> v(inner);
+        for (uint32_t k = 0; k < inner; k++) v[k] = r.be64("committed index");
+        vk.public_and_commitment_committed.push_back(v);
+    }
+    uint32_t nkeys = r.be32("len(CommitmentKeys)");
+    if (nkeys != outer) throw ParseError("vk: commitment keys do not match the commitment list");
+    for (uint32_t i = 0; i < nkeys; i++) {
+        VkFile::PedVk k;
+        k.g = r.take(64, "Pedersen vk G");
+        k.g_root_sigma_neg = r.take(64, "Pedersen vk GRootSigmaNeg");
+        vk.ped.push_back(k);
+    }
+    if (r.off != len) throw ParseError("vk: trailing bytes");
+    return vk;
+}
+
 // ------------------------------------------------------------------------------------------------ intcomp streams
 namespace {
 

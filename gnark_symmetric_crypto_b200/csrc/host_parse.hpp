@@ -37,6 +37,21 @@ struct PkFile {
 };
 PkFile parse_pk(const uint8_t* data, size_t len);
 
+// verifying key — layout of SURVEY.md Appendix B (gnark VerifyingKey.WriteTo; libraries/verifier/impl/verify_impl.go:36-58)
+struct VkFile {
+    const uint8_t* alpha = nullptr;    // G1, 32 B compressed
+    const uint8_t* beta1 = nullptr;    // G1
+    const uint8_t* beta2 = nullptr;    // G2, 64 B compressed
+    const uint8_t* gamma2 = nullptr;
+    const uint8_t* delta1 = nullptr;   // G1
+    const uint8_t* delta2 = nullptr;
+    const uint8_t* K = nullptr; uint32_t nK = 0;
+    std::vector<std::vector<uint64_t>> public_and_commitment_committed;
+    struct PedVk { const uint8_t* g; const uint8_t* g_root_sigma_neg; };   // two compressed G2 points per commitment key
+    std::vector<PedVk> ped;
+};
+VkFile parse_vk(const uint8_t* data, size_t len);
+
 enum InstrKind : uint8_t { INS_R1C = 0, INS_HINT = 1, INS_LOOKUP = 2 };
 
 struct CommitmentInfo {

@@ -101,6 +101,20 @@ void launch_fixed_base_tables(const AssemblyKeys& keys, G1Affine* tab1, G2Affine
     G16_LAUNCH(k2, 1, FB_WINDOWS, 0, st, false, keys.delta2, tab2);
     G16_CHECK_LAUNCH();
 }
+void launch_verify_unpack(const VerifyKeys& keys, const uint8_t* proofs, size_t stride, uint32_t n, G1Affine* P, G2Affine* Q,
+                          G1Affine* P2, G2Affine* Q2, G1Affine* commit, uint32_t* bad, cudaStream_t st) {
+    G16_LAUNCH(verify_unpack_kernel, dim3(div_up(n, 32), keys.n_commit ? 5 : 3), 32, 0, st, false, keys, proofs, stride, n, P, Q, P2, Q2,
+               commit, bad);
+    G16_CHECK_LAUNCH();
+}
+void launch_verify_ksum(const G1XYZZ* msm, const G1Affine* commit, uint32_t n, G1Affine* P, cudaStream_t st) {
+    G16_LAUNCH(verify_ksum_kernel, div_up(n, 32), 32, 0, st, false, msm, commit, n, P);
+    G16_CHECK_LAUNCH();
+}
+void launch_verify_verdict(const uint8_t* ok1, const uint8_t* ok2, const uint32_t* bad, uint32_t n, uint8_t* out, cudaStream_t st) {
+    G16_LAUNCH(verify_verdict_kernel, div_up(n, 128), 128, 0, st, false, ok1, ok2, bad, n, out);
+    G16_CHECK_LAUNCH();
+}
 void launch_assemble_g2(const AssemblyKeys& keys, uint32_t n, const G2XYZZ* mB2, const Fr* rs, uint8_t* out, size_t out_stride,
                         cudaStream_t st) {
     G16_LAUNCH(assemble_g2_kernel, n, FB_WINDOWS, 0, st, true, keys, n, mB2, rs, out, out_stride);

@@ -81,6 +81,16 @@ void launch_bsb22_challenge(const G1XYZZ* commit, uint32_t n, Fr* W, size_t w_st
 // proof trailer with one commitment: u32 1 | C | PoK (Appendix C) at byte 128 of each proof
 void launch_assemble_commitment(const G1Affine* commit_aff, const G1XYZZ* pok, uint32_t n, uint8_t* out, size_t out_stride,
                                 cudaStream_t st);
+// groth16.Verify: unpack n proofs (stride bytes apart) into the pairing inputs (see prover_kernels.cuh), kSum, verdict
+struct VerifyKeys {
+    G1Affine alpha;
+    G2Affine beta2, gamma2, delta2, ped_g, ped_gneg;
+    uint32_t n_commit;
+};
+void launch_verify_unpack(const VerifyKeys& keys, const uint8_t* proofs, size_t stride, uint32_t n, G1Affine* P, G2Affine* Q,
+                          G1Affine* P2, G2Affine* Q2, G1Affine* commit, uint32_t* bad, cudaStream_t st);
+void launch_verify_ksum(const G1XYZZ* msm, const G1Affine* commit, uint32_t n, G1Affine* P, cudaStream_t st);
+void launch_verify_verdict(const uint8_t* ok1, const uint8_t* ok2, const uint32_t* bad, uint32_t n, uint8_t* out, cudaStream_t st);
 void launch_g1_affine_to_xyzz(const G1Affine* in, uint32_t n, G1XYZZ* out, cudaStream_t st);
 void launch_wires_to_rows(const Fr* W, size_t w_stride, uint32_t batch, uint32_t nb_wires, Fr* out, cudaStream_t st);
 // stage-level test entry points

@@ -30,33 +30,29 @@ FD void fp_exponent(int which, uint32_t e[8]) {
     for (int i = 0; i < 8; i++) e[i] = (t[i] >> sh) | (i < 7 ? (t[i + 1] << (32 - sh)) : 0u);
 }
 
-// in: 32-byte compressed G1 points; out: affine Montgomery. err: bit 0 = not on curve, bit 1 = bad flag
-__global__ void decompress_g1_kernel(const uint8_t* __restrict__ in, uint32_t n, G1Affine* __restrict__ out,
-                                     uint32_t* __restrict__ err) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint8_t* b = in + (size_t)i * 32;
+// one compressed point -> affine Montgomery. Returns 0, or error bits: 1 = not on the curve, 2 = bad flag bits
+// (gnark-crypto ecc/bn254/marshal.go: 0b10 smallest y, 0b11 largest y, 0b01 infinity, 0b00 = uncompressed, not accepted here)
+FD uint32_t decompress_g1_point(const uint8_t* b, G1Affine& out) {
+    out = G1Affine::inf();
     uint8_t flag = b[0] & 0xC0;
-    if (flag == 0x40) { out[i] = G1Affine::inf(); return; }
-    if (flag == 0x00) { atomicOr(err, 2u); out[i] = G1Affine::inf(); return; }
+    if (flag == 0x40) return 0;
+    if (flag == 0x00) return 2;
     Fp x = fp_from_be32(b, true);
     Fp rhs = x.sqr() * x + fp_three();
     uint32_t e[8];
     fp_exponent(0, e);
     Fp y = rhs.pow(e);
-    if (y.sqr() != rhs) { atomicOr(err, 1u); out[i] = G1Affine::inf(); return; }
+    if (y.sqr() != rhs) return 1;
     bool want_largest = flag == 0xC0;
     if (y.lex_largest() != want_largest) y = y.neg();
-    out[i] = {x, y};
+    out = {x, y};
+    return 0;
 }
-__global__ void decompress_g2_kernel(const uint8_t* __restrict__ in, uint32_t n, G2Affine* __restrict__ out,
-                                     uint32_t* __restrict__ err) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint8_t* b = in + (size_t)i * 64;
+FD uint32_t decompress_g2_point(const uint8_t* b, G2Affine& out) {
+    out = G2Affine::inf();
     uint8_t flag = b[0] & 0xC0;
-    if (flag == 0x40) { out[i] = G2Affine::inf(); return; }
-    if (flag == 0x00) { atomicOr(err, 2u); out[i] = G2Affine::inf(); return; }
+    if (flag == 0x40) return 0;
+    if (flag == 0x00) return 2;
     Fp2 x = {fp_from_be32(b + 32, false), fp_from_be32(b, true)};   // X.A1 || X.A0
     Fp2 a = x.sqr() * x + g2_coeff_b();
     Fp2 y;
@@ -76,11 +72,31 @@ __global__ void decompress_g2_kernel(const uint8_t* __restrict__ in, uint32_t n,
             Fp2 bb = (Fp2::one() + alpha).pow(e);
             y = bb * x0;
         }
-        if (y.sqr() != a) { atomicOr(err, 1u); out[i] = G2Affine::inf(); return; }
+        if (y.sqr() != a) return 1;
     }
     bool want_largest = flag == 0xC0;
     if (y.lex_largest() != want_largest) y = y.neg();
-    out[i] = {x, y};
+    out = {x, y};
+    return 0;
+}
+// in: 32-byte compressed G1 points; out: affine Montgomery. err: bit 0 = not on curve, bit 1 = bad flag
+__global__ void decompress_g1_kernel(const uint8_t* __restrict__ in, uint32_t n, G1Affine* __restrict__ out,
+                                     uint32_t* __restrict__ err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine p;
+    uint32_t e = decompress_g1_point(in + (size_t)i * 32, p);
+    if (e) atomicOr(err, e);
+    out[i] = p;
+}
+__global__ void decompress_g2_kernel(const uint8_t* __restrict__ in, uint32_t n, G2Affine* __restrict__ out,
+                                     uint32_t* __restrict__ err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G2Affine p;
+    uint32_t e = decompress_g2_point(in + (size_t)i * 64, p);
+    if (e) atomicOr(err, e);
+    out[i] = p;
 }
 
 // big-endian 32-byte canonical scalars -> Fr canonical limbs (NOT Montgomery)
@@ -375,6 +391,71 @@ __global__ void wires_to_rows_kernel(const Fr* __restrict__ W, size_t w_stride, 
     if (gid >= (size_t)batch * nb_wires) return;
     uint32_t i = (uint32_t)(gid % batch), k = (uint32_t)(gid / batch);
     out[(size_t)i * nb_wires + k] = W[(size_t)k * w_stride + i];
+}
+
+// ------------------------------------------------------------------------------------------------ groth16.Verify
+// (gnark v0.11.0 backend/groth16/bn254/verify.go, reached from libraries/verifier/impl/verifiers.go:93-99,139-145; SURVEY
+// Appendix C for the proof bytes, F.4 for the equation.)
+// Per proof i the pairing inputs are  P[4i..] = (-Ar, alpha, kSum, Krs),  Q[4i..] = (Bs, beta2, gamma2, delta2), and with one
+// BSB22 commitment  P2[2i..] = (C, PoK),  Q2[2i..] = (G, GRootSigmaNeg).
+// role (blockIdx.y) 0: Ar + the fixed entries + the commitment count of the proof trailer ; 1: Krs ; 2: Bs ; 3: C ; 4: PoK.
+// bad[i] != 0 marks a malformed proof (flag bits, point not on its curve, wrong commitment count): it is rejected whatever
+// the pairing says. (G2 points are checked to be on the twist; the subgroup check gnark's decoder adds is not done.)
+__global__ void verify_unpack_kernel(VerifyKeys keys, const uint8_t* __restrict__ proofs, size_t stride, uint32_t n,
+                                     G1Affine* __restrict__ P, G2Affine* __restrict__ Q, G1Affine* __restrict__ P2,
+                                     G2Affine* __restrict__ Q2, G1Affine* __restrict__ commit, uint32_t* __restrict__ bad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* pr = proofs + (size_t)i * stride;
+    const uint32_t role = blockIdx.y;
+    uint32_t e = 0;
+    if (role == 0) {
+        G1Affine a;
+        e = decompress_g1_point(pr, a);
+        a.y = a.y.neg();
+        P[4 * (size_t)i] = a;
+        P[4 * (size_t)i + 1] = keys.alpha;
+        Q[4 * (size_t)i + 1] = keys.beta2;
+        Q[4 * (size_t)i + 2] = keys.gamma2;
+        Q[4 * (size_t)i + 3] = keys.delta2;
+        uint32_t cnt = ((uint32_t)pr[128] << 24) | ((uint32_t)pr[129] << 16) | ((uint32_t)pr[130] << 8) | pr[131];
+        if (cnt != keys.n_commit) e |= 4;
+        if (keys.n_commit) { Q2[2 * (size_t)i] = keys.ped_g; Q2[2 * (size_t)i + 1] = keys.ped_gneg; }
+    } else if (role == 1) {
+        G1Affine c;
+        e = decompress_g1_point(pr + 96, c);
+        P[4 * (size_t)i + 3] = c;
+    } else if (role == 2) {
+        G2Affine b;
+        e = decompress_g2_point(pr + 32, b);
+        Q[4 * (size_t)i] = b;
+    } else if (role == 3) {
+        G1Affine c;
+        e = decompress_g1_point(pr + 132, c);
+        P2[2 * (size_t)i] = c;
+        commit[i] = c;
+    } else {
+        G1Affine c;
+        e = decompress_g1_point(pr + 164, c);
+        P2[2 * (size_t)i + 1] = c;
+    }
+    if (e) atomicOr(&bad[i], e);
+}
+// kSum_i = sum_k pub_k K_k (the MSM result, XYZZ) + the commitment point, affine, into P[4i + 2]
+__global__ void verify_ksum_kernel(const G1XYZZ* __restrict__ msm, const G1Affine* __restrict__ commit, uint32_t n,
+                                   G1Affine* __restrict__ P) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1XYZZ v = msm[i];
+    if (commit) v.madd(commit[i], false);
+    P[4 * (size_t)i + 2] = v.to_affine();
+}
+// verdict = both pairing products are one and the proof was well-formed
+__global__ void verify_verdict_kernel(const uint8_t* __restrict__ ok1, const uint8_t* __restrict__ ok2, const uint32_t* __restrict__ bad,
+                                      uint32_t n, uint8_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = (ok1[i] && (!ok2 || ok2[i]) && !bad[i]) ? 1 : 0;
 }
 
 }  // namespace g16

@@ -322,6 +322,69 @@ def bsb22_challenge(commitments: np.ndarray) -> np.ndarray:
     return out
 
 
+class Groth16Verifier:
+    """One verifying key resident on one GPU: batched groth16.Verify (libraries/verifier/impl/verifiers.go:87-99,133-145)."""
+
+    def __init__(self, vk: bytes, device: int = 0):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        _check(self._L.g16_verify_init(vk, len(vk), device, C.byref(self._h)))
+        info = np.zeros(4, dtype=np.uint64)
+        _check(self._L.g16_verify_info(self._h, _p64(info)))
+        self.n_public, self.n_commitments, self.proof_bytes, self.nK = [int(x) for x in info]
+        self.last_ms = 0.0
+
+    def close(self):
+        if self._h:
+            self._L.g16_verify_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def verify_batch(self, proofs, public_inputs) -> np.ndarray:
+        """proofs: list of proof byte strings. public_inputs: per proof either a list of ints (sent as 32-byte big-endian
+        values) or, as one array [n, n_public, 4] of u64, gnark's in-memory Montgomery elements. -> bool array."""
+        n = len(proofs)
+        if any(len(p) != self.proof_bytes for p in proofs):
+            raise ValueError(f"every proof must be {self.proof_bytes} bytes")
+        pr = np.frombuffer(b"".join(proofs), dtype=np.uint8).copy()
+        if isinstance(public_inputs, np.ndarray):
+            pub = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(n, self.n_public, 4)
+            fmt = 0
+        else:
+            if any(len(v) != self.n_public for v in public_inputs):
+                raise ValueError(f"every proof needs {self.n_public} public inputs")
+            pub = np.frombuffer(b"".join(int(x).to_bytes(32, "big") for v in public_inputs for x in v), dtype=np.uint8).copy()
+            fmt = 1
+        ok = np.zeros(n, dtype=np.uint8)
+        ms = C.c_float(0)
+        _check(self._L.g16_verify_batch(self._h, n, _p8(pr), pub.ctypes.data_as(C.c_void_p), fmt, _p8(ok), C.byref(ms)))
+        self.last_ms = ms.value
+        return ok.astype(bool)
+
+    def verify(self, proof: bytes, public_inputs) -> bool:
+        return bool(self.verify_batch([proof], [public_inputs])[0])
+
+
+def pairing_check(g1s: np.ndarray, g2s: np.ndarray, pairs_per_check: int | None = None) -> np.ndarray:
+    """prod_j e(P_j, Q_j) == 1 for every group of `pairs_per_check` consecutive pairs (default: one check over all pairs).
+    Points affine Montgomery ([n, 8] / [n, 16] u64). Returns a bool array, one entry per check."""
+    P = np.ascontiguousarray(g1s, dtype=np.uint64).reshape(-1, 8)
+    Q = np.ascontiguousarray(g2s, dtype=np.uint64).reshape(-1, 16)
+    if len(P) != len(Q) or not len(P):
+        raise ValueError("need as many G1 as G2 points (at least one)")
+    ppc = len(P) if pairs_per_check is None else int(pairs_per_check)
+    if ppc < 1 or len(P) % ppc:
+        raise ValueError("pairs_per_check must divide the number of pairs")
+    ok = np.zeros(len(P) // ppc, dtype=np.uint8)
+    _check(_lib.load().g16_pairing_check(_p64(P), _p64(Q), ppc, len(ok), _p8(ok)))
+    return ok.astype(bool)
+
+
 def msm(group: int, points: np.ndarray, scalars: np.ndarray, scalars_mont: bool = False, window: int = 0):
     """-> (affine result, [total, accumulate, sort, reduce] ms)"""
     w = 8 if group == 1 else 16

@@ -111,6 +111,27 @@ int g16_group_op(int group, int op, const uint64_t* a, const uint64_t* b, uint64
 /* decompression of gnark-crypto compressed points (32 / 64 bytes each) -> affine Montgomery */
 int g16_decompress(int group, const uint8_t* in, uint64_t* out, size_t n);
 
+/* ---- verifier: groth16.Verify for batches of proofs of one verifying key.
+ * Replaces gnark v0.11.0 backend/groth16/bn254/verify.go Verify + VerifyingKey.ReadFrom as used by
+ * libraries/verifier/impl/verify_impl.go:36-58 and verifiers.go:87-99,133-145.
+ * vk: the bytes of VerifyingKey.WriteTo (vk.chacha20 / vk.aes128 / vk.aes256). proofs: n x proof_bytes (Proof.WriteTo, 164 B
+ * without / 196 B with one BSB22 commitment). public_inputs: n x n_public field elements (the public witness without ONE),
+ * public_format 0 = gnark in-memory fr.Element (4 x u64 LE Montgomery), 1 = 32-byte big-endian canonical.
+ * ok_out[i] = 1 iff proof i is accepted; malformed proofs are rejected (0), they do not fail the call. */
+typedef struct g16_vctx g16_vctx;
+int g16_verify_init(const uint8_t* vk, size_t vk_len, int device, g16_vctx** out);
+int g16_verify_info(const g16_vctx* ctx, uint64_t info[4]);   /* n_public, n_commitments, proof_bytes, len(G1.K) */
+int g16_verify_batch(g16_vctx* ctx, size_t n, const uint8_t* proofs, const void* public_inputs, int public_format,
+                     uint8_t* ok_out, float* device_ms);
+void g16_verify_free(g16_vctx* ctx);
+
+/* Pairing product check, the arithmetic under groth16.Verify (gnark-crypto v0.14.0 ecc/bn254 PairingCheck, called by gnark
+ * v0.11.0 backend/groth16/bn254/verify.go from libraries/verifier/impl/verifiers.go:93-99,139-145).
+ * ok_out[c] = 1 iff prod_{j < pairs_per_check} e(P[c*ppc + j], Q[c*ppc + j]) == 1. Points: affine Montgomery, G1 8 x u64,
+ * G2 16 x u64 (x.a0 x.a1 y.a0 y.a1), (0,0) = infinity (such a pair contributes 1). */
+int g16_pairing_check(const uint64_t* g1_points, const uint64_t* g2_points, size_t pairs_per_check, size_t n_checks,
+                      uint8_t* ok_out);
+
 /* Pippenger MSM over n affine points (replaces (*G1Jac).MultiExp / (*G2Jac).MultiExp).
  * scalars: n x 4 u64; scalars_mont != 0 if they are in Montgomery form (gnark passes fr.Element vectors).
  * window = 0 picks c automatically. out = affine result. timing (optional): ms[0] total device time,

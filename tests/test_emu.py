@@ -229,3 +229,27 @@ def test_aes_witness_and_bsb22_hash(emu, oracle):
     ok(emu, emu.g16_bsb22_challenge(p64(pts), 9, p64(out)))
     ref = oracle.to_mont(1, oracle.ints_to_limbs([S.hash_to_fr(S.g1_uncompressed(p), b"bsb22-commitment") for p in pts]))
     assert np.array_equal(out, ref)
+
+
+def _bilinear_pairs(oracle, rng, k):
+    """k pairs (a_i G1, b_i G2) plus one closing pair (-(sum a_i b_i) G1, G2): their pairing product is 1."""
+    R = oracle.R_MOD
+    a = [int(x) for x in rng.integers(1, 1 << 62, k)]; b = [int(x) for x in rng.integers(1, 1 << 62, k)]
+    g1 = oracle.g1_fixed_base(oracle.ints_to_limbs(a + [(-sum(x * y for x, y in zip(a, b))) % R]))
+    g2 = oracle.g2_fixed_base(oracle.ints_to_limbs(b + [1]))
+    return g1, g2
+
+
+def test_pairing_check(emu, oracle):
+    """Kernel logic of the pairing product check (Miller loop lines, block-cooperative Fp12 product, final exponentiation)
+    against the oracle's pairing: a bilinear identity is accepted, a perturbed one rejected."""
+    rng = np.random.default_rng(12)
+    g1, g2 = _bilinear_pairs(oracle, rng, 1)
+    assert oracle.pairing_check(g1, g2)
+    bad1 = g1.copy(); bad1[0] = oracle.g1_fixed_base(oracle.ints_to_limbs([5]))[0]
+    assert not oracle.pairing_check(bad1, g2)
+    P = np.concatenate([g1, bad1]); Q = np.concatenate([g2, g2])
+    out = np.full(2, 7, dtype=np.uint8)
+    ok(emu, emu.g16_pairing_check(p64(P), p64(Q), 2, 2, p8(out)))
+    assert out.tolist() == [1, 0]
+    assert emu.g16_pairing_check(p64(P), p64(Q), 0, 2, p8(out)) == 1   # G16_ERR_ARG

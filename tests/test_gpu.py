@@ -246,3 +246,23 @@ def test_batch_1024_config4(G, gpu_ctx, oracle, oracle_prover, oracle_vk):
     # sub-batching must not matter: proving request 5 alone gives the same bytes
     p5, _ = gpu_ctx.prove_chacha_batch(keys[5:6], nonces[5:6], ctrs[5:6], ins[5:6], rs[5:6])
     assert p5[0] == proofs[5]
+
+
+def test_pairing_check_matches_oracle(G, oracle):
+    """SURVEY §8f rank 4 (the arithmetic under groth16.Verify): products of 1..4 pairings that are 1 by bilinearity are
+    accepted, perturbed ones rejected, infinity pairs contribute 1 — the same verdicts as the oracle's pairing."""
+    rng = np.random.default_rng(99)
+    R = oracle.R_MOD
+    Ps, Qs, want = [], [], []
+    for k in (1, 3):
+        a = [int(x) for x in rng.integers(1, 1 << 62, k)]; b = [int(x) for x in rng.integers(1, 1 << 62, k)]
+        g1 = oracle.g1_fixed_base(oracle.ints_to_limbs(a + [(-sum(x * y for x, y in zip(a, b))) % R] + [0] * (3 - k)))
+        g2 = oracle.g2_fixed_base(oracle.ints_to_limbs(b + [1] + [7] * (3 - k)))   # padding pairs: P = infinity
+        for flip in (False, True):
+            p = g1.copy()
+            if flip:
+                p[0] = oracle.g1_fixed_base(oracle.ints_to_limbs([a[0] + 1]))[0]
+            Ps.append(p); Qs.append(g2); want.append(not flip)
+            assert oracle.pairing_check(p[:k + 1], g2[:k + 1]) == (not flip)
+    got = G.pairing_check(np.concatenate(Ps), np.concatenate(Qs), pairs_per_check=4)
+    assert got.tolist() == want
