@@ -71,6 +71,8 @@ EXPORTS = {
     "InitAlgorithm": (C.c_ubyte, [C.c_ubyte, GoSlice, GoSlice]),
     "Free": (None, [C.c_void_p]),
     "Prove": (ProveReturn, [GoSlice]),
+    "InitVerifier": (C.c_ubyte, [C.c_ubyte, GoSlice]),
+    "Verify": (C.c_ubyte, [GoSlice]),
 }
 
 

@@ -1,3 +1,4 @@
+// Outer ABI, verifier side: `Verify` of libraries/verifier/libverify.go:14-17 (+ InitVerifier, see below).
 // Outer ABI: the four cgo exports of the reference's c-shared library libraries/prover/libprove.go
 // (enforce_binding :17-18, InitAlgorithm :20-23, Free :25-28, Prove :30-47) and the JSON layer of
 // libraries/prover/impl/prove_impl.go:116-143 / provers.go:53-59,79-89 restated in C++ (no Go toolchain on this box),
@@ -19,6 +20,7 @@ namespace {
 
 const char* const ALG_NAMES[3] = {"chacha20", "aes-128-ctr", "aes-256-ctr"};   // prove_impl.go:15-25
 g16_ctx* g_provers[3] = {nullptr, nullptr, nullptr};
+g16_vctx* g_verifiers[3] = {nullptr, nullptr, nullptr};   // libraries/verifier/impl/verify_impl.go:24 `verifiers`
 std::mutex g_mu;
 
 struct Panic : std::runtime_error {
@@ -204,11 +206,122 @@ std::string prove_impl(const uint8_t* params, size_t len) {
            b64encode(ct.data(), ct.size()) + "\"}";
 }
 
+// ---- libraries/verifier: InputVerifyParams (verify_impl.go:18-22) and the public-witness layouts of verifiers.go:50-152
+struct VerifyParams {
+    std::string cipher;
+    std::vector<uint8_t> proof, signals;
+};
+VerifyParams parse_verify_params(const uint8_t* data, size_t len) {
+    Json j{(const char*)data, (const char*)data + len};
+    VerifyParams vp;
+    j.expect('{');
+    if (!j.eat('}')) {
+        do {
+            std::string k = j.str();
+            j.expect(':');
+            if (k == "cipher") vp.cipher = j.str();
+            else if (k == "proof") vp.proof = read_bytes(j);
+            else if (k == "publicSignals") vp.signals = read_bytes(j);
+            else j.skip_value();
+        } while (j.eat(','));
+        j.expect('}');
+    }
+    return vp;
+}
+void push_be32(std::vector<uint8_t>& out, uint32_t v) {   // one field element, 32-byte big-endian
+    out.insert(out.end(), 28, 0);
+    out.push_back((uint8_t)(v >> 24)); out.push_back((uint8_t)(v >> 16)); out.push_back((uint8_t)(v >> 8)); out.push_back((uint8_t)v);
+}
+void push_word_bits(std::vector<uint8_t>& out, uint32_t w) {   // utils.Uint32ToBits: LSB first
+    for (int b = 0; b < 32; b++) push_be32(out, (w >> b) & 1u);
+}
+uint32_t rd_le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+uint32_t rd_be32(const uint8_t* p) { return (uint32_t)p[3] | ((uint32_t)p[2] << 8) | ((uint32_t)p[1] << 16) | ((uint32_t)p[0] << 24); }
+
+bool verify_impl(const uint8_t* params, size_t len) {
+    VerifyParams vp = parse_verify_params(params, len);
+    int alg = -1;
+    for (int i = 0; i < 3; i++) if (vp.cipher == ALG_NAMES[i]) alg = i;
+    if (alg < 0) return false;   // verify_impl.go:78-81
+    g16_vctx* ctx;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        ctx = g_verifiers[alg];
+    }
+    if (!ctx) { printf("verifying key is not initialized for cipher: %s\n", vp.cipher.c_str()); return false; }
+    if (vp.signals.size() != 128 + 12 + 4) {   // verifiers.go:52-55,105-107: ciphertext | nonce | counter | plaintext
+        printf("public signals must be 144 bytes, not %zu\n", vp.signals.size());
+        return false;
+    }
+    uint64_t info[4];
+    if (g16_verify_info(ctx, info)) return false;
+    if (vp.proof.size() < info[2]) { printf("unexpected EOF\n"); return false; }   // Proof.ReadFrom on a short buffer
+    const uint8_t* ct = vp.signals.data();
+    const uint8_t* nonce = ct + 64;
+    const uint8_t* counter = nonce + 12;
+    const uint8_t* pt = counter + 4;
+    std::vector<uint8_t> pub;
+    pub.reserve((size_t)info[0] * 32);
+    if (alg == 0) {
+        // ChaChaCircuit public fields in declaration order: Counter, Nonce[3], In[16], Out[16] (words as LSB-first bits);
+        // In / Out words big-endian, Nonce / Counter little-endian (verifiers.go:59-85, utils/bytes.go:11-47)
+        push_word_bits(pub, rd_le32(counter));
+        for (int k = 0; k < 3; k++) push_word_bits(pub, rd_le32(nonce + 4 * k));
+        for (int k = 0; k < 16; k++) push_word_bits(pub, rd_be32(pt + 4 * k));
+        for (int k = 0; k < 16; k++) push_word_bits(pub, rd_be32(ct + 4 * k));
+    } else {
+        // AESWrapper public fields: Nonce[12], Counter (big-endian u32), Plaintext[64], Ciphertext[64] (verifiers.go:109-127)
+        for (int k = 0; k < 12; k++) push_be32(pub, nonce[k]);
+        push_be32(pub, rd_be32(counter));
+        for (int k = 0; k < 64; k++) push_be32(pub, pt[k]);
+        for (int k = 0; k < 64; k++) push_be32(pub, ct[k]);
+    }
+    if (pub.size() != (size_t)info[0] * 32) { printf("verifying key does not match cipher %s\n", vp.cipher.c_str()); return false; }
+    uint8_t ok = 0;
+    int rc = g16_verify_batch(ctx, 1, vp.proof.data(), pub.data(), 1, &ok, nullptr);
+    if (rc) { printf("%s\n", g16_last_error()); return false; }
+    return ok != 0;
+}
+
 }  // namespace
 
 extern "C" {
 
 void enforce_binding(void) {}
+
+// The reference embeds its three verifying keys with go:embed (verify_impl.go:26-33) and parses them in init() (:35-62); a C
+// library receives the same bytes once per cipher instead.
+unsigned char InitVerifier(unsigned char algorithmID, GoSlice_g16 verifyingKey) {
+    if (algorithmID > 2) return 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_verifiers[algorithmID]) return 1;
+    if (!verifyingKey.data || verifyingKey.len <= 0) {
+        printf("error reading verifying key: empty input\n");
+        return 0;
+    }
+    int device = 0;
+    if (const char* d = getenv("G16_DEVICE")) device = atoi(d);
+    g16_vctx* ctx = nullptr;
+    int rc = g16_verify_init((const uint8_t*)verifyingKey.data, (size_t)verifyingKey.len, device, &ctx);
+    if (rc) {
+        printf("error reading verifying key: %s\n", g16_last_error());
+        return 0;
+    }
+    g_verifiers[algorithmID] = ctx;
+    return 1;
+}
+
+// libraries/verifier/libverify.go:14-17 + impl/verify_impl.go:64-82: any failure (bad JSON, unknown cipher, malformed proof,
+// a recovered panic) is `false`
+unsigned char Verify(GoSlice_g16 params) {
+    try {
+        if (!params.data || params.len <= 0) return 0;
+        return verify_impl((const uint8_t*)params.data, (size_t)params.len) ? 1 : 0;
+    } catch (const std::exception& e) {
+        printf("%s\n", e.what());
+        return 0;
+    }
+}
 
 unsigned char InitAlgorithm(unsigned char algorithmID, GoSlice_g16 provingKey, GoSlice_g16 r1cs) {
     if (algorithmID > 2) return 0;   // prove_impl.go:72,113
@@ -254,6 +367,7 @@ Prove_return_g16 Prove(GoSlice_g16 params) {
 void g16_libprove_reset(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto& p : g_provers) { if (p) g16_free(p); p = nullptr; }
+    for (auto& v : g_verifiers) { if (v) g16_verify_free(v); v = nullptr; }
 }
 
 }  // extern "C"

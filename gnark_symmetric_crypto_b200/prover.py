@@ -103,6 +103,32 @@ def Prove(params: bytes) -> bytes:
     return out
 
 
+@dataclass
+class InputVerifyParams:   # libraries/verifier/impl/verify_impl.go:18-22
+    cipher: str
+    proof: bytes
+    public_signals: bytes   # ciphertext(64) | nonce(12) | counter(4: LE for chacha20, BE for AES) | plaintext(64)
+
+    def to_json(self) -> bytes:
+        return json.dumps({"cipher": self.cipher, "proof": list(self.proof), "publicSignals": list(self.public_signals)}).encode()
+
+
+def InitVerifier(algorithm_id: int, verifying_key: bytes) -> bool:
+    """Hands one of the reference's embedded verifying keys (verify_impl.go:26-62) to the library."""
+    L = _lib.load()
+    if not 0 <= int(algorithm_id) <= 255:
+        return False
+    s1, k1 = _slice(verifying_key)
+    return bool(L.InitVerifier(int(algorithm_id), s1))
+
+
+def Verify(params: bytes) -> bool:
+    """libraries/verifier/libverify.go:14-17 — every failure is False."""
+    L = _lib.load()
+    s, keep = _slice(bytes(params))
+    return bool(L.Verify(s))
+
+
 class Groth16Context:
     """One (pk, r1cs) pair resident on one GPU: the inner seam under gnark's groth16.Prove."""
 

@@ -191,6 +191,11 @@ void enforce_binding(void);                                                     
 unsigned char InitAlgorithm(unsigned char algorithmID, GoSlice_g16 provingKey, GoSlice_g16 r1cs);   /* libprove.go:20-23 */
 void Free(void* pointer);                                                          /* libprove.go:25-28 */
 Prove_return_g16 Prove(GoSlice_g16 params);                                        /* libprove.go:30-47 */
+/* verifier side, libraries/verifier/libverify.go:14-17: Verify(params JSON {"cipher","proof","publicSignals"}) -> bool.
+ * The reference embeds vk.chacha20 / vk.aes128 / vk.aes256 with go:embed (impl/verify_impl.go:26-62); this library takes the
+ * same bytes once per cipher through InitVerifier (algorithm ids as InitAlgorithm). */
+unsigned char InitVerifier(unsigned char algorithmID, GoSlice_g16 verifyingKey);
+unsigned char Verify(GoSlice_g16 params);
 
 #ifdef __cplusplus
 }

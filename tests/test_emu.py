@@ -7,6 +7,7 @@ import os
 import numpy as np
 import pytest
 
+from conftest import GOLDEN
 from gnark_symmetric_crypto_b200 import _lib
 
 
@@ -253,3 +254,38 @@ def test_pairing_check(emu, oracle):
     ok(emu, emu.g16_pairing_check(p64(P), p64(Q), 2, 2, p8(out)))
     assert out.tolist() == [1, 0]
     assert emu.g16_pairing_check(p64(P), p64(Q), 0, 2, p8(out)) == 1   # G16_ERR_ARG
+
+
+def test_verifier_orchestration(emu, oracle, kat):
+    """Host orchestration of the batched groth16.Verify (vk parsing, proof unpacking, public-input MSM, kSum, pairing inputs)
+    under emulation: the committed known-answer proof is accepted under the reference's vk.chacha20. (Rejections are covered
+    by test_pairing_check here and by tests/test_gpu_verify.py on the GPU.)"""
+    vk = (GOLDEN / "vk.chacha20").read_bytes()
+    h = C.c_void_p()
+    ok(emu, emu.g16_verify_init(vk, len(vk), 0, C.byref(h)))
+    info = np.zeros(4, dtype=np.uint64)
+    ok(emu, emu.g16_verify_info(h, p64(info)))
+    assert info.tolist() == [1152, 0, 164, 1153]
+    inputs, _ = oracle.chacha_assignment(kat["key"], kat["nonce"], kat["counter"], kat["input"])
+    pub = np.frombuffer(b"".join(int(x).to_bytes(32, "big") for x in inputs[1:1153]), dtype=np.uint8).copy()
+    pr = np.frombuffer(kat["proof"], dtype=np.uint8).copy()
+    out = np.zeros(1, dtype=np.uint8)
+    ok(emu, emu.g16_verify_batch(h, 1, p8(pr), pub.ctypes.data_as(C.c_void_p), 1, p8(out), None))
+    assert out[0] == 1
+    assert emu.g16_verify_batch(h, 0, p8(pr), pub.ctypes.data_as(C.c_void_p), 1, p8(out), None) == 1   # G16_ERR_ARG
+    emu.g16_verify_free(h)
+    bad = C.c_void_p()
+    assert emu.g16_verify_init(vk[:-3], len(vk) - 3, 0, C.byref(bad)) == 2   # G16_ERR_PARSE
+
+
+def test_libverify_json_layer(emu):
+    """libverify.go:14-17 / verify_impl.go:64-82 without a key: every failure is `false`, nothing throws across the ABI."""
+    from gnark_symmetric_crypto_b200._lib import GoSlice
+
+    def call(b):
+        buf = (C.c_uint8 * max(len(b), 1)).from_buffer_copy(b or b"\0")
+        return emu.Verify(GoSlice(C.cast(buf, C.c_void_p), len(b), len(b)))
+    assert call(b'{"cipher":"chacha20","proof":[1,2],"publicSignals":[3]}') == 0     # verifier not initialised
+    assert call(b'{"cipher":"nope","proof":[],"publicSignals":[]}') == 0
+    assert call(b'{"cipher":"chacha20","proof":"####"}') == 0                           # illegal base64
+    assert call(b'[1,2') == 0 and call(b'') == 0

@@ -79,3 +79,36 @@ def test_aes_verify_batch(G, oracle, aes128_oracle, aes256_oracle, bits):
     for p, pub, w in cases[:7]:
         assert orc.verify(p, pub) == w
     ver.close(); ctx.close()
+
+
+def test_libverify_abi_round_trip(G, oracle, pk_bytes, r1cs_bytes):
+    """core_test.go:130-172 TestFullChaCha20 and :174-260 TestFullAES128/256 end to end through the outer ABI of both
+    libraries: InitAlgorithm + Prove(JSON) -> InitVerifier + Verify(JSON); core_test.go:120-128 TestPanic's payload and other
+    broken inputs verify as false."""
+    vk = open("tests/golden/vk.chacha20", "rb").read()
+    assert G.InitAlgorithm(G.CHACHA20, pk_bytes, r1cs_bytes) is True
+    assert G.InitVerifier(G.CHACHA20, vk) is True
+    assert G.InitVerifier(G.CHACHA20, vk) is True
+    assert G.InitVerifier(9, vk) is False
+    rng = np.random.default_rng(5)
+    key, nonce, pt, counter = rng.bytes(32), rng.bytes(12), rng.bytes(64), 7
+    out = G.OutputParams.from_json(G.Prove(G.InputParams("chacha20", key, nonce, counter, pt).to_json()))
+    signals = out.public_signals + nonce + struct.pack("<I", counter) + pt      # core_test.go:157-163
+    assert G.Verify(G.InputVerifyParams("chacha20", out.proof_json, signals).to_json()) is True
+    wrong = bytearray(signals); wrong[3] ^= 1
+    assert G.Verify(G.InputVerifyParams("chacha20", out.proof_json, bytes(wrong)).to_json()) is False
+    assert G.Verify(G.InputVerifyParams("chacha20", out.proof_json, signals[:-1]).to_json()) is False
+    assert G.Verify(G.InputVerifyParams("chacha20", out.proof_json[:100], signals).to_json()) is False
+    assert G.Verify(G.InputVerifyParams("chacha21", out.proof_json, signals).to_json()) is False
+    assert G.Verify(b'{"cipher":"aes-256-ctr1","key":[0],"nonce":[0],"counter":[0,1],"input":[0]}') is False
+    assert G.Verify(b'not json') is False
+    for alg, name, bits in ((G.AES_128, "aes-128-ctr", 128), (G.AES_256, "aes-256-ctr", 256)):
+        pk, avk, r1 = aes_keys(bits)
+        assert G.InitAlgorithm(alg, pk, r1) is True
+        assert G.InitVerifier(alg, avk) is True
+        key = rng.bytes(bits // 8)
+        out = G.OutputParams.from_json(G.Prove(G.InputParams(name, key, nonce, counter, pt).to_json()))
+        signals = out.public_signals + nonce + struct.pack(">I", counter) + pt   # core_test.go:205,249: big-endian counter
+        assert G.Verify(G.InputVerifyParams(name, out.proof_json, signals).to_json()) is True
+        wrong = bytearray(signals); wrong[70] ^= 1
+        assert G.Verify(G.InputVerifyParams(name, out.proof_json, bytes(wrong)).to_json()) is False
