@@ -58,6 +58,7 @@ EXPORTS = {
     "g16_msm": (C.c_int, [C.c_int, u64p, u64p, C.c_int, C.c_size_t, C.c_int, u64p, f32p]),
     "g16_msm_plan_create": (C.c_int, [C.c_int, u64p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "g16_msm_plan_set_scalars": (C.c_int, [C.c_void_p, u64p, C.c_int]),
+    "g16_msm_plan_precompute": (C.c_int, [C.c_void_p, C.c_int]),
     "g16_msm_plan_run": (C.c_int, [C.c_void_p, u64p, f32p]),
     "g16_msm_plan_free": (None, [C.c_void_p]),
     "g16_ntt": (C.c_int, [u64p, C.c_size_t, C.c_int, C.c_int, f32p]),

@@ -22,8 +22,9 @@ struct g16_vctx {
 struct g16_msm_plan {
     int group, device, c;
     uint32_t n;
-    DevBuf<G1Affine> p1;
-    DevBuf<G2Affine> p2;
+    DevBuf<G1Affine> p1, t1;   // points ; window tables 2^(c w) P_i (precomputed mode)
+    DevBuf<G2Affine> p2, t2;
+    int precomp = 0;
     DevBuf<Fr> scalars;
     int scalars_mont = 0;
     MsmWorkspace<G1> ws1;
@@ -481,6 +482,35 @@ int g16_msm_plan_create(int group, const uint64_t* points, size_t n, int window,
         *out = p.release();
     });
 }
+// Fixed bases (an SRS): tabulate 2^(c w) P_i once, so that every later MSM needs one bucket set instead of one per window
+// and no doubling chain at the end — the mode the prover context uses for the pk queries.
+int g16_msm_plan_precompute(g16_msm_plan* plan, int window) {
+    return guarded([&] {
+        REQUIRE(plan, "NULL argument");
+        G16_CUDA(cudaSetDevice(plan->device));
+        int c = window;
+        if (c <= 0) {   // argmin over c of ceil(254/c) * n + 2^c (accumulation + one bucket reduction)
+            double best = 1e300;
+            for (int k = 4; k <= 24; k++) {
+                double cost = (double)((254 + k - 1) / k) * (double)plan->n + (double)(1u << k);
+                if (cost < best) { best = cost; c = k; }
+            }
+        }
+        REQUIRE(c >= 2 && c <= 24, "window out of range");
+        const int nwin = (254 + c - 1) / c;
+        REQUIRE((size_t)plan->n * nwin < (1ull << 31), "table too large for 31-bit point references");
+        if (plan->group == 1) {
+            plan->t1.alloc((size_t)plan->n * nwin);
+            msm_precompute_g1(plan->p1.p, plan->n, nwin, c, plan->t1.p, plan->stream);
+        } else {
+            plan->t2.alloc((size_t)plan->n * nwin);
+            msm_precompute_g2(plan->p2.p, plan->n, nwin, c, plan->t2.p, plan->stream);
+        }
+        G16_CUDA(cudaStreamSynchronize(plan->stream));
+        plan->c = c;
+        plan->precomp = 1;
+    });
+}
 int g16_msm_plan_set_scalars(g16_msm_plan* plan, const uint64_t* scalars, int scalars_mont) {
     return guarded([&] {
         REQUIRE(plan && scalars, "NULL argument");
@@ -495,14 +525,16 @@ int g16_msm_plan_run(g16_msm_plan* plan, uint64_t* out, float ms[4]) {
         REQUIRE(plan && out, "NULL argument");
         G16_CUDA(cudaSetDevice(plan->device));
         cudaStream_t st = plan->stream;
-        MsmShape sh = msm_make_shape(plan->n, 1, plan->c, 0);
+        MsmShape sh = msm_make_shape(plan->n, 1, plan->c, plan->precomp);
         plan->tm.reset();
         if (plan->group == 1) {
-            msm_run_g1(plan->ws1, sh, plan->p1.p, plan->scalars.p, plan->n, 1, nullptr, plan->scalars_mont, st, &plan->tm);
+            msm_run_g1(plan->ws1, sh, plan->precomp ? plan->t1.p : plan->p1.p, plan->scalars.p, plan->n, 1, nullptr, plan->scalars_mont, st,
+                       &plan->tm);
             xyzz_to_affine_g1(plan->ws1.result.p, 1, plan->o1.p, st);
             plan->o1.download((G1Affine*)out, 1, st);
         } else {
-            msm_run_g2(plan->ws2, sh, plan->p2.p, plan->scalars.p, plan->n, 1, nullptr, plan->scalars_mont, st, &plan->tm);
+            msm_run_g2(plan->ws2, sh, plan->precomp ? plan->t2.p : plan->p2.p, plan->scalars.p, plan->n, 1, nullptr, plan->scalars_mont, st,
+                       &plan->tm);
             xyzz_to_affine_g2(plan->ws2.result.p, 1, plan->o2.p, st);
             plan->o2.download((G2Affine*)out, 1, st);
         }

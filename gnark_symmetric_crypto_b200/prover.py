@@ -427,14 +427,18 @@ def msm(group: int, points: np.ndarray, scalars: np.ndarray, scalars_mont: bool 
 class MsmPlan:
     """Device-resident MSM (points uploaded once) for the standalone sweeps of BASELINE config 5."""
 
-    def __init__(self, group: int, points: np.ndarray, window: int = 0, device: int = 0):
+    def __init__(self, group: int, points: np.ndarray, window: int = 0, device: int = 0, precompute: bool = False):
+        """precompute=True: the bases are an SRS used by many MSMs — tabulate 2^(c w) P_i once (one bucket set per MSM
+        instead of one per window, no doubling chain at the end: the mode the prover context uses for the pk queries)."""
         self._L = _lib.load()
         self.group = group
         w = 8 if group == 1 else 16
         pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, w)
         self.n = len(pts)
         self._h = C.c_void_p()
-        _check(self._L.g16_msm_plan_create(group, _p64(pts), self.n, window, device, C.byref(self._h)))
+        _check(self._L.g16_msm_plan_create(group, _p64(pts), self.n, 0 if precompute else window, device, C.byref(self._h)))
+        if precompute:
+            _check(self._L.g16_msm_plan_precompute(self._h, window))
 
     def set_scalars(self, scalars: np.ndarray, mont: bool = False):
         sc = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)

@@ -141,6 +141,8 @@ int g16_msm(int group, const uint64_t* points, const uint64_t* scalars, int scal
 /* device-resident variant for benchmarking: upload once, run many times */
 typedef struct g16_msm_plan g16_msm_plan;
 int g16_msm_plan_create(int group, const uint64_t* points, size_t n, int window, int device, g16_msm_plan** out);
+/* bases fixed across many MSMs (an SRS): tabulate 2^(c w) P_i once (window 0 = choose). Results are unchanged. */
+int g16_msm_plan_precompute(g16_msm_plan* plan, int window);
 int g16_msm_plan_set_scalars(g16_msm_plan* plan, const uint64_t* scalars, int scalars_mont);
 int g16_msm_plan_run(g16_msm_plan* plan, uint64_t* out, float ms[4]);
 void g16_msm_plan_free(g16_msm_plan* plan);

@@ -266,3 +266,25 @@ def test_pairing_check_matches_oracle(G, oracle):
             assert oracle.pairing_check(p[:k + 1], g2[:k + 1]) == (not flip)
     got = G.pairing_check(np.concatenate(Ps), np.concatenate(Qs), pairs_per_check=4)
     assert got.tolist() == want
+
+
+def test_msm_plan_with_precomputed_tables(G, oracle):
+    """Fixed-base mode of the standalone MSM (the prover context's mode, exposed for BASELINE config 5): same points as the
+    one-shot pipeline and as the oracle, for G1 and G2, automatic and explicit windows, scalars replaced between runs."""
+    rng = np.random.default_rng(61)
+    n = 3000
+    pts = oracle.g1_fixed_base(oracle.rand_field(rng, 1, n)); pts[7] = 0
+    for window in (0, 9):
+        plan = G.MsmPlan(1, pts, window=window, precompute=True)
+        for _ in range(2):
+            sc = oracle.rand_field(rng, 1, n); sc[3] = 0
+            plan.set_scalars(sc)
+            out, _ms = plan.run()
+            assert np.array_equal(out, oracle.g1_msm(pts, sc))
+        plan.close()
+    p2 = oracle.g2_fixed_base(oracle.rand_field(rng, 1, 200)); s2 = oracle.rand_field(rng, 1, 200)
+    plan = G.MsmPlan(2, p2, window=7, precompute=True)
+    plan.set_scalars(s2)
+    out, _ms = plan.run()
+    assert np.array_equal(out, oracle.g2_msm(p2, s2))
+    plan.close()
