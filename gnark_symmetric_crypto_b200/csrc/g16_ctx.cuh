@@ -333,6 +333,7 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
             uint8_t kind = cs.bp_kind[cs.bp_id[id]];
             if (kind == INS_R1C) return cd[s0 + 1] + cd[s0 + 2] + cd[s0 + 3];
             if (kind == INS_HINT && cd[s0 + 1] == HINT_NBITS && cd[s0 + 2] == 1) return cd[s0 + 3];
+            if (kind == INS_HINT && cd[s0 + 1] == HINT_COUNT) return cd[s0 + 2];   // one expression per input: lanes split the queries
             return 0;   // lookups and the other hints stay on the witness-parallel kernel
         };
         std::vector<uint32_t> lvl_instr, lvl_off(1, 0), lvl_split;
