@@ -136,12 +136,17 @@ def cpu_reference_run(n_proofs: int, threads: int):
     return n_proofs / dt, dt
 
 
+def cpu_sample_size(cores: int) -> int:
+    """Bounded CPU sample: ~10-20 s of work for the oracle prover (~0.5 s per proof per core)."""
+    return max(cores, min(24 * cores, 768))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    sample = max(cores, min(4 * cores, 64))
+    sample = cpu_sample_size(cores)
     vals = []
     for _ in range(args.warmup and 1 or 0):
         cpu_reference_run(max(cores, 8), cores)
@@ -280,7 +285,7 @@ def run_gpu(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = max(cores, min(4 * cores, 64))
+        sample = cpu_sample_size(cores)
         v, dt = cpu_reference_run(sample, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{sample} ChaCha20-V3 proofs, one proof per thread, oracle C++ prover ({dt:.1f} s)"}
