@@ -8,10 +8,13 @@
 //     (libprove.go:33-43); success is {"proof":{"proofJson":<base64>},"publicSignals":<base64>} (prove_impl.go:129-134)
 //   * the result buffer is malloc'd and must be released with Free (libprove.go:25-28,40,46)
 #include "../../include/g16b200.h"
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -173,37 +176,129 @@ std::string json_string(const std::string& s) {
     return o + "\"";
 }
 
+// ---- dynamic batching. The reference's API proves one request per call and its callers (the attestor) issue calls
+// concurrently; the GPU only reaches its throughput on batches. Concurrent Prove calls for one cipher are therefore coalesced:
+// each call enqueues its request and sleeps, one worker thread per cipher takes everything that is queued (up to
+// G16_BATCH_MAX, default 1024) whenever the previous batch has finished, proves it in one g16_prove_*_batch call and wakes
+// the callers. A lone request is picked up immediately, so its latency is unchanged. G16_DYNAMIC_BATCH=0 disables it.
+struct Pending {
+    const InputParams* ip = nullptr;
+    uint8_t proof[196];
+    uint8_t ct[64];
+    int rc = 0;
+    std::string err;
+    bool done = false;
+};
+struct Batcher {
+    int alg = 0;
+    g16_ctx* ctx = nullptr;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::deque<Pending*> q;
+    bool stop = false;
+    std::thread worker;
+    size_t max_batch = 1024;
+    size_t proof_bytes() const { return alg == 0 ? 164 : 196; }
+
+    int prove_many(std::vector<Pending*>& b) {
+        const size_t n = b.size();
+        const size_t klen = b[0]->ip->key.size();
+        for (Pending* p : b)
+            if (p->ip->key.size() != klen) return G16_ERR_ARG;   // mixed key lengths: the caller falls back to single requests
+        std::vector<uint8_t> keys(klen * n), nonces(12 * n), inputs(64 * n), proofs(proof_bytes() * n), cts(64 * n);
+        std::vector<uint32_t> counters(n);
+        for (size_t i = 0; i < n; i++) {
+            memcpy(&keys[klen * i], b[i]->ip->key.data(), klen);
+            memcpy(&nonces[12 * i], b[i]->ip->nonce.data(), 12);
+            memcpy(&inputs[64 * i], b[i]->ip->input.data(), 64);
+            counters[i] = b[i]->ip->counter;
+        }
+        int rc = alg == 0 ? g16_prove_chacha_batch(ctx, n, keys.data(), nonces.data(), counters.data(), inputs.data(), nullptr,
+                                                   proofs.data(), cts.data())
+                          : g16_prove_aes_batch(ctx, n, keys.data(), klen, nonces.data(), counters.data(), inputs.data(), nullptr,
+                                                proofs.data(), cts.data());
+        if (rc) return rc;
+        for (size_t i = 0; i < n; i++) {
+            memcpy(b[i]->proof, &proofs[proof_bytes() * i], proof_bytes());
+            memcpy(b[i]->ct, &cts[64 * i], 64);
+            b[i]->rc = 0;
+        }
+        return 0;
+    }
+    void run() {
+        for (;;) {
+            std::vector<Pending*> batch;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return stop || !q.empty(); });
+                if (stop && q.empty()) return;
+                while (!q.empty() && batch.size() < max_batch) { batch.push_back(q.front()); q.pop_front(); }
+            }
+            int rc = prove_many(batch);
+            if (rc) {
+                const std::string msg = g16_last_error();
+                if (batch.size() == 1) {
+                    batch[0]->rc = rc;
+                    batch[0]->err = msg;
+                } else {
+                    // one request of the batch cannot be proved (e.g. an AES counter the circuit rejects): prove them one by
+                    // one so that only the offending call fails
+                    for (Pending* p : batch) {
+                        std::vector<Pending*> one(1, p);
+                        p->rc = prove_many(one);
+                        if (p->rc) p->err = g16_last_error();
+                    }
+                }
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                for (Pending* p : batch) p->done = true;
+            }
+            cv_done.notify_all();
+        }
+    }
+};
+Batcher* g_batchers[3] = {nullptr, nullptr, nullptr};
+
 std::string prove_impl(const uint8_t* params, size_t len) {
     InputParams ip = parse_params(params, len);
     int alg = -1;
     for (int i = 0; i < 3; i++) if (ip.cipher == ALG_NAMES[i]) alg = i;
     if (alg < 0) throw Panic("could not find prover for" + ip.cipher);   // prove_impl.go:140-142 (sic, no space)
     g16_ctx* ctx;
+    Batcher* bt;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         ctx = g_provers[alg];
+        bt = g_batchers[alg];
     }
     if (!ctx) throw Panic("proving params are not initialized for cipher: " + ip.cipher);   // prove_impl.go:124-126
-    std::vector<uint8_t> proof(256), ct(64);
     if (alg == 0) {
         if (ip.key.size() != 32) throw Panic("key length must be 32: " + std::to_string(ip.key.size()));         // provers.go:81-83
         if (ip.nonce.size() != 12) throw Panic("nonce length must be 12: " + std::to_string(ip.nonce.size()));   // :84-86
         if (ip.input.size() != 64) throw Panic("plaintext length must be 64: " + std::to_string(ip.input.size()));   // :87-89
-        int rc = g16_prove_chacha_batch(ctx, 1, ip.key.data(), ip.nonce.data(), &ip.counter, ip.input.data(), nullptr,
-                                        proof.data(), ct.data());
-        if (rc) throw Panic(std::string("groth16 prove failed: ") + g16_last_error());
-        proof.resize(164);
     } else {
         if (ip.key.size() != 32 && ip.key.size() != 16) throw Panic("key length must be 16 or 32: " + std::to_string(ip.key.size()));   // provers.go:174-176
         if (ip.nonce.size() != 12) throw Panic("nonce length must be 12: " + std::to_string(ip.nonce.size()));
         if (ip.input.size() != 64) throw Panic("plaintext length must be 64: " + std::to_string(ip.input.size()));
-        int rc = g16_prove_aes_batch(ctx, 1, ip.key.data(), ip.key.size(), ip.nonce.data(), &ip.counter, ip.input.data(), nullptr,
-                                     proof.data(), ct.data());
-        if (rc) throw Panic(std::string("groth16 prove failed: ") + g16_last_error());
-        proof.resize(196);
     }
-    return "{\"proof\":{\"proofJson\":\"" + b64encode(proof.data(), proof.size()) + "\"},\"publicSignals\":\"" +
-           b64encode(ct.data(), ct.size()) + "\"}";
+    const size_t pb = alg == 0 ? 164 : 196;
+    Pending pd;
+    pd.ip = &ip;
+    if (bt) {
+        std::unique_lock<std::mutex> lk(bt->mu);
+        bt->q.push_back(&pd);
+        bt->cv_work.notify_one();
+        bt->cv_done.wait(lk, [&] { return pd.done; });
+    } else {
+        int rc = alg == 0 ? g16_prove_chacha_batch(ctx, 1, ip.key.data(), ip.nonce.data(), &ip.counter, ip.input.data(), nullptr, pd.proof, pd.ct)
+                          : g16_prove_aes_batch(ctx, 1, ip.key.data(), ip.key.size(), ip.nonce.data(), &ip.counter, ip.input.data(),
+                                                nullptr, pd.proof, pd.ct);
+        pd.rc = rc;
+        if (rc) pd.err = g16_last_error();
+    }
+    if (pd.rc) throw Panic("groth16 prove failed: " + pd.err);
+    return "{\"proof\":{\"proofJson\":\"" + b64encode(pd.proof, pb) + "\"},\"publicSignals\":\"" + b64encode(pd.ct, 64) + "\"}";
 }
 
 // ---- libraries/verifier: InputVerifyParams (verify_impl.go:18-22) and the public-witness layouts of verifiers.go:50-152
@@ -341,6 +436,15 @@ unsigned char InitAlgorithm(unsigned char algorithmID, GoSlice_g16 provingKey, G
         return 0;
     }
     g_provers[algorithmID] = ctx;
+    const char* dyn = getenv("G16_DYNAMIC_BATCH");
+    if (!dyn || atoi(dyn) != 0) {
+        Batcher* b = new Batcher();
+        b->alg = algorithmID;
+        b->ctx = ctx;
+        if (const char* m = getenv("G16_BATCH_MAX")) { int v = atoi(m); if (v > 0 && v <= 65536) b->max_batch = (size_t)v; }
+        b->worker = std::thread([b] { b->run(); });
+        g_batchers[algorithmID] = b;
+    }
     return 1;
 }
 
@@ -366,6 +470,14 @@ Prove_return_g16 Prove(GoSlice_g16 params) {
 // test hook: drop the cached provers (the reference has no such call; its map lives for the process lifetime)
 void g16_libprove_reset(void) {
     std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& b : g_batchers) {
+        if (!b) continue;
+        { std::lock_guard<std::mutex> lk2(b->mu); b->stop = true; }
+        b->cv_work.notify_all();
+        if (b->worker.joinable()) b->worker.join();
+        delete b;
+        b = nullptr;
+    }
     for (auto& p : g_provers) { if (p) g16_free(p); p = nullptr; }
     for (auto& v : g_verifiers) { if (v) g16_verify_free(v); v = nullptr; }
 }

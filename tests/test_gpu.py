@@ -288,3 +288,40 @@ def test_msm_plan_with_precomputed_tables(G, oracle):
     out, _ms = plan.run()
     assert np.array_equal(out, oracle.g2_msm(p2, s2))
     plan.close()
+
+
+def test_concurrent_prove_calls_are_batched(G, oracle, oracle_vk, pk_bytes, r1cs_bytes):
+    """The reference's API takes one request per Prove call and its callers issue calls concurrently; the library coalesces
+    concurrent calls into GPU batches. 96 threads x 2 calls: every caller gets the proof of ITS request (ciphertext and
+    pairing check against vk.chacha20), and a failing call (bad key length) does not disturb the others."""
+    import threading
+    assert G.InitAlgorithm(G.CHACHA20, pk_bytes, r1cs_bytes) is True
+    nthreads, per = 96, 2
+    rng = np.random.default_rng(1234)
+    reqs = [[(rng.bytes(32), rng.bytes(12), int(rng.integers(0, 1 << 32)), rng.bytes(64)) for _ in range(per)] for _ in range(nthreads)]
+    results = [[None] * per for _ in range(nthreads)]
+    errors = []
+
+    def worker(t):
+        try:
+            for j, (key, nonce, counter, pt) in enumerate(reqs[t]):
+                if t == 5 and j == 0:
+                    with pytest.raises(RuntimeError, match="key length must be 32"):
+                        G.Prove(G.InputParams("chacha20", key[:31], nonce, counter, pt).to_json())
+                results[t][j] = G.OutputParams.from_json(G.Prove(G.InputParams("chacha20", key, nonce, counter, pt).to_json()))
+        except Exception as e:   # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
+    [x.start() for x in th]; [x.join() for x in th]
+    assert not errors, errors[:3]
+    proofs = set()
+    for t in range(nthreads):
+        for j, (key, nonce, counter, pt) in enumerate(reqs[t]):
+            out = results[t][j]
+            assert out.public_signals == oracle.chacha20_xor(key, nonce, counter, pt)
+            proofs.add(out.proof_json)
+            if (t + j) % 16 == 0:
+                signals = out.public_signals + nonce + struct.pack("<I", counter) + pt
+                assert oracle_vk.verify(out.proof_json, oracle.chacha_public_from_signals(signals))
+    assert len(proofs) == nthreads * per
