@@ -333,15 +333,60 @@ void push_word_bits(std::vector<uint8_t>& out, uint32_t w) {   // utils.Uint32To
 uint32_t rd_le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 uint32_t rd_be32(const uint8_t* p) { return (uint32_t)p[3] | ((uint32_t)p[2] << 8) | ((uint32_t)p[1] << 16) | ((uint32_t)p[0] << 24); }
 
+// concurrent Verify calls are coalesced the same way as Prove calls (one g16_verify_batch per drained queue)
+struct VPending {
+    const uint8_t* proof = nullptr;
+    const uint8_t* pub = nullptr;
+    uint8_t ok = 0;
+    int rc = 0;
+    bool done = false;
+};
+struct VBatcher {
+    g16_vctx* ctx = nullptr;
+    size_t proof_bytes = 0, pub_bytes = 0;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::deque<VPending*> q;
+    bool stop = false;
+    std::thread worker;
+    size_t max_batch = 4096;
+    void run() {
+        for (;;) {
+            std::vector<VPending*> batch;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return stop || !q.empty(); });
+                if (stop && q.empty()) return;
+                while (!q.empty() && batch.size() < max_batch) { batch.push_back(q.front()); q.pop_front(); }
+            }
+            const size_t n = batch.size();
+            std::vector<uint8_t> proofs(proof_bytes * n), pubs(pub_bytes * n), ok(n, 0);
+            for (size_t i = 0; i < n; i++) {
+                memcpy(&proofs[proof_bytes * i], batch[i]->proof, proof_bytes);
+                memcpy(&pubs[pub_bytes * i], batch[i]->pub, pub_bytes);
+            }
+            int rc = g16_verify_batch(ctx, n, proofs.data(), pubs.data(), 1, ok.data(), nullptr);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                for (size_t i = 0; i < n; i++) { batch[i]->rc = rc; batch[i]->ok = rc ? 0 : ok[i]; batch[i]->done = true; }
+            }
+            cv_done.notify_all();
+        }
+    }
+};
+VBatcher* g_vbatchers[3] = {nullptr, nullptr, nullptr};
+
 bool verify_impl(const uint8_t* params, size_t len) {
     VerifyParams vp = parse_verify_params(params, len);
     int alg = -1;
     for (int i = 0; i < 3; i++) if (vp.cipher == ALG_NAMES[i]) alg = i;
     if (alg < 0) return false;   // verify_impl.go:78-81
     g16_vctx* ctx;
+    VBatcher* vb;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         ctx = g_verifiers[alg];
+        vb = g_vbatchers[alg];
     }
     if (!ctx) { printf("verifying key is not initialized for cipher: %s\n", vp.cipher.c_str()); return false; }
     if (vp.signals.size() != 128 + 12 + 4) {   // verifiers.go:52-55,105-107: ciphertext | nonce | counter | plaintext
@@ -372,6 +417,16 @@ bool verify_impl(const uint8_t* params, size_t len) {
         for (int k = 0; k < 64; k++) push_be32(pub, ct[k]);
     }
     if (pub.size() != (size_t)info[0] * 32) { printf("verifying key does not match cipher %s\n", vp.cipher.c_str()); return false; }
+    if (vb) {
+        VPending pd;
+        pd.proof = vp.proof.data();
+        pd.pub = pub.data();
+        std::unique_lock<std::mutex> lk(vb->mu);
+        vb->q.push_back(&pd);
+        vb->cv_work.notify_one();
+        vb->cv_done.wait(lk, [&] { return pd.done; });
+        return pd.rc == 0 && pd.ok != 0;
+    }
     uint8_t ok = 0;
     int rc = g16_verify_batch(ctx, 1, vp.proof.data(), pub.data(), 1, &ok, nullptr);
     if (rc) { printf("%s\n", g16_last_error()); return false; }
@@ -403,6 +458,16 @@ unsigned char InitVerifier(unsigned char algorithmID, GoSlice_g16 verifyingKey) 
         return 0;
     }
     g_verifiers[algorithmID] = ctx;
+    const char* dyn = getenv("G16_DYNAMIC_BATCH");
+    uint64_t info[4];
+    if ((!dyn || atoi(dyn) != 0) && g16_verify_info(ctx, info) == 0) {
+        VBatcher* b = new VBatcher();
+        b->ctx = ctx;
+        b->proof_bytes = (size_t)info[2];
+        b->pub_bytes = (size_t)info[0] * 32;
+        b->worker = std::thread([b] { b->run(); });
+        g_vbatchers[algorithmID] = b;
+    }
     return 1;
 }
 
@@ -479,6 +544,14 @@ void g16_libprove_reset(void) {
         b = nullptr;
     }
     for (auto& p : g_provers) { if (p) g16_free(p); p = nullptr; }
+    for (auto& b : g_vbatchers) {
+        if (!b) continue;
+        { std::lock_guard<std::mutex> lk2(b->mu); b->stop = true; }
+        b->cv_work.notify_all();
+        if (b->worker.joinable()) b->worker.join();
+        delete b;
+        b = nullptr;
+    }
     for (auto& v : g_verifiers) { if (v) g16_verify_free(v); v = nullptr; }
 }
 

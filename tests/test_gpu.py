@@ -325,3 +325,20 @@ def test_concurrent_prove_calls_are_batched(G, oracle, oracle_vk, pk_bytes, r1cs
                 signals = out.public_signals + nonce + struct.pack("<I", counter) + pt
                 assert oracle_vk.verify(out.proof_json, oracle.chacha_public_from_signals(signals))
     assert len(proofs) == nthreads * per
+    # concurrent Verify calls are coalesced the same way: every caller gets the verdict of ITS proof
+    assert G.InitVerifier(G.CHACHA20, open("tests/golden/vk.chacha20", "rb").read()) is True
+    verdicts = [[None] * per for _ in range(nthreads)]
+
+    def vworker(t):
+        for j, (key, nonce, counter, pt) in enumerate(reqs[t]):
+            out = results[t][j]
+            signals = bytearray(out.public_signals + nonce + struct.pack("<I", counter) + pt)
+            if (t + j) % 7 == 0:
+                signals[t % 64] ^= 0x10   # a wrong ciphertext byte: must be rejected
+            verdicts[t][j] = G.Verify(G.InputVerifyParams("chacha20", out.proof_json, bytes(signals)).to_json())
+
+    th = [threading.Thread(target=vworker, args=(t,)) for t in range(nthreads)]
+    [x.start() for x in th]; [x.join() for x in th]
+    for t in range(nthreads):
+        for j in range(per):
+            assert verdicts[t][j] is ((t + j) % 7 != 0), (t, j)
