@@ -78,8 +78,10 @@ struct Ctx {
     uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t sub_batch = 512;
     bool tables_ready = false;
+    SolverGraphCache* solver_graphs = nullptr;
 
     ~Ctx() {
+        solver_graph_cache_destroy(solver_graphs);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         if (ev_join3) cudaEventDestroy(ev_join3);
@@ -409,6 +411,7 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
         if (cx->tables_ready) { cx->tables_ready = false; ctx_build_tables(*cx); }
     }
     cx->d_status.alloc(1);
+    cx->solver_graphs = solver_graph_cache_create();
     return cx;
 }
 
@@ -446,14 +449,14 @@ static size_t ctx_solve(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaStream_
     Fr* B = cx.Bev.p + sb * cx.n_dom;
     Fr* C = cx.Cev.p + sb * cx.n_dom;
     if (!cx.n_commit)
-        return launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), 0, cx.nlevels, rows, W, n, A, B, C, cx.d_status.p, st);
-    size_t launches = launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), 0, cx.bsb_level + 1, rows, W, n, A, B, C, cx.d_status.p, st);
+        return launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), 0, cx.nlevels, rows, W, n, A, B, C, cx.d_status.p, st, cx.solver_graphs);
+    size_t launches = launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), 0, cx.bsb_level + 1, rows, W, n, A, B, C, cx.d_status.p, st, cx.solver_graphs);
     for (size_t o = 0; o < rows; o += cx.sub_batch) {
         uint32_t r = (uint32_t)((rows - o) < cx.sub_batch ? (rows - o) : cx.sub_batch);
         run_query_g1(wsc, st, cx.qPed, W + o, 1, n, true, r, cx.resCommit.p + sb + o, nullptr);
     }
     launch_bsb22_challenge(cx.resCommit.p + sb, rows, W, n, cx.commit_wire, cx.commit_aff.p + sb, st);
-    launches += 1 + launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), cx.bsb_level + 1, cx.nlevels, rows, W, n, A, B, C, cx.d_status.p, st);
+    launches += 1 + launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), cx.bsb_level + 1, cx.nlevels, rows, W, n, A, B, C, cx.d_status.p, st, cx.solver_graphs);
     return launches;
 }
 

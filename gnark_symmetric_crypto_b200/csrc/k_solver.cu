@@ -2,12 +2,81 @@
 // independent coefficient products of an unrolled term group overlap.
 #include "solver.cuh"
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 namespace g16 {
 
+static size_t launch_solver_levels(const SolverProgram& sp, const uint32_t* h_level_off, const uint32_t* h_level_split,
+                                   uint32_t lev_begin, uint32_t lev_end, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C,
+                                   uint32_t* status, cudaStream_t st);
+
+// Small batches replay the level launches from a CUDA graph: the sequence is fixed for a given (level range, batch, buffers),
+// and a level of a single request is a few microseconds of work, so the per-launch overhead matters (163 launches for
+// ChaCha, 441 for AES). The cache belongs to one prover context (one solver program). G16_SOLVER_GRAPH=0: plain launches.
+#if !defined(G16_EMU)
+typedef std::tuple<const void*, const void*, const void*, const void*, const void*, const void*, uint32_t, size_t, uint32_t, uint32_t>
+    SolverGraphKey;
+struct SolverGraph { cudaGraphExec_t exec; size_t launches; };
+struct SolverGraphCache {
+    std::map<SolverGraphKey, SolverGraph> graphs;
+    std::mutex mu;
+    void clear() {
+        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second.exec);
+        graphs.clear();
+    }
+};
+SolverGraphCache* solver_graph_cache_create() { return new SolverGraphCache(); }
+void solver_graph_cache_destroy(SolverGraphCache* c) {
+    if (!c) return;
+    c->clear();
+    delete c;
+}
+#else
+struct SolverGraphCache {};
+SolverGraphCache* solver_graph_cache_create() { return nullptr; }
+void solver_graph_cache_destroy(SolverGraphCache*) {}
+#endif
+
 size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, const uint32_t* h_level_split, uint32_t lev_begin,
                      uint32_t lev_end, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C, uint32_t* status,
-                     cudaStream_t st) {
+                     cudaStream_t st, SolverGraphCache* cache) {
+#if !defined(G16_EMU)
+    static const uint32_t graph_max = [] { const char* v = getenv("G16_SOLVER_GRAPH"); return (uint32_t)(v && *v ? atoi(v) : 16); }();
+    if (cache && batch <= graph_max && lev_end > lev_begin) {
+        SolverGraphKey key(sp.randomize, W, A, B, C, status, batch, w_stride, lev_begin, lev_end);
+        std::lock_guard<std::mutex> lk(cache->mu);
+        auto& graphs = cache->graphs;
+        auto it = graphs.find(key);
+        if (it == graphs.end()) {
+            if (graphs.size() >= 64) cache->clear();   // buffers were reallocated many times: start over
+            cudaGraph_t graph = nullptr;
+            SolverGraph sg{nullptr, 0};
+            G16_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            try {
+                sg.launches = launch_solver_levels(sp, h_level_off, h_level_split, lev_begin, lev_end, batch, W, w_stride, A, B, C, status, st);
+            } catch (...) {
+                cudaStreamEndCapture(st, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                throw;
+            }
+            G16_CUDA(cudaStreamEndCapture(st, &graph));
+            cudaError_t e = cudaGraphInstantiate(&sg.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) throw CudaError(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+            it = graphs.emplace(key, sg).first;
+        }
+        G16_CUDA(cudaGraphLaunch(it->second.exec, st));
+        return it->second.launches;
+    }
+#endif
+    return launch_solver_levels(sp, h_level_off, h_level_split, lev_begin, lev_end, batch, W, w_stride, A, B, C, status, st);
+}
+
+static size_t launch_solver_levels(const SolverProgram& sp, const uint32_t* h_level_off, const uint32_t* h_level_split,
+                                   uint32_t lev_begin, uint32_t lev_end, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C,
+                                   uint32_t* status, cudaStream_t st) {
     const uint32_t groups = div_up(batch, 32);
     size_t launches = 0;
     if (lev_end > sp.nlevels) lev_end = sp.nlevels;

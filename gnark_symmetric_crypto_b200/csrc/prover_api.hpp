@@ -56,9 +56,13 @@ void launch_witness_copy(const Fr* witness, uint32_t n_witness, uint32_t batch, 
 // h_level_off: host copy of the level offsets (nlevels + 1); h_level_split[l] in [off[l], off[l+1]]: instructions from there
 // to the end of level l have long linear expressions (term-parallel kernel). Returns the number of kernel launches.
 // runs levels [lev_begin, lev_end)
+// cache (optional, owned by one prover context): CUDA graphs of the level launches for small batches
+struct SolverGraphCache;
+SolverGraphCache* solver_graph_cache_create();
+void solver_graph_cache_destroy(SolverGraphCache* cache);
 size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, const uint32_t* h_level_split, uint32_t lev_begin,
                      uint32_t lev_end, uint32_t batch,
-                     Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C, uint32_t* status, cudaStream_t st);
+                     Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C, uint32_t* status, cudaStream_t st, SolverGraphCache* cache = nullptr);
 // fills ucoef_inv (n_instr entries) and returns whether coefficient ids 0..4 are 0,1,2,-1,-2 (synchronises the stream)
 int launch_solver_init(const SolverProgram& sp, uint32_t n_instr, uint32_t n_coeffs, Fr* ucoef_inv, cudaStream_t st);
 // builds the 64 x 15 fixed-base tables of delta / delta2 (device buffers owned by the caller)
