@@ -39,11 +39,11 @@ struct Ctx {
     DevBuf<G2Affine> delta2_tab;
     NttDomain dom;
     // solver program
-    DevBuf<uint32_t> d_calldata, d_level_instr, d_level_off;
+    DevBuf<uint32_t> d_calldata, d_level_instr, d_level_off, d_count_index;
     DevBuf<InsMeta> d_meta;
     DevBuf<Fr> d_coeffs, d_ucoef_inv, d_lookup_tabs;
     SolverProgram sp;
-    std::vector<uint32_t> h_level_off, h_level_split;   // split: first "long" instruction of each level (see ctx_create)
+    std::vector<uint32_t> h_level_off, h_level_split, h_level_split2;   // split: first "long" instruction of each level (see ctx_create)
     bool solver_supported = true;
     std::string solver_unsupported_reason;
     // BSB22 commitment (AES circuits): at most one commitment is supported
@@ -273,6 +273,8 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
         uint32_t ntab = 0;
         for (size_t b = 0; b < cs.bp_kind.size(); b++) if (cs.bp_kind[b] == INS_LOOKUP) lk_index[b] = ntab++;
         const std::vector<uint32_t>& cd = cs.calldata;
+        std::vector<uint32_t> count_ids;
+        uint32_t count_words = 0;
         for (size_t i = 0; i < cs.n_instr(); i++) {
             InsMeta& m = meta[i];
             uint64_t s0 = cs.start[i];
@@ -309,6 +311,11 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
                 uint32_t o0 = cd[pos], o1 = cd[pos + 1];
                 if (o1 < o0 || o1 > cx->nb_wires) throw ParseError("r1cs: hint output range out of bounds");
                 for (uint32_t w = o0; w < o1; w++) solved[w] = 1;
+                if (hid == HINT_COUNT) {   // room for the query index built on the device below
+                    m.lookup_tab = count_words;
+                    count_ids.push_back((uint32_t)i);
+                    count_words += 6 + nin / 2;
+                }
                 if (hid == HINT_RANDOMIZE) cx->has_randomize = true;
                 else if (hid == HINT_BSB22) {
                     if (cx->bsb_ins != 0xFFFFFFFFu) { cx->solver_supported = false; cx->solver_unsupported_reason = "more than one BSB22 commitment"; }
@@ -335,23 +342,30 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
             uint8_t kind = cs.bp_kind[cs.bp_id[id]];
             if (kind == INS_R1C) return cd[s0 + 1] + cd[s0 + 2] + cd[s0 + 3];
             if (kind == INS_HINT && cd[s0 + 1] == HINT_NBITS && cd[s0 + 2] == 1) return cd[s0 + 3];
-            if (kind == INS_HINT && cd[s0 + 1] == HINT_COUNT) return cd[s0 + 2];   // one expression per input: lanes split the queries
             return 0;   // lookups and the other hints stay on the witness-parallel kernel
         };
-        std::vector<uint32_t> lvl_instr, lvl_off(1, 0), lvl_split;
+        auto is_count = [&](uint32_t id) -> bool {
+            uint64_t s0 = cs.start[id];
+            return cs.bp_kind[cs.bp_id[id]] == INS_HINT && cd[s0 + 1] == HINT_COUNT;
+        };
+        std::vector<uint32_t> lvl_instr, lvl_off(1, 0), lvl_split, lvl_split2;
         for (auto& lv : cs.levels) {
-            std::vector<uint32_t> longs;
+            std::vector<uint32_t> longs, counts;
             for (uint32_t id : lv) {
                 if (id >= cs.n_instr()) throw ParseError("r1cs: level references unknown instruction");
                 if (id == cx->bsb_ins) cx->bsb_level = (uint32_t)(lvl_off.size() - 1);
-                if (n_terms(id) > long_terms) longs.push_back(id);
+                if (is_count(id)) counts.push_back(id);   // logderivarg.countHint: a block per instruction and witness
+                else if (n_terms(id) > long_terms) longs.push_back(id);
                 else lvl_instr.push_back(id);
             }
             lvl_split.push_back((uint32_t)lvl_instr.size());
             lvl_instr.insert(lvl_instr.end(), longs.begin(), longs.end());
+            lvl_split2.push_back((uint32_t)lvl_instr.size());
+            lvl_instr.insert(lvl_instr.end(), counts.begin(), counts.end());
             lvl_off.push_back((uint32_t)lvl_instr.size());
         }
         cx->h_level_split = lvl_split;
+        cx->h_level_split2 = lvl_split2;
         if (lvl_instr.size() != cs.n_instr()) throw ParseError("r1cs: levels do not cover every instruction exactly once");
         // lookup tables: entry k of table t = coeffs[cid] of the single constant term of that entry (pure gather)
         std::vector<uint64_t> tabs((size_t)(ntab ? ntab : 1) * 256 * 4, 0);
@@ -382,6 +396,15 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
         sp.lookup_tabs = cx->d_lookup_tabs.p; sp.nlevels = cx->nlevels; sp.n_wires = cx->nb_wires;
         sp.n_dom = (uint32_t)cx->n_dom; sp.fast_coeffs = 0;
         sp.randomize = nullptr; sp.bsb_ins = cx->bsb_ins;
+        sp.count_index = nullptr;
+        if (!count_ids.empty()) {
+            DevBuf<uint32_t> d_ids;
+            d_ids.upload(count_ids.data(), count_ids.size(), st);
+            cx->d_count_index.alloc(count_words);
+            sp.count_index = cx->d_count_index.p;
+            launch_solver_count_index(sp, d_ids.p, (uint32_t)count_ids.size(), cx->d_count_index.p, st);
+            G16_CUDA(cudaStreamSynchronize(st));
+        }
         G16_CUDA(cudaStreamSynchronize(st));   // host vectors above must outlive the copies
         sp.fast_coeffs = launch_solver_init(sp, (uint32_t)cs.n_instr(), (uint32_t)(cs.coeffs.size() / 4), cx->d_ucoef_inv.p, st);
     }
@@ -449,14 +472,14 @@ static size_t ctx_solve(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaStream_
     Fr* B = cx.Bev.p + sb * cx.n_dom;
     Fr* C = cx.Cev.p + sb * cx.n_dom;
     if (!cx.n_commit)
-        return launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), 0, cx.nlevels, rows, W, n, A, B, C, cx.d_status.p, st, cx.solver_graphs);
-    size_t launches = launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), 0, cx.bsb_level + 1, rows, W, n, A, B, C, cx.d_status.p, st, cx.solver_graphs);
+        return launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), cx.h_level_split2.data(), 0, cx.nlevels, rows, W, n, A, B, C, cx.d_status.p, st, cx.solver_graphs);
+    size_t launches = launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), cx.h_level_split2.data(), 0, cx.bsb_level + 1, rows, W, n, A, B, C, cx.d_status.p, st, cx.solver_graphs);
     for (size_t o = 0; o < rows; o += cx.sub_batch) {
         uint32_t r = (uint32_t)((rows - o) < cx.sub_batch ? (rows - o) : cx.sub_batch);
         run_query_g1(wsc, st, cx.qPed, W + o, 1, n, true, r, cx.resCommit.p + sb + o, nullptr);
     }
     launch_bsb22_challenge(cx.resCommit.p + sb, rows, W, n, cx.commit_wire, cx.commit_aff.p + sb, st);
-    launches += 1 + launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), cx.bsb_level + 1, cx.nlevels, rows, W, n, A, B, C, cx.d_status.p, st, cx.solver_graphs);
+    launches += 1 + launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), cx.h_level_split2.data(), cx.bsb_level + 1, cx.nlevels, rows, W, n, A, B, C, cx.d_status.p, st, cx.solver_graphs);
     return launches;
 }
 

@@ -9,7 +9,7 @@
 namespace g16 {
 
 static size_t launch_solver_levels(const SolverProgram& sp, const uint32_t* h_level_off, const uint32_t* h_level_split,
-                                   uint32_t lev_begin, uint32_t lev_end, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C,
+                                   const uint32_t* h_level_split2, uint32_t lev_begin, uint32_t lev_end, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C,
                                    uint32_t* status, cudaStream_t st);
 
 // Small batches replay the level launches from a CUDA graph: the sequence is fixed for a given (level range, batch, buffers),
@@ -39,8 +39,8 @@ SolverGraphCache* solver_graph_cache_create() { return nullptr; }
 void solver_graph_cache_destroy(SolverGraphCache*) {}
 #endif
 
-size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, const uint32_t* h_level_split, uint32_t lev_begin,
-                     uint32_t lev_end, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C, uint32_t* status,
+size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, const uint32_t* h_level_split,
+                     const uint32_t* h_level_split2, uint32_t lev_begin, uint32_t lev_end, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C, uint32_t* status,
                      cudaStream_t st, SolverGraphCache* cache) {
 #if !defined(G16_EMU)
     static const uint32_t graph_max = [] { const char* v = getenv("G16_SOLVER_GRAPH"); return (uint32_t)(v && *v ? atoi(v) : 16); }();
@@ -55,7 +55,7 @@ size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, const
             SolverGraph sg{nullptr, 0};
             G16_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             try {
-                sg.launches = launch_solver_levels(sp, h_level_off, h_level_split, lev_begin, lev_end, batch, W, w_stride, A, B, C, status, st);
+                sg.launches = launch_solver_levels(sp, h_level_off, h_level_split, h_level_split2, lev_begin, lev_end, batch, W, w_stride, A, B, C, status, st);
             } catch (...) {
                 cudaStreamEndCapture(st, &graph);
                 if (graph) cudaGraphDestroy(graph);
@@ -71,11 +71,11 @@ size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, const
         return it->second.launches;
     }
 #endif
-    return launch_solver_levels(sp, h_level_off, h_level_split, lev_begin, lev_end, batch, W, w_stride, A, B, C, status, st);
+    return launch_solver_levels(sp, h_level_off, h_level_split, h_level_split2, lev_begin, lev_end, batch, W, w_stride, A, B, C, status, st);
 }
 
 static size_t launch_solver_levels(const SolverProgram& sp, const uint32_t* h_level_off, const uint32_t* h_level_split,
-                                   uint32_t lev_begin, uint32_t lev_end, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C,
+                                   const uint32_t* h_level_split2, uint32_t lev_begin, uint32_t lev_end, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C,
                                    uint32_t* status, cudaStream_t st) {
     const uint32_t groups = div_up(batch, 32);
     size_t launches = 0;
@@ -87,10 +87,13 @@ static size_t launch_solver_levels(const SolverProgram& sp, const uint32_t* h_le
 #endif
     for (uint32_t lev = lev_begin; lev < lev_end; lev++) {
         uint32_t lo = h_level_off[lev], hi = h_level_off[lev + 1];
-        uint32_t split = hi;   // [lo, split) witness-parallel, [split, hi) term-parallel
+        uint32_t split = hi;   // [lo, split) witness-parallel, [split, hi) term-parallel, countHints [end, hi) block-parallel
 #if !defined(G16_EMU)
+        const uint32_t end = hi;
+        if (h_level_split2 && sp.count_index) hi = h_level_split2[lev];
         if (small) split = lo;
         else if (h_level_split) split = h_level_split[lev];
+        if (split > hi) split = hi;
 #endif
         if (split > lo) {
             dim3 grid(div_up(split - lo, SOLVER_WARPS), groups);
@@ -105,10 +108,20 @@ static size_t launch_solver_levels(const SolverProgram& sp, const uint32_t* h_le
                        B, C, status);
             launches++;
         }
+        if (end > hi) {
+            G16_LAUNCH(solver_count_kernel, dim3(end - hi, batch), SOLVER_COUNT_THREADS, 0, st, false, sp, hi, end, batch, W, w_stride,
+                       status);
+            launches++;
+        }
 #endif
     }
     G16_CHECK_LAUNCH();
     return launches;
+}
+void launch_solver_count_index(const SolverProgram& sp, const uint32_t* ids, uint32_t n, uint32_t* out, cudaStream_t st) {
+    if (!n) return;
+    G16_LAUNCH(solver_count_index_kernel, div_up(n, 32), 32, 0, st, false, sp, ids, n, out);
+    G16_CHECK_LAUNCH();
 }
 int launch_solver_init(const SolverProgram& sp, uint32_t n_instr, uint32_t n_coeffs, Fr* ucoef_inv, cudaStream_t st) {
     DevBuf<uint32_t> flag(1);

@@ -17,7 +17,7 @@ struct InsMeta {
     uint32_t solve_wire;   // wire this R1C defines, or SOLVE_WIRE_NONE (pure check)
     uint32_t cons_off;
     uint32_t wire_off;
-    uint32_t lookup_tab;   // lookup instructions: index of the 256-entry table
+    uint32_t lookup_tab;   // lookup instructions: index of the 256-entry table ; countHint: offset into count_index
 };
 
 struct SolverProgram {
@@ -34,6 +34,7 @@ struct SolverProgram {
     int fast_coeffs;               // coefficient ids 1,2,3,4 are +1,+2,-1,-2 (verified on the device at init)
     const Fr* randomize;           // per witness: value of the hints.Randomize wire (Montgomery), or null
     uint32_t bsb_ins;              // instruction id of the Bsb22 commitment hint (executed by the host pipeline), or ~0
+    const uint32_t* count_index;   // per countHint: nq, row_pos0, row_stride_words, nrows, then nq + 1 calldata positions (or null)
 };
 
 struct AssemblyKeys {
@@ -53,16 +54,20 @@ void launch_scalars_from_be(const uint8_t* in, uint32_t n, Fr* out, cudaStream_t
 void launch_chacha_witness(const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters, const uint8_t* inputs,
                            uint32_t n, Fr* W, size_t w_stride, uint8_t* ct_out, cudaStream_t st);
 void launch_witness_copy(const Fr* witness, uint32_t n_witness, uint32_t batch, Fr* W, size_t w_stride, cudaStream_t st);
-// h_level_off: host copy of the level offsets (nlevels + 1); h_level_split[l] in [off[l], off[l+1]]: instructions from there
-// to the end of level l have long linear expressions (term-parallel kernel). Returns the number of kernel launches.
-// runs levels [lev_begin, lev_end)
+// h_level_off: host copy of the level offsets (nlevels + 1). Inside level l the instructions are ordered
+//   [off[l], split[l])  short expressions          -> witness-parallel kernel (a lane per witness)
+//   [split[l], split2[l]) long expressions          -> term-parallel kernel (a warp per instruction and witness)
+//   [split2[l], off[l+1]) logderivarg.countHint     -> block-parallel kernel (needs sp.count_index)
+// (split / split2 may be null: everything is "short".) Returns the number of kernel launches. Runs levels [lev_begin, lev_end).
 // cache (optional, owned by one prover context): CUDA graphs of the level launches for small batches
 struct SolverGraphCache;
 SolverGraphCache* solver_graph_cache_create();
 void solver_graph_cache_destroy(SolverGraphCache* cache);
-size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, const uint32_t* h_level_split, uint32_t lev_begin,
-                     uint32_t lev_end, uint32_t batch,
+size_t launch_solver(const SolverProgram& sp, const uint32_t* h_level_off, const uint32_t* h_level_split,
+                     const uint32_t* h_level_split2, uint32_t lev_begin, uint32_t lev_end, uint32_t batch,
                      Fr* W, size_t w_stride, Fr* A, Fr* B, Fr* C, uint32_t* status, cudaStream_t st, SolverGraphCache* cache = nullptr);
+// fills the count_index entries of the given countHint instructions (device array `ids`, n of them); out = sp.count_index
+void launch_solver_count_index(const SolverProgram& sp, const uint32_t* ids, uint32_t n, uint32_t* out, cudaStream_t st);
 // fills ucoef_inv (n_instr entries) and returns whether coefficient ids 0..4 are 0,1,2,-1,-2 (synchronises the stream)
 int launch_solver_init(const SolverProgram& sp, uint32_t n_instr, uint32_t n_coeffs, Fr* ucoef_inv, cudaStream_t st);
 // builds the 64 x 15 fixed-base tables of delta / delta2 (device buffers owned by the caller)

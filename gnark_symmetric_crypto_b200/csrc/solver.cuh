@@ -362,6 +362,80 @@ solver_level_small_kernel(SolverProgram sp, uint32_t lo, uint32_t hi, uint32_t b
 // the tail of a level with the head of the next, a grid-wide barrier cannot.)
 #endif
 
+// ------------------------------------------------------------------------------------------------ countHint, block-parallel
+// Init: one thread per countHint instruction walks its calldata once and records where every query starts, so that the
+// solve-time kernel can hand queries to threads directly. Header: nq (or ~0 = unsupported shape), row_pos0,
+// row_stride_words, nrows; then nq + 1 positions (the last one is where the output range is stored).
+__global__ void solver_count_index_kernel(SolverProgram sp, const uint32_t* __restrict__ ids, uint32_t n, uint32_t* __restrict__ out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const InsMeta m = sp.meta[ids[t]];
+    uint32_t* ix = out + m.lookup_tab;
+    const uint32_t base = m.cd_start, nin = sp.calldata[base + 2];
+    uint32_t pos = base + 3;
+    // nbRows and rowWidth must be constants (single constant term): they are evaluated without a witness
+    uint32_t hdr[2];
+    bool ok = true;
+    for (int k = 0; k < 2; k++) {
+        ok = ok && sp.calldata[pos] == 1 && sp.calldata[pos + 2] == WIRE_CONST;
+        Fr v = ok ? sp.coeffs[sp.calldata[pos + 1]].from_mont() : Fr::zero();
+        ok = ok && (v.l[1] | v.l[2] | v.l[3] | v.l[4] | v.l[5] | v.l[6] | v.l[7]) == 0;
+        hdr[k] = v.l[0];
+        pos += 1 + 2 * sp.calldata[pos];
+    }
+    const uint32_t nrows = hdr[0], width = hdr[1];
+    if (!ok || nrows > 256 || width != 2 || nin < 2 + nrows * width) { ix[0] = 0xFFFFFFFFu; return; }
+    const uint32_t row_pos0 = pos;
+    for (uint32_t k = 0; k < nrows * width; k++) pos += 1 + 2 * sp.calldata[pos];
+    const uint32_t nq = (nin - 2 - nrows * width) / width;
+    ix[0] = nq; ix[1] = row_pos0; ix[2] = nrows ? (pos - row_pos0) / nrows : 0; ix[3] = nrows;
+    for (uint32_t q = 0; q < nq; q++) {
+        ix[4 + q] = pos;
+        pos += 1 + 2 * sp.calldata[pos];
+        pos += 1 + 2 * sp.calldata[pos];
+    }
+    ix[4 + nq] = pos;
+}
+#if !defined(G16_EMU)
+static const int SOLVER_COUNT_THREADS = 256;
+// grid.x = the countHint instructions [lo, hi) of a level, grid.y = witnesses; the threads of a block split the queries
+__global__ void __launch_bounds__(SOLVER_COUNT_THREADS)
+solver_count_kernel(SolverProgram sp, uint32_t lo, uint32_t hi, uint32_t batch, Fr* W, size_t ws, uint32_t* status) {
+    __shared__ uint32_t cnt[256];
+    const uint32_t tid = threadIdx.x, inst = blockIdx.y;
+    const uint32_t ins = sp.level_instr[lo + blockIdx.x];
+    W += inst;
+    const uint32_t* ix = sp.count_index + sp.meta[ins].lookup_tab;
+    const uint32_t nq = ix[0], row_pos0 = ix[1], row_stride_words = ix[2], nrows = ix[3];
+    if (nq == 0xFFFFFFFFu) {
+        if (tid == 0) atomicOr(status, 4u);
+        return;
+    }
+    cnt[tid] = 0;
+    __syncthreads();
+    for (uint32_t q = tid; q < nq; q += SOLVER_COUNT_THREADS) {
+        uint32_t pos = ix[4 + q];
+        Fr qi = eval_le(sp, W, ws, pos);
+        Fr qv = eval_le(sp, W, ws, pos);
+        Fr qc = qi.from_mont();
+        uint32_t hi2 = qc.l[1] | qc.l[2] | qc.l[3] | qc.l[4] | qc.l[5] | qc.l[6] | qc.l[7];
+        if (hi2 || qc.l[0] >= nrows) continue;
+        uint32_t rp = row_pos0 + qc.l[0] * row_stride_words;
+        Fr ri = eval_le(sp, W, ws, rp);
+        Fr rv = eval_le(sp, W, ws, rp);
+        if (ri == qi && rv == qv) atomicAdd(&cnt[qc.l[0]], 1u);
+    }
+    __syncthreads();
+    const uint32_t pos = ix[4 + nq];
+    const uint32_t o0 = sp.calldata[pos], o1 = sp.calldata[pos + 1];
+    for (uint32_t k = tid; k < o1 - o0; k += SOLVER_COUNT_THREADS) {
+        Fr v = Fr::zero();
+        v.l[0] = k < 256 ? cnt[k] : 0u;
+        W[(size_t)(o0 + k) * ws] = v.to_mont();
+    }
+}
+#endif
+
 // per instruction: 1 / (sum of coefficients of the wire it solves)   (init-time)
 __global__ void solver_ucoef_kernel(SolverProgram sp, uint32_t n_instr, Fr* __restrict__ out) {
     uint32_t ins = blockIdx.x * blockDim.x + threadIdx.x;
