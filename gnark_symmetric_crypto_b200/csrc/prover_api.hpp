@@ -44,7 +44,7 @@ struct AssemblyKeys {
     const G2Affine* delta2_tab;   // device: j*16^i*delta2
 };
 struct AssemblyScratch {
-    DevBuf<G1XYZZ> Ar, Bs1, nrsd, win_tab;   // win_tab: 15 window multiples per variable-base product (2 per proof)
+    DevBuf<G1XYZZ> Ar, Bs1, nrsd, win_tab;   // win_tab: 15 window multiples per variable-base half-product (4 per proof)
 };
 
 // all pointers are device pointers
