@@ -19,7 +19,7 @@ void pairing_check_run(PairingWorkspace& ws, const G1Affine* Ps, const G2Affine*
     G16_LAUNCH(pairing_lines_kernel, div_up(n_pairs, 64), 64, 0, st, false, Ps, Qs, n_pairs, (const PairingConsts*)ws.consts.p, recs,
                (size_t)n_pairs);
     G16_LAUNCH(pairing_check_kernel, n_checks, PAIRING_THREADS, 0, st, true, (const LineRec*)recs, (size_t)n_pairs, pairs_per_check,
-               ok_out);
+               (const PairingConsts*)ws.consts.p, ok_out);
     G16_CHECK_LAUNCH();
 }
 
