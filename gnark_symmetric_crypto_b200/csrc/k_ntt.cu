@@ -33,13 +33,13 @@ static std::vector<NttPass> ntt_plan(int k, bool dif) {
 void ntt_domain_init(NttDomain& d, int k, const Fr& w, const Fr& g, cudaStream_t stream) {
     d.k = k;
     d.n = 1u << k;
-    DevBuf<Fr> consts(4);
+    DevBuf<Fr> consts(5);
     G16_LAUNCH(ntt_domain_consts_kernel, 1, 1, 0, stream, false, w, g, d.n, consts.p);
     G16_CHECK_LAUNCH();
-    Fr h[4];
-    consts.download(h, 4, stream);
+    Fr h[5];
+    consts.download(h, 5, stream);
     G16_CUDA(cudaStreamSynchronize(stream));
-    Fr winv = h[0], ninv = h[1], ginv = h[2];
+    Fr winv = h[0], ninv = h[1], ginv = h[2], ninv_den = h[4];
     d.den = h[3];
     uint32_t half = d.n > 1 ? d.n / 2 : 1;
     d.tw_fwd.alloc(half);
@@ -50,10 +50,14 @@ void ntt_domain_init(NttDomain& d, int k, const Fr& w, const Fr& g, cudaStream_t
     d.scale_coset_fwd.alloc(d.n);
     d.scale_coset_inv.alloc(d.n);
     d.scale_coset_only.alloc(d.n);
+    d.scale_ninv_den.alloc(d.n);
+    d.scale_coset_inv_den.alloc(d.n);
     G16_LAUNCH(ntt_coset_table_kernel, div_up(d.n, 128), 128, 0, stream, false, Fr::one(), ninv, k, d.scale_ninv.p);
     G16_LAUNCH(ntt_coset_table_kernel, div_up(d.n, 128), 128, 0, stream, false, g, ninv, k, d.scale_coset_fwd.p);
     G16_LAUNCH(ntt_coset_table_kernel, div_up(d.n, 128), 128, 0, stream, false, ginv, ninv, k, d.scale_coset_inv.p);
     G16_LAUNCH(ntt_coset_table_kernel, div_up(d.n, 128), 128, 0, stream, false, g, Fr::one(), k, d.scale_coset_only.p);
+    G16_LAUNCH(ntt_coset_table_kernel, div_up(d.n, 128), 128, 0, stream, false, Fr::one(), ninv_den, k, d.scale_ninv_den.p);
+    G16_LAUNCH(ntt_coset_table_kernel, div_up(d.n, 128), 128, 0, stream, false, ginv, ninv_den, k, d.scale_coset_inv_den.p);
     G16_CHECK_LAUNCH();
     d.dif_passes = ntt_plan(k, true);
     d.dit_passes = ntt_plan(k, false);
@@ -106,17 +110,26 @@ void ntt_run(NttDomain& d, Fr* data, size_t vec_stride, uint32_t batch, bool dif
     G16_CHECK_LAUNCH();
 }
 
+// H = (A.B - C) / (x^n - 1) with SIX transforms instead of gnark's seven (prove.go:359-384 runs C through the coset as well).
+// The witness satisfies the system (the solver checked it), so C interpolates a_i b_i on the domain: C = A.B mod (x^n - 1).
+// Writing A.B = P_lo + x^n P_hi gives C = P_lo + P_hi and H = P_hi. On the coset g.w^i, x^n = g^n =: G, so the products
+// d_i = A(g w^i) B(g w^i) are the evaluations of E = P_lo + G P_hi, and H = (E - C) / (G - 1) coefficient by coefficient:
+//   coefficients of C (one inverse transform, no trip through the coset)  and  coefficients of E (inverse coset transform of d).
+// Same polynomial, hence bit-identical coefficients; den = 1/(G - 1) and 1/n are folded into the scale tables of the two
+// inverse transforms, so the last step is a subtraction.
 void compute_h_run(NttDomain& d, Fr* a, Fr* b, Fr* c, size_t vec_stride, uint32_t batch, cudaStream_t stream) {
     if (vec_stride != d.n) throw std::invalid_argument("compute_h: vectors must be contiguous (stride == n)");
-    Fr* v[3] = {a, b, c};
-    for (int i = 0; i < 3; i++) {
+    Fr* v[2] = {a, b};
+    for (int i = 0; i < 2; i++) {
         ntt_run(d, v[i], vec_stride, batch, true, true, d.scale_coset_fwd.p, stream);    // iNTT, then * g^i / n
         ntt_run(d, v[i], vec_stride, batch, false, false, nullptr, stream);              // evaluate on the coset
     }
+    ntt_run(d, c, vec_stride, batch, true, true, d.scale_ninv_den.p, stream);            // den * coefficients of C (bit-reversed)
     size_t total = (size_t)batch * vec_stride;
-    G16_LAUNCH(h_pointwise_kernel, div_up(total, 256), 256, 0, stream, false, a, b, c, d.den, total);
-    d.launches++;
-    ntt_run(d, a, vec_stride, batch, true, true, d.scale_coset_inv.p, stream);           // coset iNTT
+    G16_LAUNCH(h_mul_kernel, div_up(total, 256), 256, 0, stream, false, a, (const Fr*)b, total);
+    ntt_run(d, a, vec_stride, batch, true, true, d.scale_coset_inv_den.p, stream);       // den * coefficients of E (bit-reversed)
+    G16_LAUNCH(h_sub_kernel, div_up(total, 256), 256, 0, stream, false, a, (const Fr*)c, total);
+    d.launches += 2;
 }
 
 void ntt_bitrev(const Fr* in, Fr* out, int k, cudaStream_t stream) {

@@ -147,16 +147,20 @@ __global__ void ntt_bitrev_kernel(const Fr* __restrict__ in, Fr* __restrict__ ou
     uint32_t r = k ? (__brev(j) >> (32 - k)) : 0u;
     out[r] = in[j];
 }
-// a[i] = (a[i]*b[i] - c[i]) * den      (prove.go:380-384)
-__global__ void h_pointwise_kernel(Fr* __restrict__ a, const Fr* __restrict__ b, const Fr* __restrict__ c, Fr den,
-                                   size_t total) {
+// compute_h, pointwise steps (see compute_h_run): a[i] *= b[i] on the coset ; a[i] -= c[i] on the coefficients
+__global__ void h_mul_kernel(Fr* __restrict__ a, const Fr* __restrict__ b, size_t total) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    a[i] = (a[i] * b[i] - c[i]) * den;
+    a[i] = a[i] * b[i];
+}
+__global__ void h_sub_kernel(Fr* __restrict__ a, const Fr* __restrict__ c, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    a[i] = a[i] - c[i];
 }
 
 // every constant is derived on the device: the product has no host-side field arithmetic
-__global__ void ntt_domain_consts_kernel(Fr w, Fr g, uint32_t n, Fr* out /* [0]=w^-1 [1]=1/n [2]=g^-1 [3]=den */) {
+__global__ void ntt_domain_consts_kernel(Fr w, Fr g, uint32_t n, Fr* out /* [0]=w^-1 [1]=1/n [2]=g^-1 [3]=den [4]=den/n */) {
     if (threadIdx.x || blockIdx.x) return;
     out[0] = w.inv();
     Fr nn = Fr::zero();
@@ -167,6 +171,7 @@ __global__ void ntt_domain_consts_kernel(Fr w, Fr g, uint32_t n, Fr* out /* [0]=
     Fr gn = g;
     for (uint32_t m = 1; m < n; m <<= 1) gn = gn.sqr();
     out[3] = (gn - Fr::one()).inv();
+    out[4] = out[3] * out[1];
 }
 // w = root28^(2^(28-k)), g = 5, both Montgomery
 __global__ void ntt_root_kernel(const uint8_t* root_be, int k, Fr* out /* [0]=w [1]=g */) {

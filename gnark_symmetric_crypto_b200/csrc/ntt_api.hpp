@@ -30,6 +30,8 @@ struct NttDomain {
     DevBuf<Fr> scale_coset_fwd;         // g^brev(j) / n    (iNTT output -> coset coefficients)
     DevBuf<Fr> scale_coset_inv;         // g^-brev(j) / n   (coset iNTT output -> coefficients)
     DevBuf<Fr> scale_coset_only;        // g^brev(j)
+    DevBuf<Fr> scale_ninv_den;          // den / n            (compute_h: coefficients of C, pre-multiplied by den = 1/(g^n - 1))
+    DevBuf<Fr> scale_coset_inv_den;     // g^-brev(j) den / n (compute_h: coefficients of E)
     Fr den;                             // 1/(g^n - 1), Montgomery
     std::vector<NttPass> dif_passes, dit_passes;
     size_t launches = 0;
