@@ -155,7 +155,10 @@ int g16_ntt(uint64_t* data, size_t n, int inverse, int coset, float* ms);
 int g16_ntt_bench(size_t n, size_t batch, int iters, float* ms_per_iter, uint64_t* checksum);
 
 /* H = (A.B - C)/Z (replaces prove.go:computeH): a,b,c = nbConstraints evaluations each.
- * h_out = n coefficients in gnark's array order (bit-reversed), which pairs index-for-index with pk.G1.Z. */
+ * h_out = n coefficients in gnark's array order (bit-reversed), which pairs index-for-index with pk.G1.Z.
+ * Precondition (what the solver guarantees, and what makes the quotient a polynomial at all): c[i] == a[i] * b[i] for every
+ * constraint. Under it the result is bit-identical with gnark's; it is obtained from six transforms instead of seven
+ * (C never visits the coset, see csrc/k_ntt.cu compute_h_run). */
 int g16_compute_h(g16_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint64_t* h_out);
 /* R1CS solve (replaces constraint/bn254 (*system).Solve) for `batch` independent witnesses.
  * witness: batch x n_witness. Outputs (any may be NULL): W batch x nbWires, A/B/C batch x nbConstraints. */
