@@ -48,6 +48,7 @@ EXPORTS = {
     "g16_verify_info": (C.c_int, [C.c_void_p, u64p]),
     "g16_verify_batch": (C.c_int, [C.c_void_p, C.c_size_t, u8p, C.c_void_p, C.c_int, u8p, C.POINTER(C.c_float)]),
     "g16_verify_free": (None, [C.c_void_p]),
+    "g16_g2_subgroup_check": (C.c_int, [u64p, C.c_size_t, u8p]),
     "g16_pairing_check": (C.c_int, [u64p, u64p, C.c_size_t, C.c_size_t, u8p]),
     "g16_set_schedule": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "g16_last_stage_ms": (C.c_int, [C.c_void_p, f32p]),

@@ -623,6 +623,21 @@ int g16_pairing_check(const uint64_t* g1_points, const uint64_t* g2_points, size
     });
 }
 
+int g16_g2_subgroup_check(const uint64_t* g2_points, size_t n, uint8_t* ok_out) {
+    return guarded([&] {
+        REQUIRE(g2_points && ok_out && n >= 1 && n <= (1u << 20), "bad argument");
+        require_device();
+        DevBuf<G2Affine> Q;
+        DevBuf<uint8_t> ok(n);
+        Q.upload((const G2Affine*)g2_points, n);
+        PairingWorkspace ws;
+        pairing_consts_ensure(ws, 0);
+        launch_g2_subgroup(Q.p, (uint32_t)n, ws.consts.p, ok.p, 0);
+        ok.download(ok_out, n);
+        G16_CUDA(cudaStreamSynchronize(0));
+    });
+}
+
 // ------------------------------------------------------------------------------------------------ stage-level: NTT
 int g16_ntt(uint64_t* data, size_t n, int inverse, int coset, float* ms) {
     return guarded([&] {

@@ -130,7 +130,8 @@ static float vctx_verify_batch(VCtx& v, size_t n, const uint8_t* proofs, const v
         v.bad.ensure(rows);
         G16_CUDA(cudaMemsetAsync(v.bad.p, 0, (size_t)rows * 4, st));
         if (v.n_commit) { v.P2.ensure((size_t)rows * 2); v.Q2.ensure((size_t)rows * 2); v.commit.ensure(rows); v.commit_tmp.ensure(rows); v.commit_x.ensure(rows); }
-        launch_verify_unpack(v.keys, v.d_proofs.p, pb, rows, v.P.p, v.Q.p, v.P2.p, v.Q2.p, v.commit.p, v.bad.p, st);
+        pairing_consts_ensure(v.pw, st);
+        launch_verify_unpack(v.keys, v.d_proofs.p, pb, rows, v.P.p, v.Q.p, v.P2.p, v.Q2.p, v.commit.p, v.pw.consts.p, v.bad.p, st);
         if (v.n_commit) {
             // challenge = hash_to_field(C) goes to the last scalar (prove.go does the same on the prover side, a11)
             launch_g1_affine_to_xyzz(v.commit.p, rows, v.commit_x.p, st);

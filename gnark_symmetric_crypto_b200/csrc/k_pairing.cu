@@ -5,15 +5,18 @@
 
 namespace g16 {
 
+void pairing_consts_ensure(PairingWorkspace& ws, cudaStream_t st) {
+    if (ws.consts_ready) return;
+    ws.consts.ensure(sizeof(PairingConsts));
+    G16_LAUNCH(pairing_consts_kernel, 1, 1, 0, st, false, (PairingConsts*)ws.consts.p);
+    G16_CHECK_LAUNCH();
+    ws.consts_ready = true;
+}
 void pairing_check_run(PairingWorkspace& ws, const G1Affine* Ps, const G2Affine* Qs, uint32_t pairs_per_check, uint32_t n_checks,
                        uint8_t* ok_out, cudaStream_t st) {
     const uint32_t n_pairs = pairs_per_check * n_checks;
     if (!n_pairs) return;
-    if (!ws.consts_ready) {
-        ws.consts.ensure(sizeof(PairingConsts));
-        G16_LAUNCH(pairing_consts_kernel, 1, 1, 0, st, false, (PairingConsts*)ws.consts.p);
-        ws.consts_ready = true;
-    }
+    pairing_consts_ensure(ws, st);
     ws.recs.ensure((size_t)n_pairs * PAIRING_STEPS * sizeof(LineRec));
     LineRec* recs = (LineRec*)ws.recs.p;
     G16_LAUNCH(pairing_lines_kernel, div_up(n_pairs, 64), 64, 0, st, false, Ps, Qs, n_pairs, (const PairingConsts*)ws.consts.p, recs,

@@ -102,9 +102,13 @@ void launch_fixed_base_tables(const AssemblyKeys& keys, G1Affine* tab1, G2Affine
     G16_CHECK_LAUNCH();
 }
 void launch_verify_unpack(const VerifyKeys& keys, const uint8_t* proofs, size_t stride, uint32_t n, G1Affine* P, G2Affine* Q,
-                          G1Affine* P2, G2Affine* Q2, G1Affine* commit, uint32_t* bad, cudaStream_t st) {
+                          G1Affine* P2, G2Affine* Q2, G1Affine* commit, const void* frob, uint32_t* bad, cudaStream_t st) {
     G16_LAUNCH(verify_unpack_kernel, dim3(div_up(n, 32), keys.n_commit ? 5 : 3), 32, 0, st, false, keys, proofs, stride, n, P, Q, P2, Q2,
-               commit, bad);
+               commit, (const Fp2*)frob, bad);
+    G16_CHECK_LAUNCH();
+}
+void launch_g2_subgroup(const G2Affine* pts, uint32_t n, const void* frob, uint8_t* ok, cudaStream_t st) {
+    G16_LAUNCH(g2_subgroup_kernel, div_up(n, 32), 32, 0, st, false, pts, n, (const Fp2*)frob, ok);
     G16_CHECK_LAUNCH();
 }
 void launch_verify_ksum(const G1XYZZ* msm, const G1Affine* commit, uint32_t n, G1Affine* P, cudaStream_t st) {

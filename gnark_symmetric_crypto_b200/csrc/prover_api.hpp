@@ -97,7 +97,9 @@ struct VerifyKeys {
     uint32_t n_commit;
 };
 void launch_verify_unpack(const VerifyKeys& keys, const uint8_t* proofs, size_t stride, uint32_t n, G1Affine* P, G2Affine* Q,
-                          G1Affine* P2, G2Affine* Q2, G1Affine* commit, uint32_t* bad, cudaStream_t st);
+                          G1Affine* P2, G2Affine* Q2, G1Affine* commit, const void* frob, uint32_t* bad, cudaStream_t st);
+// frob: device pointer to the two Frobenius constants xi^((p-1)/3), xi^((p-1)/2) (the head of PairingConsts, pairing_api.hpp)
+void launch_g2_subgroup(const G2Affine* pts, uint32_t n, const void* frob, uint8_t* ok, cudaStream_t st);
 void launch_verify_ksum(const G1XYZZ* msm, const G1Affine* commit, uint32_t n, G1Affine* P, cudaStream_t st);
 void launch_verify_verdict(const uint8_t* ok1, const uint8_t* ok2, const uint32_t* bad, uint32_t n, uint8_t* out, cudaStream_t st);
 void launch_g1_affine_to_xyzz(const G1Affine* in, uint32_t n, G1XYZZ* out, cudaStream_t st);

@@ -400,10 +400,42 @@ __global__ void wires_to_rows_kernel(const Fr* __restrict__ W, size_t w_stride, 
 // BSB22 commitment  P2[2i..] = (C, PoK),  Q2[2i..] = (G, GRootSigmaNeg).
 // role (blockIdx.y) 0: Ar + the fixed entries + the commitment count of the proof trailer ; 1: Krs ; 2: Bs ; 3: C ; 4: PoK.
 // bad[i] != 0 marks a malformed proof (flag bits, point not on its curve, wrong commitment count): it is rejected whatever
-// the pairing says. (G2 points are checked to be on the twist; the subgroup check gnark's decoder adds is not done.)
+// the pairing says. Bs is checked to be on the twist AND in the r-torsion subgroup, as gnark's decoder does (G1 has cofactor 1).
+// r-torsion test for a point of the twist, as gnark-crypto v0.14.0 ecc/bn254/g2.go IsInSubGroup (which G2Affine.SetBytes runs
+// on every decoded point): [r]P = 0  <=>  [x0+1]P + psi([x0]P) + psi^2([x0]P) = psi^3([2 x0]P), x0 = 4965661367192848881 the
+// curve seed, psi = untwist-Frobenius-twist: psi(x, y) = (conj(x) gx, conj(y) gy), gx = xi^((p-1)/3), gy = xi^((p-1)/2).
+FD G2XYZZ g2_psi(const G2XYZZ& p, const Fp2& gx, const Fp2& gy) {
+    return {p.X.conj() * gx, p.Y.conj() * gy, p.ZZ.conj(), p.ZZZ.conj()};
+}
+FD bool g2_xyzz_equal(const G2XYZZ& a, const G2XYZZ& b) {
+    if (a.is_inf() || b.is_inf()) return a.is_inf() && b.is_inf();
+    return a.X * b.ZZ == b.X * a.ZZ && a.Y * b.ZZZ == b.Y * a.ZZZ;
+}
+FD bool g2_in_subgroup(const G2Affine& q, const Fp2& gx, const Fp2& gy) {
+    if (q.is_inf()) return true;
+    Scalar256 x0;
+    x0.w[0] = 0x4a6909f1u; x0.w[1] = 0x44e992b4u;   // 4965661367192848881
+    for (int i = 2; i < 8; i++) x0.w[i] = 0;
+    const G2XYZZ P = G2XYZZ::from_affine(q);
+    const G2XYZZ a = scalar_mul(P, x0);          // [x0]P
+    const G2XYZZ b = g2_psi(a, gx, gy);          // psi([x0]P)
+    G2XYZZ lhs = a;
+    lhs.add(P);                                  // [x0+1]P
+    lhs.add(b);
+    lhs.add(g2_psi(b, gx, gy));                  // + psi^2([x0]P)
+    const G2XYZZ rhs = g2_psi(g2_psi(g2_psi(a.dbl(), gx, gy), gx, gy), gx, gy);
+    return g2_xyzz_equal(lhs, rhs);
+}
+__global__ void g2_subgroup_kernel(const G2Affine* __restrict__ pts, uint32_t n, const Fp2* __restrict__ frob, uint8_t* __restrict__ ok) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ok[i] = g2_in_subgroup(pts[i], frob[0], frob[1]) ? 1 : 0;
+}
+
 __global__ void verify_unpack_kernel(VerifyKeys keys, const uint8_t* __restrict__ proofs, size_t stride, uint32_t n,
                                      G1Affine* __restrict__ P, G2Affine* __restrict__ Q, G1Affine* __restrict__ P2,
-                                     G2Affine* __restrict__ Q2, G1Affine* __restrict__ commit, uint32_t* __restrict__ bad) {
+                                     G2Affine* __restrict__ Q2, G1Affine* __restrict__ commit, const Fp2* __restrict__ frob,
+                                     uint32_t* __restrict__ bad) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint8_t* pr = proofs + (size_t)i * stride;
@@ -428,6 +460,7 @@ __global__ void verify_unpack_kernel(VerifyKeys keys, const uint8_t* __restrict_
     } else if (role == 2) {
         G2Affine b;
         e = decompress_g2_point(pr + 32, b);
+        if (!e && !g2_in_subgroup(b, frob[0], frob[1])) e = 8;   // on the twist but outside the r-torsion: gnark's decoder rejects it
         Q[4 * (size_t)i] = b;
     } else if (role == 3) {
         G1Affine c;

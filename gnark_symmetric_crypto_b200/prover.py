@@ -396,6 +396,14 @@ class Groth16Verifier:
         return bool(self.verify_batch([proof], [public_inputs])[0])
 
 
+def g2_subgroup_check(g2s: np.ndarray) -> np.ndarray:
+    """gnark-crypto G2Affine.IsInSubGroup for affine Montgomery twist points ([n, 16] u64) -> bool array."""
+    Q = np.ascontiguousarray(g2s, dtype=np.uint64).reshape(-1, 16)
+    ok = np.zeros(len(Q), dtype=np.uint8)
+    _check(_lib.load().g16_g2_subgroup_check(_p64(Q), len(Q), _p8(ok)))
+    return ok.astype(bool)
+
+
 def pairing_check(g1s: np.ndarray, g2s: np.ndarray, pairs_per_check: int | None = None) -> np.ndarray:
     """prod_j e(P_j, Q_j) == 1 for every group of `pairs_per_check` consecutive pairs (default: one check over all pairs).
     Points affine Montgomery ([n, 8] / [n, 16] u64). Returns a bool array, one entry per check."""

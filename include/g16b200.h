@@ -131,6 +131,9 @@ void g16_verify_free(g16_vctx* ctx);
  * G2 16 x u64 (x.a0 x.a1 y.a0 y.a1), (0,0) = infinity (such a pair contributes 1). */
 int g16_pairing_check(const uint64_t* g1_points, const uint64_t* g2_points, size_t pairs_per_check, size_t n_checks,
                       uint8_t* ok_out);
+/* ok_out[i] = 1 iff the affine twist point i lies in the r-torsion subgroup G2 (gnark-crypto ecc/bn254/g2.go IsInSubGroup, the
+ * check G2Affine.SetBytes applies to every decoded point; g16_verify_batch applies it to Bs). */
+int g16_g2_subgroup_check(const uint64_t* g2_points, size_t n, uint8_t* ok_out);
 
 /* Pippenger MSM over n affine points (replaces (*G1Jac).MultiExp / (*G2Jac).MultiExp).
  * scalars: n x 4 u64; scalars_mont != 0 if they are in Montgomery form (gnark passes fr.Element vectors).

@@ -289,3 +289,29 @@ def test_libverify_json_layer(emu):
     assert call(b'{"cipher":"nope","proof":[],"publicSignals":[]}') == 0
     assert call(b'{"cipher":"chacha20","proof":"####"}') == 0                           # illegal base64
     assert call(b'[1,2') == 0 and call(b'') == 0
+
+
+def _twist_point_outside_g2(L):
+    """A point of the twist E'(Fp2) that is (almost surely) not in the r-torsion: compressed x = small values until the
+    decoder finds a square root. The twist's group order is r times a 254-bit cofactor."""
+    for t in range(2, 200):
+        raw = bytearray(64)
+        raw[63] = t          # X.A0 = t (second half of the encoding), X.A1 = 1
+        raw[31] = 1
+        raw[0] |= 0x80
+        out = np.zeros(16, dtype=np.uint64)
+        if L.g16_decompress(2, p8(np.frombuffer(bytes(raw), dtype=np.uint8).copy()), p64(out), 1) == 0 and out.any():
+            return out
+    raise AssertionError("no twist point found")
+
+
+def test_g2_subgroup_check(emu, oracle):
+    """gnark's G2 decoder rejects points outside the r-torsion subgroup (g2.go IsInSubGroup); so does the verifier."""
+    rng = np.random.default_rng(8)
+    good = oracle.g2_fixed_base(oracle.rand_field(rng, 1, 3))
+    bad = _twist_point_outside_g2(emu)
+    assert oracle.g2_add(oracle.g2_mul(bad, oracle.R_MOD - 1), bad).any()   # [r]P != 0: really outside G2 (scalars are taken mod r)
+    pts = np.concatenate([good, bad.reshape(1, 16), np.zeros((1, 16), dtype=np.uint64)])
+    ok_out = np.full(5, 7, dtype=np.uint8)
+    ok(emu, emu.g16_g2_subgroup_check(p64(pts), 5, p8(ok_out)))
+    assert ok_out.tolist() == [1, 1, 1, 0, 1]               # infinity is in the subgroup

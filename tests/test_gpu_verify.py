@@ -39,6 +39,21 @@ def test_chacha_verify_batch(G, gpu_ctx, oracle, oracle_vk, kat):
     cases.append((proofs[4][:128] + b"\x00\x00\x00\x01" + proofs[4][132:], pubs[4])); want.append(False)   # commitment count
     x_not_on_curve = bytes([0x80]) + bytes(30) + bytes([5])   # x = 5: 5^3 + 3 = 128 is not a square mod p? checked by the oracle below
     cases.append((x_not_on_curve + proofs[5][32:], pubs[5])); want.append(False)
+    # Bs on the twist but outside the r-torsion subgroup: gnark's G2 decoder (IsInSubGroup) rejects it, so must we
+    off = None
+    for t in range(2, 200):
+        raw = bytearray(64); raw[63] = t; raw[31] = 1; raw[0] |= 0x80
+        try:
+            pt = G.decompress(2, bytes(raw))
+        except G.ProverError:
+            continue
+        if pt.any():
+            off = bytes(raw)
+            assert G.g2_subgroup_check(pt).tolist() == [False]
+            break
+    assert off is not None
+    assert G.g2_subgroup_check(oracle.g2_fixed_base(oracle.ints_to_limbs([3, 0, 77]))).tolist() == [True, True, True]
+    cases.append((proofs[0][:32] + off + proofs[0][96:], pubs[0])); want.append(False)
     got = ver.verify_batch([c[0] for c in cases], [c[1] for c in cases])
     assert got.tolist() == want
     for (p, pub), w in zip(cases[:9], want[:9]):   # the oracle's verdicts on the well-formed cases
