@@ -7,6 +7,7 @@
 #include "host_parse.hpp"
 #include "msm_types.hpp"
 #include "ntt_api.hpp"
+#include "pairing_api.hpp"
 #include "prover_api.hpp"
 #include <memory>
 
@@ -204,6 +205,21 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     err.download(&herr, 1, st);
     G16_CUDA(cudaStreamSynchronize(st));
     if (herr) throw ParseError("pk: point decompression failed (flags=" + std::to_string(herr) + ")");
+    {
+        // gnark's decoder (ProvingKey.ReadFrom -> G2Affine.SetBytes) also checks that G2 points lie in the r-torsion subgroup
+        PairingWorkspace pw;
+        pairing_consts_ensure(pw, st);
+        DevBuf<G2Affine> all(2 + (size_t)pk.nB2);
+        G16_CUDA(cudaMemcpyAsync(all.p, bd2.p, 2 * sizeof(G2Affine), cudaMemcpyDeviceToDevice, st));
+        if (pk.nB2) G16_CUDA(cudaMemcpyAsync(all.p + 2, cx->B2.p, (size_t)pk.nB2 * sizeof(G2Affine), cudaMemcpyDeviceToDevice, st));
+        DevBuf<uint8_t> okb(all.n);
+        launch_g2_subgroup(all.p, (uint32_t)all.n, pw.consts.p, okb.p, st);
+        std::vector<uint8_t> hok(all.n);
+        okb.download(hok.data(), all.n, st);
+        G16_CUDA(cudaStreamSynchronize(st));
+        for (uint8_t v : hok)
+            if (!v) throw ParseError("pk: a G2 point is not in the correct subgroup");
+    }
     {
         G1Affine h1[3];
         G2Affine h2[2];

@@ -91,6 +91,16 @@ static std::unique_ptr<VCtx> vctx_create(const uint8_t* vk_bytes, size_t vk_len,
     err.download(&herr, 1, st);
     G16_CUDA(cudaStreamSynchronize(st));
     if (herr) throw ParseError("vk: point decompression failed (flags=" + std::to_string(herr) + ")");
+    {   // VerifyingKey.ReadFrom checks the subgroup of its G2 points as well
+        pairing_consts_ensure(v->pw, st);
+        DevBuf<uint8_t> okb(5);
+        launch_g2_subgroup(a2.p, 5, v->pw.consts.p, okb.p, st);
+        uint8_t hok[5];
+        okb.download(hok, 5, st);
+        G16_CUDA(cudaStreamSynchronize(st));
+        for (uint8_t x : hok)
+            if (!x) throw ParseError("vk: a G2 point is not in the correct subgroup");
+    }
     v->keys.beta2 = h2[0]; v->keys.gamma2 = h2[1]; v->keys.delta2 = h2[2]; v->keys.ped_g = h2[3]; v->keys.ped_gneg = h2[4];
     v->keys.n_commit = v->n_commit;
     // fixed-base table of K: one bucket set per proof, like the prover's wire-driven queries
