@@ -13,10 +13,13 @@ serialisation) over one batch of 1024 synthetic requests per GPU. Prints ONE JSO
   roofline  the dominant kernel (G1 bucket accumulation): algorithmic IMADs (2640 per mixed addition) per
           launch / its mean launch time, against the IMAD rate measured in this run by g16_imad_peak
   cpu_baseline  the oracle's prover ("port": gnark cannot run here) on the host cores, bounded sample
+  verified  all 1024 proofs of the measured batch pass the GPU verifier (g16_verify_batch) under the reference's vk.chacha20
+  single_request  one request through the inner seam with host buffers (BASELINE config 1), wall clock
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -105,6 +108,23 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def chacha_public_inputs_be(cts, nonces, counters, inputs):
+    """Public witness of the ChaCha circuit (libraries/verifier/impl/verifiers.go:59-85) for n requests, as 32-byte big-endian
+    field elements [n, 1152, 32]: Counter bits, Nonce[3] (little-endian words), In[16], Out[16] (big-endian words), every
+    word as 32 bits LSB first."""
+    import numpy as np
+    n = len(counters)
+    words = np.concatenate([
+        np.asarray(counters, dtype=np.uint32).reshape(n, 1),
+        np.frombuffer(nonces.tobytes(), dtype="<u4").reshape(n, 3),
+        np.frombuffer(inputs.tobytes(), dtype=">u4").reshape(n, 16).astype(np.uint32),
+        np.frombuffer(cts.tobytes(), dtype=">u4").reshape(n, 16).astype(np.uint32)], axis=1)          # [n, 36]
+    bits = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).astype(np.uint8)   # [n, 36, 32]
+    out = np.zeros((n, 36 * 32, 32), dtype=np.uint8)
+    out[:, :, 31] = bits.reshape(n, 36 * 32)
+    return out
 
 
 def make_requests(n: int, seed: bytes):
@@ -268,6 +288,25 @@ def run_gpu(args):
     e2e_total_ms, _ = aggregate(e2e_ms, BATCH * args.steps, dev)
     assert np.array_equal(pproofs.numpy(), ref_proofs), "device-resident and end-to-end paths disagree"
 
+    # ---------------- every proof of the measured batch goes through the GPU verifier under the reference's vk.chacha20
+    verified = None
+    if rank == 0:
+        vk = (ROOT / "tests/golden/vk.chacha20").read_bytes()
+        ver = G.Groth16Verifier(vk, device=local)
+        pub = chacha_public_inputs_be(cts, no, c, i)
+        prs = [ref_proofs[j * ctx.proof_bytes:(j + 1) * ctx.proof_bytes].tobytes() for j in range(n)]
+        okv = np.zeros(n, dtype=np.uint8)
+        ms_v = ctypes.c_float(0)
+        rc = L.g16_verify_batch(ver._h, n, ref_proofs.ctypes.data_as(u8p), pub.ctypes.data_as(ctypes.c_void_p), 1,
+                                okv.ctypes.data_as(u8p), ctypes.byref(ms_v))
+        if rc:
+            raise RuntimeError(L.g16_last_error().decode())
+        assert int(okv.sum()) == n and len(set(prs)) == n, "a proof of the measured batch was rejected by the verifier"
+        verified = {"proofs": n, "accepted": int(okv.sum()), "device_ms": float(ms_v.value), "key": "vk.chacha20 (the reference's)",
+                    "path": "g16_verify_batch (GPU pairing check, one verdict per proof)"}
+        ver.close()
+    barrier()
+
     # ---------------- single-request latency (BASELINE config 1: what one libprove Prove call costs), rank 0 only
     single = None
     if rank == 0:
@@ -346,6 +385,7 @@ def run_gpu(args):
                          "imad_wide_peak": imad["imad_wide_per_s"] / 1e12, "modmul_per_s": imad["modmul_per_s"]},
             "roofline_ntt": ntt_roof,
             "stages_ms_per_step": {kk: v / args.steps for kk, v in stages.items() if kk != "launches"},
+            "verified": verified,
             "single_request": single,
             "cpu_baseline": cpu,
         }
