@@ -13,6 +13,7 @@ serialisation) over one batch of 1024 synthetic requests per GPU. Prints ONE JSO
   roofline  the dominant kernel (G1 bucket accumulation): algorithmic IMADs (2640 per mixed addition) per
           launch / its mean launch time, against the IMAD rate measured in this run by g16_imad_peak
   cpu_baseline  the oracle's prover ("port": gnark cannot run here) on the host cores, bounded sample
+  msm_standalone  one 2^22-point G1 MSM (BASELINE config 5), one-shot and fixed-base, Gpts/s and fraction of the IMAD peak
   verified  all 1024 proofs of the measured batch pass the GPU verifier (g16_verify_batch) under the reference's vk.chacha20
   single_request  one request through the inner seam with host buffers (BASELINE config 1), wall clock
 """
@@ -307,6 +308,37 @@ def run_gpu(args):
         ver.close()
     barrier()
 
+    # ---------------- second half of BASELINE's metric: one standalone G1 MSM (config 5) vs the IMAD roofline, rank 0 only.
+    # Points: pk.G1.Z (decompressed on the GPU) tiled to 2^22; scalars uniform 254-bit. Correctness of this path is the
+    # tests' job (tests/test_gpu.py: MSM 2^20 against the field-only oracle); here it is only timed.
+    msm_line = None
+    if rank == 0 and not args.no_msm:
+        import struct
+        off = 8 + 160 + 1 + 96
+        for _ in range(2):                                  # skip G1.A, G1.B
+            cnt = struct.unpack(">I", pk[off:off + 4])[0]
+            off += 4 + 32 * cnt
+        nz = struct.unpack(">I", pk[off:off + 4])[0]
+        zpts = G.decompress(1, pk[off + 4:off + 4 + 32 * nz])
+        lg = 22
+        nn = 1 << lg
+        rng = np.random.default_rng(5)
+        pts = zpts[rng.integers(0, nz, nn)]
+        sc = rng.integers(0, 1 << 63, size=(nn, 4), dtype=np.int64).astype(np.uint64)
+        sc[:, 3] &= np.uint64((1 << 60) - 1)                # < r
+        adds = min(((254 + cc - 1) // cc) * (nn + (1 << cc)) for cc in range(4, 25))   # SURVEY 8d adds_alg(N)
+        msm_line = {"log2n": lg, "adds_alg": adds}
+        for mode in ("one_shot", "fixed_base"):
+            plan = G.MsmPlan(1, pts, precompute=(mode == "fixed_base"), device=local)
+            plan.set_scalars(sc)
+            plan.run()
+            best = min(float(plan.run()[1][0]) for _ in range(3))
+            plan.close()
+            msm_line[mode] = {"ms": best, "Gpts_per_s": nn / best / 1e6,
+                              "frac_of_imad_peak": adds * IMAD_PER_MADD_G1 / (best / 1e3) / imad["imad_per_s"]}
+        del pts, sc
+    barrier()
+
     # ---------------- single-request latency (BASELINE config 1: what one libprove Prove call costs), rank 0 only
     single = None
     if rank == 0:
@@ -385,6 +417,7 @@ def run_gpu(args):
                          "imad_wide_peak": imad["imad_wide_per_s"] / 1e12, "modmul_per_s": imad["modmul_per_s"]},
             "roofline_ntt": ntt_roof,
             "stages_ms_per_step": {kk: v / args.steps for kk, v in stages.items() if kk != "launches"},
+            "msm_standalone": msm_line,
             "verified": verified,
             "single_request": single,
             "cpu_baseline": cpu,
@@ -402,6 +435,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-msm", action="store_true", help="skip the standalone 2^22-point MSM line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
