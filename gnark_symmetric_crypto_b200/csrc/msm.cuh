@@ -473,11 +473,16 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     // serial chain inside a node instead (2 x arity additions per level), so it gets arity 4 and more, shorter levels.
     const uint32_t segs = sh.rows * sh.segs_per_row();
     uint32_t n_in = (uint32_t)sh.nbk;
-    const int log_g = ((size_t)segs * ((n_in + MSM_TREE_G - 1) / MSM_TREE_G) < (size_t)148 * 256) ? MSM_TREE_LOG_G_SMALL : MSM_TREE_LOG_G;
+    // A single MSM re-decides the arity at every level (its upper levels are small problems: 2^22 points, fixed base, reduce
+    // 3.8 -> 2.7 ms); a batch keeps arity 32 below a wide first level (measured: 16.6 vs 17.4 ms per 1024 proofs).
+    const bool tree_dynamic = sh.rows == 1;
+    int log_g = ((size_t)segs * ((n_in + MSM_TREE_G - 1) / MSM_TREE_G) < (size_t)148 * 256) ? MSM_TREE_LOG_G_SMALL : MSM_TREE_LOG_G;
     const X* inR = ws.buckets.p;
     const X* inV = nullptr;
     int level = 1, log_span = 0, pp = 0;
     while (true) {
+        if (tree_dynamic)   // re-decide per level: the upper levels of a wide tree are small problems too
+            log_g = ((size_t)segs * ((n_in + MSM_TREE_G - 1) / MSM_TREE_G) < (size_t)148 * 256) ? MSM_TREE_LOG_G_SMALL : MSM_TREE_LOG_G;
         uint32_t n_out = (n_in + (1u << log_g) - 1) >> log_g;
         ws.lvlR[pp].ensure((size_t)segs * n_out);
         ws.lvlV[pp].ensure((size_t)segs * n_out);
