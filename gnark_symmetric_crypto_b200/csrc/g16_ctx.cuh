@@ -32,6 +32,12 @@ struct Ctx {
     DevBuf<G1Affine> A, B, Z, K, ped_basis, ped_basis_sigma;
     DevBuf<G2Affine> B2;
     PrecompQuery qA, qB, qZ, qK;
+    // evaluation-basis form of the Z query (ctx_build_eval_tables): Sum_j d_j Qd_j + Sum_j c_j Qc_j = Sum_k h_k Z_k
+    PrecompQuery qQd, qQc;
+    int eval_z = -1;                  // G16_EVAL_Z: 0 never, 1 always, -1 (default) for batches >= eval_z_min
+    uint32_t eval_z_min = 256;
+    bool eval_ready = false;
+    DevBuf<G1XYZZ> resZc;
     DevBuf<G2Affine> tabB2;
     int cB2 = 0;
     AssemblyKeys keys;
@@ -138,13 +144,67 @@ static void ctx_build_tables(Ctx& cx) {
     cx.tables_ready = true;
 }
 
+// Evaluation-basis tables of the Z query. h = compute_h(a, b, c) is linear in (d, c): d_j = A(g w^j) B(g w^j) on the coset
+// and c_j the evaluations of C on the domain (compute_h_run: h = M1 d - M2 c). Hence
+//     Sum_k h_k Z_k = Sum_j d_j Qd_j + Sum_j c_j Qc_j,   Qd_j = Sum_k M1[k][j] Z_k,   Qc_j = -Sum_k M2[k][j] Z_k,
+// the same group element as gnark's MultiExp(pk.G1.Z, h) (prove.go:267-275), so the proof bytes do not change. With these
+// bases the prover skips the last two of the six transforms (coefficients of C, coefficients of E) and the subtraction;
+// the evaluations of C are {0, +-1} and a few 34-bit sums in the ChaCha circuit, so the second sum is
+// a handful of additions. The columns of M1 / M2 come from the very transform compute_h_run uses (unit vectors through
+// ntt_run), 512 at a time, and each Q is one row of the batched fixed-base MSM over pk.G1.Z: built once per context.
+static void ctx_build_eval_tables(Ctx& cx) {
+    if (cx.eval_ready) return;
+    cudaStream_t st = cx.stream;
+    auto nwin = [](int c) { return (254 + c - 1) / c; };
+    const uint32_t n = (uint32_t)cx.n_dom;
+    const uint32_t blk = 512;
+    DevBuf<Fr> cols((size_t)blk * n);
+    DevBuf<G1XYZZ> qx(n);
+    DevBuf<G1Affine> qaff(n);
+    for (int which = 0; which < 2; which++) {
+        // columns of C beyond the last constraint only ever meet zero scalars: left at infinity
+        const uint32_t ncols = which ? cx.n_constraints : n;
+        G16_CUDA(cudaMemsetAsync(qx.p, 0, (size_t)n * sizeof(G1XYZZ), st));
+        for (uint32_t j0 = 0; j0 < ncols; j0 += blk) {
+            uint32_t rows = ncols - j0 < blk ? ncols - j0 : blk;
+            compute_h_columns(cx.dom, cols.p, rows, j0, which, st);
+            MsmShape sh = msm_make_shape(cx.qZ.n, rows, cx.qZ.c, 1);
+            msm_run_g1(cx.ws1, sh, cx.qZ.table.p, cols.p, n, 1, nullptr, 1, st, nullptr);
+            G16_CUDA(cudaMemcpyAsync(qx.p + j0, cx.ws1.result.p, (size_t)rows * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
+        }
+        xyzz_to_affine_g1(qx.p, n, qaff.p, st);
+        PrecompQuery& q = which ? cx.qQc : cx.qQd;
+        // The C half meets ~6 k scalars +-1 and a few hundred 34-bit values per proof: a narrow window keeps its bucket set
+        // (and the reduction tree over it, which costs per bucket, not per entry) tiny. Measured with c = 13: 6 ms per
+        // 1024 proofs in msm_tree_kernel alone, as much as the two transforms this path removes.
+        q.n = ncols;
+        q.c = which ? env_int("G16_C_QC", 8) : cx.qZ.c;
+        q.table.alloc((size_t)q.n * nwin(q.c));
+        msm_precompute_g1(qaff.p, q.n, nwin(q.c), q.c, q.table.p, st);
+    }
+    G16_CUDA(cudaStreamSynchronize(st));
+    cx.ws1.log_reset();
+    cx.eval_ready = true;
+}
+
 static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, const uint8_t* r1cs_bytes, size_t r1cs_len,
                                        int device) {
     std::unique_ptr<Ctx> cx(new Ctx());
     cx->device = device;
     G16_CUDA(cudaSetDevice(device));
     G16_CUDA(cudaStreamCreate(&cx->stream));
+#if defined(G16_EMU)
     G16_CUDA(cudaStreamCreate(&cx->stream2));
+#else
+    {
+        // The side stream carries the short wire-driven queries. At default priority its blocks are only dispatched when a
+        // long kernel of the main stream drains, so the side stream trails the main one and the assembly waits for it;
+        // at the highest priority its blocks take the next free slots and the work hides inside the long kernels.
+        int least = 0, greatest = 0;
+        G16_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        G16_CUDA(cudaStreamCreateWithPriority(&cx->stream2, cudaStreamDefault, env_int("G16_SIDE_PRIO", 1) ? greatest : least));
+    }
+#endif
     G16_CUDA(cudaEventCreate(&cx->ev_fork));
     G16_CUDA(cudaEventCreate(&cx->ev_join));
     G16_CUDA(cudaStreamCreate(&cx->stream3));
@@ -157,6 +217,8 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     // lane only time-slice with them; the pipelined schedule stays available (G16_PIPELINE=1) but is not the default.
     cx->pipeline = env_int("G16_PIPELINE", 0);
     cx->sub_batch = (uint32_t)env_int("G16_SUBBATCH", 512);
+    cx->eval_z = env_int("G16_EVAL_Z", -1);
+    cx->eval_z_min = (uint32_t)env_int("G16_EVAL_Z_MIN", 256);
     if (cx->sub_batch == 0) cx->sub_batch = 1;
 
     PkFile pk = parse_pk(pk_bytes, pk_len);
@@ -462,7 +524,7 @@ static void ctx_ensure_batch(Ctx& cx, size_t n) {
     cx.Aev.ensure(n * cx.n_dom);
     cx.Bev.ensure(n * cx.n_dom);
     cx.Cev.ensure(n * cx.n_dom);
-    cx.resA.ensure(n); cx.resB1.ensure(n); cx.resK.ensure(n); cx.resZ.ensure(n); cx.resB2.ensure(n);
+    cx.resA.ensure(n); cx.resB1.ensure(n); cx.resK.ensure(n); cx.resZ.ensure(n); cx.resB2.ensure(n); cx.resZc.ensure(n);
     cx.d_proofs.ensure(n * cx.proof_bytes());
     cx.d_ct.ensure(n * 64);
     cx.d_rs.ensure(2 * n);
@@ -500,8 +562,10 @@ static size_t ctx_solve(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaStream_
 }
 
 // the wire-driven queries of one sub-batch (A, B1, K on G1, B on G2, the commitment PoK): short, latency-bound kernels
-static void ctx_wire_queries(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaStream_t st2) {
+static void ctx_wire_queries(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaStream_t st2, bool eval_z = false) {
     const Fr* w = cx.W.p + sb;   // column offset into the wire-major array
+    if (eval_z)   // C-evaluation half of the Z query: almost every scalar is 0 or +-1
+        run_query_g1(cx.ws1b, st2, cx.qQc, cx.Cev.p + sb * cx.n_dom, cx.n_dom, 1, false, rows, cx.resZc.p + sb, nullptr);
     run_query_g1(cx.ws1b, st2, cx.qA, w, 1, n, true, rows, cx.resA.p + sb, nullptr);
     run_query_g1(cx.ws1b, st2, cx.qB, w, 1, n, true, rows, cx.resB1.p + sb, nullptr);
     run_query_g1(cx.ws1b, st2, cx.qK, w, 1, n, true, rows, cx.resK.p + sb, nullptr);
@@ -518,6 +582,9 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     cudaStream_t st = cx.stream;
     ctx_build_tables(cx);
     ctx_ensure_batch(cx, n);
+    // evaluation-basis Z query (no commitment circuits only: their C evaluations are mostly full-width)
+    const bool eval_z = !cx.n_commit && !cx.pipeline && (cx.eval_z > 0 || (cx.eval_z < 0 && n >= cx.eval_z_min));
+    if (eval_z) ctx_build_eval_tables(cx);
     StageTimer& tm = cx.timer;
     tm.reset();
     size_t l0 = cx.ws1.launches + cx.ws1c.launches + cx.ws1b.launches + cx.ws2.launches + cx.dom.launches;
@@ -554,10 +621,15 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
             uint32_t rows = (uint32_t)((n - sb) < cx.sub_batch ? (n - sb) : cx.sub_batch);
             Fr* a = cx.Aev.p + sb * cx.n_dom;
             tm.mark(ST_H, st);
-            compute_h_run(cx.dom, a, cx.Bev.p + sb * cx.n_dom, cx.Cev.p + sb * cx.n_dom, cx.n_dom, rows, st);
-            // h (gnark order) pairs index-for-index with G1.Z; the other queries read wire values through their maps
-            run_query_g1(cx.ws1, st, cx.qZ, a, cx.n_dom, 1, false, rows, cx.resZ.p + sb, &tm);
-            ctx_wire_queries(cx, n, sb, rows, st2);
+            if (eval_z) {
+                compute_d_run(cx.dom, a, cx.Bev.p + sb * cx.n_dom, cx.n_dom, rows, st);
+                run_query_g1(cx.ws1, st, cx.qQd, a, cx.n_dom, 1, false, rows, cx.resZ.p + sb, &tm);
+            } else {
+                compute_h_run(cx.dom, a, cx.Bev.p + sb * cx.n_dom, cx.Cev.p + sb * cx.n_dom, cx.n_dom, rows, st);
+                // h (gnark order) pairs index-for-index with G1.Z; the other queries read wire values through their maps
+                run_query_g1(cx.ws1, st, cx.qZ, a, cx.n_dom, 1, false, rows, cx.resZ.p + sb, &tm);
+            }
+            ctx_wire_queries(cx, n, sb, rows, st2, eval_z);
         }
     } else {
         // Pipelined schedule: sub-batch k runs its whole chain (solve -> H -> Z query) on lane k % 2, so the latency-bound
@@ -591,6 +663,7 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     G16_CUDA(cudaEventRecord(cx.ev_join, st2));
     G16_CUDA(cudaStreamWaitEvent(st, cx.ev_join, 0));
     tm.mark(ST_ASSEMBLE, st);
+    if (eval_z) { xyzz_add_g1(cx.resZ.p, cx.resZc.p, (uint32_t)n, st); own += 1; }
     own += launch_assemble(cx.keys, cx.asm_scratch, cx.n_commit != 0, (uint32_t)n, cx.resA.p, cx.resB1.p, cx.resK.p, cx.resZ.p,
                            cx.d_rs.p, cx.d_proofs.p, cx.proof_bytes(), st);
     if (cx.n_commit) {
@@ -616,7 +689,7 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     cx.counters[3] = cx.ws2.log_n;
     cx.counters[4] = cx.launches;
     cx.counters[5] = n;
-    cx.counters[7] = (uint64_t)cx.sub_batch | ((uint64_t)(piped ? 1 : 0) << 32);
+    cx.counters[7] = (uint64_t)cx.sub_batch | ((uint64_t)(piped ? 1 : 0) << 32) | ((uint64_t)(eval_z ? 1 : 0) << 33);
     if (status & 4u) throw std::runtime_error("solver: unsupported hint");
     if (status & 3u) throw std::domain_error("witness does not satisfy the constraint system");
     return total;

@@ -132,6 +132,30 @@ void compute_h_run(NttDomain& d, Fr* a, Fr* b, Fr* c, size_t vec_stride, uint32_
     d.launches += 2;
 }
 
+// The first four transforms of compute_h_run and the pointwise product: on return `a` holds d_i = A(g w^i) B(g w^i) in natural
+// order; b is clobbered. The Z query can consume d (and the untouched evaluations of C) directly over the evaluation-basis
+// tables built by ctx_build_eval_tables, so H is never materialised on that path.
+void compute_d_run(NttDomain& d, Fr* a, Fr* b, size_t vec_stride, uint32_t batch, cudaStream_t stream) {
+    if (vec_stride != d.n) throw std::invalid_argument("compute_d: vectors must be contiguous (stride == n)");
+    Fr* v[2] = {a, b};
+    for (int i = 0; i < 2; i++) {
+        ntt_run(d, v[i], vec_stride, batch, true, true, d.scale_coset_fwd.p, stream);
+        ntt_run(d, v[i], vec_stride, batch, false, false, nullptr, stream);
+    }
+    size_t total = (size_t)batch * vec_stride;
+    G16_LAUNCH(h_mul_kernel, div_up(total, 256), 256, 0, stream, false, a, (const Fr*)b, total);
+    d.launches += 1;
+    G16_CHECK_LAUNCH();
+}
+// Column j0 + r of the linear map (d, c) -> h of compute_h_run, one column per row of `out` (rows x n, contiguous):
+// which = 0: h as a function of d (inverse coset transform, den/n folded in); which = 1: minus h as a function of the
+// evaluations of C (inverse transform) -- the sign is folded into the unit vector.
+void compute_h_columns(NttDomain& d, Fr* out, uint32_t rows, uint32_t j0, int which, cudaStream_t stream) {
+    G16_CUDA(cudaMemsetAsync(out, 0, (size_t)rows * d.n * sizeof(Fr), stream));
+    G16_LAUNCH(unit_rows_kernel, div_up(rows, 128), 128, 0, stream, false, out, d.n, rows, j0, which);
+    ntt_run(d, out, d.n, rows, true, true, which ? d.scale_ninv_den.p : d.scale_coset_inv_den.p, stream);
+}
+
 void ntt_bitrev(const Fr* in, Fr* out, int k, cudaStream_t stream) {
     G16_LAUNCH(ntt_bitrev_kernel, div_up((size_t)1 << k, 256), 256, 0, stream, false, in, out, k);
     G16_CHECK_LAUNCH();

@@ -159,6 +159,15 @@ __global__ void h_sub_kernel(Fr* __restrict__ a, const Fr* __restrict__ c, size_
     a[i] = a[i] - c[i];
 }
 
+// rows of unit vectors (evaluation-basis tables of the Z query, g16_ctx.cuh ctx_build_eval_tables): out must be zeroed;
+// row r gets +-1 (Montgomery) at position j0 + r
+__global__ void unit_rows_kernel(Fr* __restrict__ out, uint32_t n, uint32_t rows, uint32_t j0, int negate) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows || j0 + r >= n) return;
+    Fr one = Fr::one();
+    out[(size_t)r * n + j0 + r] = negate ? one.neg() : one;
+}
+
 // every constant is derived on the device: the product has no host-side field arithmetic
 __global__ void ntt_domain_consts_kernel(Fr w, Fr g, uint32_t n, Fr* out /* [0]=w^-1 [1]=1/n [2]=g^-1 [3]=den [4]=den/n */) {
     if (threadIdx.x || blockIdx.x) return;

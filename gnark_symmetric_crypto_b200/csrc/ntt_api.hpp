@@ -48,6 +48,10 @@ void ntt_run(NttDomain& d, Fr* data, size_t vec_stride, uint32_t batch, bool dif
 // a, b, c: `batch` contiguous vectors of n Fr each (vec_stride == n), zero-padded evaluations in natural order. On
 // return `a` holds the coefficients of H in gnark's array order (bit-reversed); b and c are clobbered.
 void compute_h_run(NttDomain& d, Fr* a, Fr* b, Fr* c, size_t vec_stride, uint32_t batch, cudaStream_t stream);
+// a <- d_i = A(g w^i) B(g w^i) (natural order), b clobbered: compute_h_run without its last two transforms
+void compute_d_run(NttDomain& d, Fr* a, Fr* b, size_t vec_stride, uint32_t batch, cudaStream_t stream);
+// rows of `out` (rows x n) <- columns j0.. of the map d -> h (which = 0) or c_evals -> -h... see k_ntt.cu
+void compute_h_columns(NttDomain& d, Fr* out, uint32_t rows, uint32_t j0, int which, cudaStream_t stream);
 void ntt_bitrev(const Fr* in, Fr* out, int k, cudaStream_t stream);
 // big-endian canonical 32-byte scalars -> Montgomery Fr (reduced mod r)
 void fr_be_to_mont(const uint8_t* d_in, uint32_t n, Fr* d_out, cudaStream_t stream);

@@ -262,7 +262,8 @@ class Groth16Context:
         names = ["g1_madds", "g2_madds", "g1_acc_launches", "g2_acc_launches", "launches", "proofs", "g1_madds_main_stream"]
         out = {k: int(v) for k, v in zip(names, c)}
         out["sub_batch"] = int(c[7]) & 0xFFFFFFFF
-        out["pipelined"] = bool(int(c[7]) >> 32)
+        out["pipelined"] = bool((int(c[7]) >> 32) & 1)
+        out["eval_basis_z"] = bool((int(c[7]) >> 33) & 1)   # Z query over the evaluation-basis tables (4 transforms, no H)
         return out
 
     # ---- stage-level

@@ -248,6 +248,31 @@ def test_batch_1024_config4(G, gpu_ctx, oracle, oracle_prover, oracle_vk):
     assert p5[0] == proofs[5]
 
 
+def test_evaluation_basis_z_query_is_bit_identical(G, gpu_ctx, pk_bytes, r1cs_bytes, kat, monkeypatch):
+    """Large batches take the Z query over the evaluation-basis tables (four transforms, H never materialised).
+    Forced on for a single request it must reproduce the KAT proof; forced off for a batch above the switch-over it must
+    give the bytes the default path gives."""
+    rs = kat["r"].to_bytes(32, "big") + kat["s"].to_bytes(32, "big")
+    monkeypatch.setenv("G16_EVAL_Z", "1")
+    on = G.Groth16Context(pk_bytes, r1cs_bytes, device=0)
+    monkeypatch.setenv("G16_EVAL_Z", "0")
+    off = G.Groth16Context(pk_bytes, r1cs_bytes, device=0)
+    monkeypatch.delenv("G16_EVAL_Z")
+    try:
+        proofs, cts = on.prove_chacha_batch([kat["key"]], [kat["nonce"]], [kat["counter"]], [kat["input"]], [rs])
+        assert proofs[0] == kat["proof"] and cts[0] == kat["ct"]
+        n = 300
+        keys, nonces, ctrs, ins, rss = batch_inputs(n, b"g16-b200-evalz")
+        p_def, _ = gpu_ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rss)     # n >= 256: evaluation basis
+        p_off, _ = off.prove_chacha_batch(keys, nonces, ctrs, ins, rss)         # coefficient basis (compute_h + pk.G1.Z)
+        p_on, _ = on.prove_chacha_batch(keys[:40], nonces[:40], ctrs[:40], ins[:40], rss[:40])
+        assert p_def == p_off
+        assert p_on == p_off[:40]
+    finally:
+        on.close()
+        off.close()
+
+
 def test_pairing_check_matches_oracle(G, oracle):
     """SURVEY §8f rank 4 (the arithmetic under groth16.Verify): products of 1..4 pairings that are 1 by bilinearity are
     accepted, perturbed ones rejected, infinity pairs contribute 1 — the same verdicts as the oracle's pairing."""
