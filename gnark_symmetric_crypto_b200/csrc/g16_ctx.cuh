@@ -150,29 +150,38 @@ static void ctx_build_tables(Ctx& cx) {
 // the same group element as gnark's MultiExp(pk.G1.Z, h) (prove.go:267-275), so the proof bytes do not change. With these
 // bases the prover skips the last two of the six transforms (coefficients of C, coefficients of E) and the subtraction;
 // the evaluations of C are {0, +-1} and a few 34-bit sums in the ChaCha circuit, so the second sum is
-// a handful of additions. The columns of M1 / M2 come from the very transform compute_h_run uses (unit vectors through
-// ntt_run), 512 at a time, and each Q is one row of the batched fixed-base MSM over pk.G1.Z: built once per context.
+// a handful of additions. Built once per context, as a DFT over group elements (default) or, as a cross-check
+// (G16_EVAL_BUILD_MSM=1), column by column from the very transform compute_h_run uses (unit vectors through ntt_run, 512 at
+// a time, each Q one row of the batched fixed-base MSM over pk.G1.Z).
 static void ctx_build_eval_tables(Ctx& cx) {
     if (cx.eval_ready) return;
     cudaStream_t st = cx.stream;
     auto nwin = [](int c) { return (254 + c - 1) / c; };
     const uint32_t n = (uint32_t)cx.n_dom;
     const uint32_t blk = 512;
-    DevBuf<Fr> cols((size_t)blk * n);
+    const bool by_msm = env_int("G16_EVAL_BUILD_MSM", 0) != 0;   // cross-check builder: one batched MSM row per table point
+    DevBuf<Fr> cols(by_msm ? (size_t)blk * n : 0);
     DevBuf<G1XYZZ> qx(n);
     DevBuf<G1Affine> qaff(n);
     for (int which = 0; which < 2; which++) {
-        // columns of C beyond the last constraint only ever meet zero scalars: left at infinity
+        // columns of C beyond the last constraint only ever meet zero scalars: not built
         const uint32_t ncols = which ? cx.n_constraints : n;
-        G16_CUDA(cudaMemsetAsync(qx.p, 0, (size_t)n * sizeof(G1XYZZ), st));
-        for (uint32_t j0 = 0; j0 < ncols; j0 += blk) {
-            uint32_t rows = ncols - j0 < blk ? ncols - j0 : blk;
-            compute_h_columns(cx.dom, cols.p, rows, j0, which, st);
-            MsmShape sh = msm_make_shape(cx.qZ.n, rows, cx.qZ.c, 1);
-            msm_run_g1(cx.ws1, sh, cx.qZ.table.p, cols.p, n, 1, nullptr, 1, st, nullptr);
-            G16_CUDA(cudaMemcpyAsync(qx.p + j0, cx.ws1.result.p, (size_t)rows * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
+        if (!by_msm) {
+            // Q = DFT over the group of the pre-scaled key points (k_msm_g1.cu group_dft_g1): 15 stages of 16 384 scalar
+            // products instead of 56 k MSM rows (7.7 s -> tens of ms)
+            group_dft_g1(cx.Z.p, cx.nZ, cx.k_dom, which ? cx.dom.scale_ninv_den.p : cx.dom.scale_coset_inv_den.p, which,
+                         cx.dom.tw_inv.p, qx.p, ncols, qaff.p, st);
+        } else {
+            G16_CUDA(cudaMemsetAsync(qx.p, 0, (size_t)n * sizeof(G1XYZZ), st));
+            for (uint32_t j0 = 0; j0 < ncols; j0 += blk) {
+                uint32_t rows = ncols - j0 < blk ? ncols - j0 : blk;
+                compute_h_columns(cx.dom, cols.p, rows, j0, which, st);
+                MsmShape sh = msm_make_shape(cx.qZ.n, rows, cx.qZ.c, 1);
+                msm_run_g1(cx.ws1, sh, cx.qZ.table.p, cols.p, n, 1, nullptr, 1, st, nullptr);
+                G16_CUDA(cudaMemcpyAsync(qx.p + j0, cx.ws1.result.p, (size_t)rows * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
+            }
+            xyzz_to_affine_g1(qx.p, n, qaff.p, st);
         }
-        xyzz_to_affine_g1(qx.p, n, qaff.p, st);
         PrecompQuery& q = which ? cx.qQc : cx.qQd;
         // The C half meets ~6 k scalars +-1 and a few hundred 34-bit values per proof: a narrow window keeps its bucket set
         // (and the reduction tree over it, which costs per bucket, not per entry) tiny. Measured with c = 13: 6 ms per

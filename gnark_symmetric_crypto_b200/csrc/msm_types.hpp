@@ -72,6 +72,9 @@ void msm_run_g2(MsmWorkspace<G2>& ws, const MsmShape& sh, const G2Affine* bases,
 void msm_precompute_g1(const G1Affine* pts, uint32_t n, int nwin, int c, G1Affine* table, cudaStream_t stream);
 void msm_precompute_g2(const G2Affine* pts, uint32_t n, int nwin, int c, G2Affine* table, cudaStream_t stream);
 void xyzz_add_g1(G1XYZZ* a, const G1XYZZ* b, uint32_t n, cudaStream_t stream);   // a[i] += b[i]
+// out[j] = affine(Sum_k w^(-jk) * scale[brev(k)] * Z[brev(k)]), j < n_out (sign flipped if negate); work: 2^lg elements
+void group_dft_g1(const G1Affine* Z, uint32_t nZ, int lg, const Fr* scale, int negate, const Fr* tw_inv, G1XYZZ* work,
+                  uint32_t n_out, G1Affine* out, cudaStream_t stream);
 void xyzz_to_affine_g1(const G1XYZZ* in, uint32_t n, G1Affine* out, cudaStream_t stream);
 void xyzz_to_affine_g2(const G2XYZZ* in, uint32_t n, G2Affine* out, cudaStream_t stream);
 

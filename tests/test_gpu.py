@@ -273,6 +273,21 @@ def test_evaluation_basis_z_query_is_bit_identical(G, gpu_ctx, pk_bytes, r1cs_by
         off.close()
 
 
+def test_evaluation_basis_tables_two_builders(G, pk_bytes, r1cs_bytes, kat, monkeypatch):
+    """The evaluation-basis tables are built as a DFT over group elements; the cross-check builder derives every table point
+    as an MSM over pk.G1.Z of a column of compute_h's own linear map. Both must give the KAT proof."""
+    rs = kat["r"].to_bytes(32, "big") + kat["s"].to_bytes(32, "big")
+    monkeypatch.setenv("G16_EVAL_Z", "1")
+    monkeypatch.setenv("G16_EVAL_BUILD_MSM", "1")
+    ctx = G.Groth16Context(pk_bytes, r1cs_bytes, device=0)
+    try:
+        proofs, _ = ctx.prove_chacha_batch([kat["key"]], [kat["nonce"]], [kat["counter"]], [kat["input"]], [rs])
+        assert proofs[0] == kat["proof"]
+        assert ctx.counters()["eval_basis_z"]
+    finally:
+        ctx.close()
+
+
 def test_pairing_check_matches_oracle(G, oracle):
     """SURVEY §8f rank 4 (the arithmetic under groth16.Verify): products of 1..4 pairings that are 1 by bilinearity are
     accepted, perturbed ones rejected, infinity pairs contribute 1 — the same verdicts as the oracle's pairing."""
