@@ -263,7 +263,7 @@ def test_evaluation_basis_z_query_is_bit_identical(G, gpu_ctx, pk_bytes, r1cs_by
         assert proofs[0] == kat["proof"] and cts[0] == kat["ct"]
         n = 300
         keys, nonces, ctrs, ins, rss = batch_inputs(n, b"g16-b200-evalz")
-        p_def, _ = gpu_ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rss)     # n >= 256: evaluation basis
+        p_def, _ = gpu_ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rss)     # n >= 128: evaluation basis
         p_off, _ = off.prove_chacha_batch(keys, nonces, ctrs, ins, rss)         # coefficient basis (compute_h + pk.G1.Z)
         p_on, _ = on.prove_chacha_batch(keys[:40], nonces[:40], ctrs[:40], ins[:40], rss[:40])
         assert p_def == p_off
