@@ -131,6 +131,8 @@ static void prove_witness_impl(g16_ctx* ctx, const uint64_t* witness, size_t n_w
     stage_rs(c, 1, rs);
     c.staged = 1;
     c.staged_kind = 0;
+    struct WantH { Ctx& c; ~WantH() { c.want_h = false; } } want_h_guard{c};
+    c.want_h = h_out != nullptr;
     ctx_run_batch(c, 1, 0);
     c.d_proofs.download(proof_out, c.proof_bytes(), c.stream);
     if (proof_len) *proof_len = c.proof_bytes();

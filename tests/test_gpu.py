@@ -248,7 +248,7 @@ def test_batch_1024_config4(G, gpu_ctx, oracle, oracle_prover, oracle_vk):
     assert p5[0] == proofs[5]
 
 
-def test_evaluation_basis_z_query_is_bit_identical(G, gpu_ctx, pk_bytes, r1cs_bytes, kat, monkeypatch):
+def test_evaluation_basis_z_query_is_bit_identical(G, gpu_ctx, oracle, pk_bytes, r1cs_bytes, kat, monkeypatch):
     """Large batches take the Z query over the evaluation-basis tables (four transforms, H never materialised).
     Forced on for a single request it must reproduce the KAT proof; forced off for a batch above the switch-over it must
     give the bytes the default path gives."""
@@ -268,6 +268,15 @@ def test_evaluation_basis_z_query_is_bit_identical(G, gpu_ctx, pk_bytes, r1cs_by
         p_on, _ = on.prove_chacha_batch(keys[:40], nonces[:40], ctrs[:40], ins[:40], rss[:40])
         assert p_def == p_off
         assert p_on == p_off[:40]
+        # a caller that reads H back gets the coefficients even from a context forced onto the evaluation basis, and the
+        # Z-query point is the same group element on both paths
+        inputs, _ = oracle.chacha_assignment(kat["key"], kat["nonce"], kat["counter"], kat["input"])
+        wit = oracle.to_mont(1, oracle.ints_to_limbs(inputs[1:]))
+        pr_on, det_on = on.prove_witness(wit, rs, detail=True)
+        pr_ref, det_ref = gpu_ctx.prove_witness(wit, rs, detail=True)
+        assert pr_on == pr_ref == kat["proof"]
+        assert np.array_equal(det_on["h"], det_ref["h"]) and np.array_equal(det_on["msmZ"], det_ref["msmZ"])
+        assert on.prove_witness(wit, rs) == kat["proof"]          # no detail: evaluation basis, same bytes
     finally:
         on.close()
         off.close()
