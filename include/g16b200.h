@@ -88,16 +88,21 @@ int g16_aes_batch_stage(g16_ctx* ctx, size_t n, const uint8_t* keys, size_t key_
  * pipeline = 1 (env G16_PIPELINE=1): sub-batches alternate between two CUDA streams so that the latency-bound phases of
  * one sub-batch overlap the multiply-bound phases of the other; only the total time is measured. On B200 this is not
  * faster (the hot kernels fill every SM's register file), so it is off by default. sub_batch = 0 keeps
- * the current value. Results are identical under every schedule. */
+ * the current value. Results are identical under every schedule.
+ * Z query (circuits without commitment): batches of >= 128 proofs (env G16_EVAL_Z_MIN; G16_EVAL_Z=0/1 forces the choice)
+ * never materialise H: four transforms, then MultiExp over the coset products and the C evaluations against
+ * evaluation-basis tables derived once per context from pk.G1.Z. Same group element as gnark's
+ * MultiExp(pk.G1.Z, h) (prove.go:267-275), same proof bytes; g16_prove_witness_detail with h_out keeps the coefficient path.
+ * The side stream runs at the highest stream priority (env G16_SIDE_PRIO=0 for default priority). */
 int g16_set_schedule(g16_ctx* ctx, int pipeline, int sub_batch);
 
-/* per-stage timings of the last g16_chacha_batch_run, milliseconds: 0 witness+solve, 1 compute_h (7 NTT + pointwise),
+/* per-stage timings of the last g16_chacha_batch_run, milliseconds: 0 witness+solve, 1 compute_h (transforms + pointwise; also hosts side-stream kernels),
  * 2 MSM scalar prep + sort, 3 MSM bucket accumulation, 4 MSM reductions, 5 proof assembly, 6 total, 7 kernel launches */
 int g16_last_stage_ms(const g16_ctx* ctx, float ms[8]);
 /* work counters of the last run: 0 G1 mixed additions done by the bucket-accumulation kernel (= sorted entries),
  * 1 G2 mixed additions, 2 G1 accumulate launches, 3 G2 accumulate launches, 4 kernel launches, 5 proofs,
  * 6 the part of [0] that belongs to the Z query (what the stage timers of the pipeline = 0 schedule bracket),
- * 7 sub-batch size | (1 << 32 if the pipelined schedule ran) */
+ * 7 sub-batch size | (1 << 32 if the pipelined schedule ran) | (1 << 33 if the Z query ran over the evaluation basis) */
 int g16_last_counters(const g16_ctx* ctx, uint64_t out[8]);
 
 /* ------------------------------------------------------------------------------------------------------------------
