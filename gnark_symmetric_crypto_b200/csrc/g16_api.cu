@@ -9,6 +9,14 @@
 
 using namespace g16;
 
+#if !defined(G16_EMU)
+// CUDA 12 loads kernels lazily: the first launch of every kernel variant (tree arities, merge levels, ... chosen by the batch
+// size) stalls for its load, 100-300 ms for the large hot kernels. A serving process meets new batch sizes for a long time
+// (measured: 1 s stalls in the middle of a 1024-caller run). Ask for eager loading unless the host process decided
+// otherwise; this runs when the library is loaded, before its first CUDA call.
+__attribute__((constructor)) static void g16_eager_module_loading() { setenv("CUDA_MODULE_LOADING", "EAGER", 0); }
+#endif
+
 struct g16_ctx {
     std::unique_ptr<Ctx> cx;
     std::mutex mu;

@@ -507,6 +507,23 @@ unsigned char InitAlgorithm(unsigned char algorithmID, GoSlice_g16 provingKey, G
         b->alg = algorithmID;
         b->ctx = ctx;
         if (const char* m = getenv("G16_BATCH_MAX")) { int v = atoi(m); if (v > 0 && v <= 65536) b->max_batch = (size_t)v; }
+#if !defined(G16_EMU)
+        if (algorithmID == 0) {
+            // Warm start. Every (key, nonce, counter, input) is a valid ChaCha request, so one dummy batch of the largest size
+            // the worker can form builds the key tables (both bases of the Z query), sizes every device buffer and touches
+            // every stage before the first caller arrives; without it a serving process keeps meeting first-time stalls
+            // (table build, buffer growth) while the batch sizes it sees still grow. G16_PREWARM=0 skips it, =N sets the size.
+            size_t n = b->max_batch;
+            if (const char* w = getenv("G16_PREWARM")) n = (size_t)(atoi(w) > 0 ? atoi(w) : 0);
+            if (n) {
+                std::vector<uint8_t> keys(n * 32), nonces(n * 12), inputs(n * 64), proofs(n * 164), cts(n * 64);
+                std::vector<uint32_t> counters(n);
+                if (g16_prove_chacha_batch(ctx, n, keys.data(), nonces.data(), counters.data(), inputs.data(), nullptr,
+                                           proofs.data(), cts.data()))
+                    printf("warm-up batch failed: %s\n", g16_last_error());
+            }
+        }
+#endif
         b->worker = std::thread([b] { b->run(); });
         g_batchers[algorithmID] = b;
     }
