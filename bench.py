@@ -39,6 +39,16 @@ METRIC = "ChaCha20-V3 Groth16 proofs/sec"
 UNIT = "proofs/s"
 IMAD_PER_MADD_G1 = 2640      # 10 modmul x 264 IMAD
 WORKLOAD = "batched ChaCha20-V3 Groth16 BN254 proofs, 1024 synthetic key/nonce/counter/input requests per GPU (BASELINE config 4)"
+R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617   # BN254 group order
+
+
+def config_dict(world: int) -> dict:
+    """The `config` both arms print (identical keys and values, so the driver's same_config check holds). What is specific to
+    the GPU arm's schedule is reported under `schedule`, what the CPU arm sampled under `cpu_baseline.sample`."""
+    return {"workload": WORKLOAD, "batch_per_gpu": BATCH,
+            "inputs": "ChaCha20(SHA-256('g16-b200-batch'), nonce 0) keystream cut into key|nonce|counter|input|r|s per request (SURVEY 8d)",
+            "l2": "working set per step (wires 0.76 GB + A/B/C 3.2 GB + MSM scratch) exceeds the 126 MB L2; no flush needed",
+            "parallelism": f"{world} x independent proof shards, no collective"}
 
 
 def shard_range(total: int, rank: int, world: int):
@@ -128,10 +138,49 @@ def chacha_public_inputs_be(cts, nonces, counters, inputs):
     return out
 
 
+def _chacha20_blocks(key: bytes, nblocks: int) -> bytes:
+    """RFC 7539 block function, counter 0..nblocks-1, nonce 0, all blocks at once with numpy (input generator only)."""
+    import numpy as np
+    const = np.frombuffer(b"expand 32-byte k", dtype="<u4")
+    st = np.zeros((16, nblocks), dtype=np.uint32)
+    st[0:4] = const[:, None]
+    st[4:12] = np.frombuffer(key, dtype="<u4")[:, None]
+    st[12] = np.arange(nblocks, dtype=np.uint32)
+    x = st.copy()
+
+    def rotl(v, n):
+        return (v << np.uint32(n)) | (v >> np.uint32(32 - n))
+
+    def qr(a, b, c, d):
+        x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 16)
+        x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 12)
+        x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 8)
+        x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 7)
+
+    for _ in range(10):
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+    x += st
+    return x.T.astype("<u4").tobytes()
+
+
 def make_requests(n: int, seed: bytes):
-    sys.path.insert(0, str(ROOT / "tests"))
-    from conftest import batch_inputs
-    return batch_inputs(n, seed)
+    """BASELINE config 4 input stream: ChaCha20(key = SHA-256(seed), nonce = 0) keystream cut into
+    key(32) | nonce(12) | counter(4, LE) | input(64) | r(32) | s(32) per request, r and s reduced mod the group order.
+    Self-contained (hashlib + numpy): the GPU arm's process imports nothing from oracle/ or tests/ to make its inputs;
+    tests/test_bench_inputs.py checks this generator against the tests' own (oracle-based) one."""
+    import hashlib
+    import struct
+    per = 32 + 12 + 4 + 64 + 64
+    stream = _chacha20_blocks(hashlib.sha256(seed).digest(), (n * per + 63) // 64)
+    keys, nonces, ctrs, ins, rs = [], [], [], [], []
+    for i in range(n):
+        b = stream[i * per:(i + 1) * per]
+        keys.append(b[:32]); nonces.append(b[32:44]); ctrs.append(struct.unpack("<I", b[44:48])[0]); ins.append(b[48:112])
+        r = int.from_bytes(b[112:144], "big") % R_MOD
+        s_ = int.from_bytes(b[144:176], "big") % R_MOD
+        rs.append(r.to_bytes(32, "big") + s_.to_bytes(32, "big"))
+    return keys, nonces, ctrs, ins, rs
 
 
 def cpu_reference_run(n_proofs: int, threads: int):
@@ -155,6 +204,12 @@ def cpu_reference_run(n_proofs: int, threads: int):
     dt = time.perf_counter() - t
     assert len(set(proofs)) == n_proofs
     return n_proofs / dt, dt
+
+
+def oracle_variant() -> str:
+    from oracle import oracle as O
+    O.lib()
+    return O.BUILD_VARIANT
 
 
 def cpu_sample_size(cores: int) -> int:
@@ -181,10 +236,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{sample} proofs per step on the host cores"},
+        "config": config_dict(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} ChaCha20-V3 proofs per step, one proof per thread, oracle C++ prover "
-                                   "(CPU restatement of gnark's Groth16 prover; gnark itself cannot run here: no Go toolchain)"},
+                         "sample": f"{sample} ChaCha20-V3 proofs per step (first requests of the config's input stream), one proof "
+                                   f"per thread, oracle C++ prover built {oracle_variant()} (a CPU RESTATEMENT of gnark's Groth16 "
+                                   "prover, not gnark: no Go toolchain on this box; gnark's assembly field arithmetic is faster)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -339,6 +395,134 @@ def run_gpu(args):
         del pts, sc
     barrier()
 
+    # ---------------- BASELINE config 4 read as written: 1024 requests IN TOTAL, proof i -> rank i mod N (strong scaling).
+    # Every rank proves its share of rank 0's request stream; time = max over ranks; both the device-resident run and the
+    # end-to-end call (host buffers in, proofs out) are reported. At N = 1 this is the headline workload itself.
+    strong = None
+    if not args.no_strong:
+        all_reqs = make_requests(BATCH, b"g16-b200-batch")
+        mine = [x[rank::world] for x in all_reqs]
+        sn, sk, sno, sc_, si, sr = ctx._pack(*mine)
+        sproofs = np.zeros(sn * ctx.proof_bytes, dtype=np.uint8); scts = np.zeros(sn * 64, dtype=np.uint8)
+        ctx.stage(sk, sno, sc_, si, sr)
+        for _ in range(3):
+            ctx.run()
+        barrier()
+        s_ms = sum(ctx.run() for _ in range(args.steps))
+        barrier()
+        s_total_ms, _ = aggregate(s_ms, sn * args.steps, dev)
+        ctx.fetch(sproofs, scts)
+
+        def strong_e2e():
+            rc = L.g16_prove_chacha_batch(ctx._h, sn, sk.ctypes.data_as(u8p), sno.ctypes.data_as(u8p), sc_.ctypes.data_as(u32p),
+                                          si.ctypes.data_as(u8p), sr.ctypes.data_as(u8p), sproofs.ctypes.data_as(u8p), scts.ctypes.data_as(u8p))
+            if rc:
+                raise RuntimeError(L.g16_last_error().decode())
+        strong_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            strong_e2e()
+        barrier()
+        se_total_ms, _ = aggregate((time.perf_counter() - t0) * 1e3, sn * args.steps, dev)
+        if rank == 0:
+            # rank 0's share of the fixed stream must be the very proofs the headline batch produced for those requests
+            assert np.array_equal(sproofs.reshape(sn, -1), ref_proofs.reshape(n, -1)[0::world]), "strong-scaling shard disagrees with the headline batch"
+            strong = {"requests_total": BATCH, "per_gpu": [len(all_reqs[0][g::world]) for g in range(world)], "sharding": "proof i -> rank i mod N",
+                      "value": BATCH * args.steps / (s_total_ms / 1e3), "ms_per_step": s_total_ms / args.steps,
+                      "e2e_value": BATCH * args.steps / (se_total_ms / 1e3), "unit": UNIT, "scaling": "strong",
+                      "timing": "max over ranks; device-resident (CUDA events) and end-to-end (wall clock around the C-ABI call with host buffers)"}
+    barrier()
+
+    # ---------------- BASELINE config 5, multi-GPU half: ONE 2^24-point G1 MSM split by point range, rank g computes the
+    # partial MSM over points [gN/G, (g+1)N/G), the G partial points are gathered and added on the host (no NCCL in the data
+    # path: the gather below carries G x 64 bytes through torch.distributed only because the ranks are separate processes).
+    # Points a_d * G1 for 4096 distinct a_d (generated on the GPU by the scalar-product kernel), tiled; expected result
+    # (sum a_i s_i) * G1 from the same kernel: an O(N) field-only check that does not need the oracle.
+    msm_split = None
+    if not args.no_msm:
+        lg = args.split_log
+        nn, distinct = 1 << lg, 1 << 12
+        rng = np.random.default_rng(24)
+        a = rng.integers(0, 1 << 63, size=(distinct, 4), dtype=np.int64).astype(np.uint64)
+        a[:, 3] &= np.uint64((1 << 60) - 1)
+        idx = rng.integers(0, distinct, nn)
+        sc = rng.integers(0, 1 << 63, size=(nn, 4), dtype=np.int64).astype(np.uint64)
+        sc[:, 3] &= np.uint64((1 << 60) - 1)
+        g1 = np.zeros((1, 8), dtype=np.uint64)
+        g1[0, :4] = G.field_op(0, "to_mont", np.array([[1, 0, 0, 0]], dtype=np.uint64))[0]
+        g1[0, 4:] = G.field_op(0, "to_mont", np.array([[2, 0, 0, 0]], dtype=np.uint64))[0]   # BN254 G1 generator (1, 2)
+        base = G.group_op(1, "mul", np.repeat(g1, distinct, axis=0), a)
+        lo, hi = shard_range(nn, rank, world)
+        plan = G.MsmPlan(1, base[idx[lo:hi]], device=local)
+        plan.set_scalars(sc[lo:hi])
+        plan.run()
+        barrier()
+        part, ms = plan.run()
+        best = float(ms[0])
+        for _ in range(2):
+            part, ms = plan.run()
+            best = min(best, float(ms[0]))
+        plan.close()
+        barrier()
+        split_ms, _ = aggregate(best, hi - lo, dev)
+        parts = [part]
+        if dist is not None:
+            t = torch.from_numpy(part.view(np.int64).copy()).to(dev)
+            gathered = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(gathered, t)
+            parts = [g.cpu().numpy().view(np.uint64) for g in gathered]
+        if rank == 0:
+            acc = parts[0]
+            for q in parts[1:]:
+                acc = G.group_op(1, "add", acc.reshape(1, 8), q.reshape(1, 8))[0]
+            limbs = sc.view(np.uint32).reshape(nn, 8).astype(np.uint64)
+            col = np.zeros((distinct, 8), dtype=np.uint64)
+            np.add.at(col, idx, limbs)
+            tot = 0
+            for d in range(distinct):
+                a_d = sum(int(a[d, k]) << (64 * k) for k in range(4))
+                tot += a_d * sum(int(col[d, k]) << (32 * k) for k in range(8))
+            tot %= R_MOD
+            want = G.group_op(1, "mul", g1, np.array([[(tot >> (64 * k)) & ((1 << 64) - 1) for k in range(4)]], dtype=np.uint64))[0]
+            adds = min(((254 + cc - 1) // cc) * (nn + (1 << cc)) for cc in range(4, 25))
+            msm_split = {"log2n": lg, "gpus": world, "split": "point range, partial points added on the host",
+                         "ms_max_over_gpus": split_ms, "Gpts_per_s": nn / split_ms / 1e6, "correct": bool(np.array_equal(acc, want)),
+                         "frac_of_imad_peak": adds * IMAD_PER_MADD_G1 / (split_ms / 1e3) / (imad["imad_per_s"] * world)}
+            assert msm_split["correct"], "split MSM disagrees with the field-only expectation"
+        del sc, idx, base
+    barrier()
+
+    # ---------------- multi-GPU INSIDE the library: one process, one g16_init_multi handle over all N GPUs of
+    # the node, one g16_prove_chacha_batch call with host buffers for N x 1024 requests (request i -> device i mod N).
+    # Rank 0 only, while the other ranks wait at the barrier; measured only when N > 1 (at N = 1 it is the e2e line above).
+    lib_multi = None
+    if world > 1 and not args.no_lib_multi:
+        if rank == 0:
+            mctx = G.Groth16Context(pk, r1, devices=list(range(world)))
+            reqs_m = make_requests(BATCH * world, b"g16-b200-batch")
+            mn, mk, mno, mc, mi, mr = mctx._pack(*reqs_m)
+            mproofs = np.zeros(mn * mctx.proof_bytes, dtype=np.uint8); mcts = np.zeros(mn * 64, dtype=np.uint8)
+
+            def multi_step():
+                rc = L.g16_prove_chacha_batch(mctx._h, mn, mk.ctypes.data_as(u8p), mno.ctypes.data_as(u8p), mc.ctypes.data_as(u32p),
+                                              mi.ctypes.data_as(u8p), mr.ctypes.data_as(u8p), mproofs.ctypes.data_as(u8p), mcts.ctypes.data_as(u8p))
+                if rc:
+                    raise RuntimeError(L.g16_last_error().decode())
+            for _ in range(3):
+                multi_step()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                multi_step()
+            m_ms = (time.perf_counter() - t0) * 1e3
+            # request i of the N x 1024 stream with i < 1024 is request i of the headline batch: same proof bytes
+            assert np.array_equal(mproofs.reshape(mn, -1)[:n], ref_proofs.reshape(n, -1)), "multi-device handle disagrees with the single-device batch"
+            lib_multi = {"devices": world, "requests_per_call": mn, "value": mn * args.steps / (m_ms / 1e3), "unit": UNIT,
+                         "ms_per_call": m_ms / args.steps,
+                         "path": "one process: g16_init_multi + g16_prove_chacha_batch (host buffers in, proofs out; request i -> device i mod N, one host thread per device)"}
+            mctx.close()
+        barrier()
+
     # ---------------- single-request latency (BASELINE config 1: what one libprove Prove call costs), rank 0 only
     single = None
     if rank == 0:
@@ -359,7 +543,8 @@ def run_gpu(args):
         sample = cpu_sample_size(cores)
         v, dt = cpu_reference_run(sample, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{sample} ChaCha20-V3 proofs, one proof per thread, oracle C++ prover ({dt:.1f} s)"}
+               "sample": f"{sample} ChaCha20-V3 proofs, one proof per thread, oracle C++ prover built {oracle_variant()} ({dt:.1f} s); "
+                         "a CPU RESTATEMENT of gnark's prover, not gnark (no Go toolchain here)"}
 
     if rank == 0:
         value = total_units / (total_ms / 1e3)
@@ -401,11 +586,10 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "sub_batch": sched["sub_batch"],
-                       "schedule": "sub-batches pipelined over two CUDA streams" if sched["pipelined"] else "single stream",
-                       "z_query": "evaluation basis (4 transforms + MSM over d and C evaluations)" if sched["eval_basis_z"] else "coefficient basis (6 transforms + MSM over H)",
-                       "l2": "working set per step (wires 0.76 GB + A/B/C 3.2 GB + MSM scratch) exceeds the 126 MB L2; no flush needed",
-                       "parallelism": f"{world} x independent proof shards, no collective"},
+            "config": config_dict(world),
+            "schedule": {"sub_batch": sched["sub_batch"],
+                         "streams": "sub-batches pipelined over two CUDA streams" if sched["pipelined"] else "single main stream + high-priority side stream",
+                         "z_query": "evaluation basis (4 transforms + MSM over d and C evaluations)" if sched["eval_basis_z"] else "coefficient basis (6 transforms + MSM over H)"},
             "e2e": {"value": total_units / (e2e_total_ms / 1e3), "unit": UNIT,
                     "h2d_bytes_per_step": int(k.nbytes + no.nbytes + c.nbytes + i.nbytes + r.nbytes),
                     "d2h_bytes_per_step": int(proofs.nbytes + cts.nbytes)},
@@ -423,10 +607,18 @@ def run_gpu(args):
                                  "taken in the steps that follow it); "
                                  "peak = mad.lo.u32 rate measured in this run (not in MEASURED_PEAKS.json); HBM is not the bound "
                                  "(SURVEY finding 8)",
-                         "imad_wide_peak": imad["imad_wide_per_s"] / 1e12, "modmul_per_s": imad["modmul_per_s"]},
+                         "imad_wide_peak": imad["imad_wide_per_s"] / 1e12, "modmul_per_s": imad["modmul_per_s"],
+                         # the instruction the Montgomery product is actually made of (carry-chained wide MAD, half rate) and the
+                         # two readings of `achieved` that follow from it: one wide MAD = 2 algorithmic IMADs (lo + hi)
+                         "imad_wide_carry_per_s": imad.get("imad_wide_carry_per_s"),
+                         "frac_of_carry_chain_ceiling": (achieved * 1e12 / (2 * imad["imad_wide_carry_per_s"])) if (achieved and imad.get("imad_wide_carry_per_s")) else None,
+                         "frac_of_plain_wide_mad_ceiling": (achieved * 1e12 / (2 * imad["imad_wide_per_s"])) if achieved else None},
             "roofline_ntt": ntt_roof,
             "stages_ms_per_step": {kk: v / args.steps for kk, v in stages.items() if kk != "launches"},
             "msm_standalone": msm_line,
+            "strong_1024": strong,
+            "msm_split": msm_split,
+            "library_multi_gpu": lib_multi,
             "verified": verified,
             "single_request": single,
             "cpu_baseline": cpu,
@@ -444,7 +636,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-msm", action="store_true", help="skip the standalone 2^22-point MSM line")
+    ap.add_argument("--no-msm", action="store_true", help="skip the standalone 2^22-point MSM line and the 2^24 point-range split")
+    ap.add_argument("--no-strong", action="store_true", help="skip the fixed-total (1024 requests over all GPUs) reading of config 4")
+    ap.add_argument("--no-lib-multi", action="store_true", help="skip the one-process multi-GPU library measurement (N > 1 only)")
+    ap.add_argument("--split-log", type=int, default=24, help="log2 of the point-range-split MSM size")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -33,6 +33,10 @@ EXPORTS = {
     "g16_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "g16_init": (C.c_int, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
     "g16_free": (None, [C.c_void_p]),
+    "g16_init_multi": (C.c_int, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.c_size_t, C.POINTER(C.c_void_p)]),
+    "g16_ctx_devices": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_size_t, C.POINTER(C.c_size_t)]),
+    "g16_ctx_device_handle": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "g16_last_batch_status": (C.c_int, [C.c_void_p, u32p, C.c_size_t]),
     "g16_info": (C.c_int, [C.c_void_p, u64p]),
     "g16_prove_witness": (C.c_int, [C.c_void_p, u64p, C.c_size_t, u8p, u8p, C.POINTER(C.c_size_t)]),
     "g16_prove_chacha_batch": (C.c_int, [C.c_void_p, C.c_size_t, u8p, u8p, u32p, u8p, u8p, u8p, u8p]),
@@ -73,6 +77,8 @@ EXPORTS = {
     "InitAlgorithm": (C.c_ubyte, [C.c_ubyte, GoSlice, GoSlice]),
     "Free": (None, [C.c_void_p]),
     "Prove": (ProveReturn, [GoSlice]),
+    "ProveBatch": (ProveReturn, [GoSlice]),
+    "g16_libprove_stats": (C.c_int, [C.c_int, u64p]),
     "InitVerifier": (C.c_ubyte, [C.c_ubyte, GoSlice]),
     "Verify": (C.c_ubyte, [GoSlice]),
 }

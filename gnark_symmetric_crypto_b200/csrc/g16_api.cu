@@ -6,6 +6,7 @@
 #include "pairing_api.hpp"
 #include <mutex>
 #include <random>
+#include <thread>
 
 using namespace g16;
 
@@ -17,9 +18,17 @@ using namespace g16;
 __attribute__((constructor)) static void g16_eager_module_loading() { setenv("CUDA_MODULE_LOADING", "EAGER", 0); }
 #endif
 
+// One handle = the context of one GPU (cx) plus, for a multi-device handle (g16_init_multi), the handles of the other
+// devices of the list. Independent proofs are the sharding unit: request i of a batch goes to device i mod G,
+// every device runs its own pipeline from its own host thread, results are gathered in input order; no collective.
 struct g16_ctx {
     std::unique_ptr<Ctx> cx;
     std::mutex mu;
+    std::vector<std::unique_ptr<g16_ctx>> extra;   // devices[1..] of a multi-device handle
+    std::vector<size_t> shard_n;                   // requests staged on each device by the last multi-device stage
+    size_t staged_total = 0;
+    size_t ndev() const { return 1 + extra.size(); }
+    g16_ctx* dev(size_t k) { return k == 0 ? this : extra[k - 1].get(); }
 };
 
 struct g16_vctx {
@@ -125,6 +134,9 @@ static void stage_rs(Ctx& c, size_t n, const uint8_t* rs) {
         stage_masks(c, n, masks.data());
     }
     G16_CUDA(cudaStreamSynchronize(c.stream));   // host temporaries must outlive the copies
+    // r, s and the commitment masks are the proof's zero-knowledge randomness: do not leave copies on the host heap
+    auto wipe = [](std::vector<uint8_t>& v) { if (!v.empty()) { volatile uint8_t* p = v.data(); for (size_t i = 0; i < v.size(); i++) p[i] = 0; } };
+    wipe(tmp); wipe(rs64); wipe(masks);
 }
 
 static void prove_witness_impl(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, const uint8_t* rs,
@@ -190,9 +202,63 @@ int g16_init(const uint8_t* pk, size_t pk_len, const uint8_t* r1cs, size_t r1cs_
         *out = h.release();
     });
 }
+// Same key on every device of the list (a device may appear more than once: two contexts on one GPU, which is how the
+// sharding is tested on a one-GPU box). The contexts are created concurrently, one host thread per device.
+int g16_init_multi(const uint8_t* pk, size_t pk_len, const uint8_t* r1cs, size_t r1cs_len, const int* devices, size_t n_devices,
+                   g16_ctx** out) {
+    return guarded([&] {
+        REQUIRE(pk && r1cs && out && devices, "NULL argument");
+        REQUIRE(n_devices >= 1 && n_devices <= 64, "device list must hold 1..64 entries");
+        require_device();
+        int have = 0;
+        G16_CUDA(cudaGetDeviceCount(&have));
+        for (size_t k = 0; k < n_devices; k++) REQUIRE(devices[k] >= 0 && devices[k] < have, "device index out of range");
+        std::vector<std::unique_ptr<g16_ctx>> hs(n_devices);
+        std::vector<std::exception_ptr> errs(n_devices);
+        std::vector<std::thread> th;
+        for (size_t k = 0; k < n_devices; k++)
+            th.emplace_back([&, k] {
+                try {
+                    hs[k].reset(new g16_ctx());
+                    hs[k]->cx = ctx_create(pk, pk_len, r1cs, r1cs_len, devices[k]);
+                } catch (...) {
+                    errs[k] = std::current_exception();
+                }
+            });
+        for (auto& t : th) t.join();
+        auto release_all = [&] {
+            for (auto& h : hs)
+                if (h && h->cx) { cudaSetDevice(h->cx->device); h.reset(); }
+        };
+        for (size_t k = 0; k < n_devices; k++)
+            if (errs[k]) { release_all(); std::rethrow_exception(errs[k]); }
+        std::unique_ptr<g16_ctx> head = std::move(hs[0]);
+        for (size_t k = 1; k < n_devices; k++) head->extra.push_back(std::move(hs[k]));
+        *out = head.release();
+    });
+}
+int g16_ctx_devices(const g16_ctx* ctx, int* devices_out, size_t cap, size_t* n_out) {
+    return guarded([&] {
+        REQUIRE(ctx && n_out, "NULL argument");
+        g16_ctx* c = const_cast<g16_ctx*>(ctx);
+        *n_out = c->ndev();
+        for (size_t k = 0; devices_out && k < c->ndev() && k < cap; k++) devices_out[k] = c->dev(k)->cx->device;
+    });
+}
+int g16_ctx_device_handle(g16_ctx* ctx, size_t k, g16_ctx** out) {
+    return guarded([&] {
+        REQUIRE(ctx && out, "NULL argument");
+        REQUIRE(k < ctx->ndev(), "device slot out of range");
+        *out = ctx->dev(k);
+    });
+}
 void g16_free(g16_ctx* ctx) {
     if (!ctx) return;
     try {
+        for (auto& e : ctx->extra) {
+            cudaSetDevice(e->cx->device);
+            e.reset();
+        }
         cudaSetDevice(ctx->cx->device);
         delete ctx;
     } catch (...) {
@@ -201,6 +267,7 @@ void g16_free(g16_ctx* ctx) {
 int g16_info(const g16_ctx* ctx, uint64_t info[16]) {
     return guarded([&] {
         REQUIRE(ctx && info, "NULL argument");
+        std::lock_guard<std::mutex> lk(const_cast<g16_ctx*>(ctx)->mu);
         const Ctx& c = *ctx->cx;
         uint64_t v[16] = {c.n_dom, c.nA, c.nB, c.nZ, c.nK, c.nB2, c.nb_wires, c.n_public, c.n_secret, c.n_constraints,
                           c.n_instr, c.nlevels, c.n_commit, c.proof_bytes(), (uint64_t)c.device,
@@ -209,8 +276,11 @@ int g16_info(const g16_ctx* ctx, uint64_t info[16]) {
     });
 }
 
-int g16_chacha_batch_stage(g16_ctx* ctx, size_t n, const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters,
-                           const uint8_t* inputs, const uint8_t* rs) {
+}  // extern "C"
+
+// ---- single-device phases (the multi-device entry points below run them per device)
+static int chacha_stage_one(g16_ctx* ctx, size_t n, const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters,
+                            const uint8_t* inputs, const uint8_t* rs) {
     return guarded([&] {
         REQUIRE(ctx && keys && nonces && counters && inputs, "NULL argument");
         REQUIRE(n > 0 && n <= (1u << 20), "batch size out of range");
@@ -227,7 +297,7 @@ int g16_chacha_batch_stage(g16_ctx* ctx, size_t n, const uint8_t* keys, const ui
         c.staged_kind = 1;
     });
 }
-int g16_chacha_batch_run(g16_ctx* ctx, float* ms) {
+static int batch_run_one(g16_ctx* ctx, float* ms) {
     return guarded([&] {
         REQUIRE(ctx, "NULL argument");
         std::lock_guard<std::mutex> lk(ctx->mu);
@@ -238,28 +308,24 @@ int g16_chacha_batch_run(g16_ctx* ctx, float* ms) {
         if (ms) *ms = t;
     });
 }
-int g16_chacha_batch_fetch(g16_ctx* ctx, uint8_t* proofs_out, uint8_t* ct_out) {
+static int batch_fetch_one(g16_ctx* ctx, uint8_t* proofs_out, uint8_t* ct_out) {
     return guarded([&] {
         REQUIRE(ctx && proofs_out, "NULL argument");
         std::lock_guard<std::mutex> lk(ctx->mu);
         Ctx& c = *ctx->cx;
         REQUIRE(c.staged > 0, "no staged batch");
         G16_CUDA(cudaSetDevice(c.device));
-        c.d_proofs.download(proofs_out, c.staged * c.proof_bytes(), c.stream);
+        const size_t pb = c.proof_bytes();
+        c.d_proofs.download(proofs_out, c.staged * pb, c.stream);
         if (ct_out) c.d_ct.download(ct_out, c.staged * 64, c.stream);
         G16_CUDA(cudaStreamSynchronize(c.stream));
+        // a request whose witness did not satisfy the system has no proof: its slot is zeroed (g16_last_batch_status)
+        for (size_t i = 0; i < c.staged && i < c.h_status.size(); i++)
+            if (c.h_status[i]) memset(proofs_out + i * pb, 0, pb);
     });
 }
-int g16_prove_chacha_batch(g16_ctx* ctx, size_t n, const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters,
-                           const uint8_t* inputs, const uint8_t* rs, uint8_t* proofs_out, uint8_t* ct_out) {
-    int rc = g16_chacha_batch_stage(ctx, n, keys, nonces, counters, inputs, rs);
-    if (rc) return rc;
-    rc = g16_chacha_batch_run(ctx, nullptr);
-    if (rc) return rc;
-    return g16_chacha_batch_fetch(ctx, proofs_out, ct_out);
-}
-int g16_aes_batch_stage(g16_ctx* ctx, size_t n, const uint8_t* keys, size_t key_len, const uint8_t* nonces,
-                        const uint32_t* counters, const uint8_t* inputs, const uint8_t* rsm) {
+static int aes_stage_one(g16_ctx* ctx, size_t n, const uint8_t* keys, size_t key_len, const uint8_t* nonces,
+                         const uint32_t* counters, const uint8_t* inputs, const uint8_t* rsm) {
     return guarded([&] {
         REQUIRE(ctx && keys && nonces && counters && inputs, "NULL argument");
         REQUIRE(n > 0 && n <= (1u << 20), "batch size out of range");
@@ -278,27 +344,167 @@ int g16_aes_batch_stage(g16_ctx* ctx, size_t n, const uint8_t* keys, size_t key_
         c.staged_key_len = (uint32_t)key_len;
     });
 }
+
+// ---- multi-device plumbing: request i of the batch -> device i mod G (slot i / G on that device)
+static size_t shard_count(size_t n, size_t G, size_t k) { return n / G + (k < n % G ? 1 : 0); }
+template <class T>
+static std::vector<T> shard_gather(const T* src, size_t n, size_t per, size_t G, size_t k) {
+    std::vector<T> out(shard_count(n, G, k) * per);
+    size_t j = 0;
+    for (size_t i = k; i < n; i += G, j++) memcpy(&out[j * per], src + i * per, per * sizeof(T));
+    return out;
+}
+// kind 1 = chacha (key_len 32), 2 = aes
+static int multi_stage(g16_ctx* ctx, int kind, size_t n, const uint8_t* keys, size_t key_len, const uint8_t* nonces,
+                       const uint32_t* counters, const uint8_t* inputs, const uint8_t* rs) {
+    if (!ctx) { t_last_error = "NULL argument"; return G16_ERR_ARG; }
+    const size_t G = ctx->ndev();
+    if (G == 1 || n < 2) {
+        ctx->shard_n.clear();
+        ctx->staged_total = n;
+        return kind == 1 ? chacha_stage_one(ctx, n, keys, nonces, counters, inputs, rs)
+                         : aes_stage_one(ctx, n, keys, key_len, nonces, counters, inputs, rs);
+    }
+    if (!keys || !nonces || !counters || !inputs) { t_last_error = "NULL argument"; return G16_ERR_ARG; }
+    const size_t rs_per = rs_bytes_per_proof(*ctx->cx);
+    std::vector<size_t> shards(G, 0);
+    for (size_t k = 0; k < G; k++) {
+        const size_t m = shard_count(n, G, k);
+        shards[k] = m;
+        if (!m) continue;
+        auto k_ = shard_gather(keys, n, key_len, G, k);
+        auto n_ = shard_gather(nonces, n, 12, G, k);
+        auto c_ = shard_gather(counters, n, 1, G, k);
+        auto i_ = shard_gather(inputs, n, 64, G, k);
+        std::vector<uint8_t> r_;
+        if (rs) r_ = shard_gather(rs, n, rs_per, G, k);
+        int rc = kind == 1 ? chacha_stage_one(ctx->dev(k), m, k_.data(), n_.data(), c_.data(), i_.data(), rs ? r_.data() : nullptr)
+                           : aes_stage_one(ctx->dev(k), m, k_.data(), key_len, n_.data(), c_.data(), i_.data(), rs ? r_.data() : nullptr);
+        if (rc) return rc;
+    }
+    ctx->shard_n = shards;
+    ctx->staged_total = n;
+    return G16_OK;
+}
+static int multi_run(g16_ctx* ctx, float* ms) {
+    if (!ctx) { t_last_error = "NULL argument"; return G16_ERR_ARG; }
+    if (ctx->shard_n.empty()) return batch_run_one(ctx, ms);
+    const size_t G = ctx->ndev();
+    std::vector<int> rcs(G, 0);
+    std::vector<float> t(G, 0.f);
+    std::vector<std::string> msg(G);
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < G; k++) {
+        if (!ctx->shard_n[k]) continue;
+        th.emplace_back([&, k] {
+            rcs[k] = batch_run_one(ctx->dev(k), &t[k]);
+            if (rcs[k]) msg[k] = t_last_error;   // thread-local in the worker: carried back by hand
+        });
+    }
+    for (auto& x : th) x.join();
+    float mx = 0.f;
+    int rc = 0;
+    for (size_t k = 0; k < G; k++) {
+        if (t[k] > mx) mx = t[k];
+        // an unsatisfied witness on one device does not stop the others; any other failure wins
+        if (rcs[k] && (rc == 0 || rc == G16_ERR_UNSAT)) { rc = rcs[k]; t_last_error = msg[k]; }
+    }
+    if (ms) *ms = mx;   // the devices run concurrently: the batch takes as long as the slowest
+    return rc;
+}
+static int multi_fetch(g16_ctx* ctx, uint8_t* proofs_out, uint8_t* ct_out) {
+    if (!ctx) { t_last_error = "NULL argument"; return G16_ERR_ARG; }
+    if (ctx->shard_n.empty()) return batch_fetch_one(ctx, proofs_out, ct_out);
+    if (!proofs_out) { t_last_error = "NULL argument"; return G16_ERR_ARG; }
+    const size_t G = ctx->ndev(), pb = ctx->cx->proof_bytes();
+    for (size_t k = 0; k < G; k++) {
+        const size_t m = ctx->shard_n[k];
+        if (!m) continue;
+        std::vector<uint8_t> p(m * pb), c(m * 64);
+        int rc = batch_fetch_one(ctx->dev(k), p.data(), c.data());
+        if (rc) return rc;
+        for (size_t j = 0; j < m; j++) {
+            memcpy(proofs_out + (k + j * G) * pb, &p[j * pb], pb);
+            if (ct_out) memcpy(ct_out + (k + j * G) * 64, &c[j * 64], 64);
+        }
+    }
+    return G16_OK;
+}
+
+extern "C" {
+
+int g16_chacha_batch_stage(g16_ctx* ctx, size_t n, const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters,
+                           const uint8_t* inputs, const uint8_t* rs) {
+    return multi_stage(ctx, 1, n, keys, 32, nonces, counters, inputs, rs);
+}
+int g16_aes_batch_stage(g16_ctx* ctx, size_t n, const uint8_t* keys, size_t key_len, const uint8_t* nonces,
+                        const uint32_t* counters, const uint8_t* inputs, const uint8_t* rsm) {
+    return multi_stage(ctx, 2, n, keys, key_len, nonces, counters, inputs, rsm);
+}
+int g16_chacha_batch_run(g16_ctx* ctx, float* ms) { return multi_run(ctx, ms); }
+int g16_chacha_batch_fetch(g16_ctx* ctx, uint8_t* proofs_out, uint8_t* ct_out) { return multi_fetch(ctx, proofs_out, ct_out); }
+// A batch with unsatisfiable requests still proves the others: the call returns G16_ERR_UNSAT after writing every proof
+// that exists (the slots of the failed requests are zero); g16_last_batch_status tells which ones failed.
+int g16_prove_chacha_batch(g16_ctx* ctx, size_t n, const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters,
+                           const uint8_t* inputs, const uint8_t* rs, uint8_t* proofs_out, uint8_t* ct_out) {
+    int rc = g16_chacha_batch_stage(ctx, n, keys, nonces, counters, inputs, rs);
+    if (rc) return rc;
+    rc = g16_chacha_batch_run(ctx, nullptr);
+    if (rc && rc != G16_ERR_UNSAT) return rc;
+    std::string keep = t_last_error;
+    int rc2 = g16_chacha_batch_fetch(ctx, proofs_out, ct_out);
+    if (rc2) return rc2;
+    t_last_error = keep;
+    return rc;
+}
 int g16_prove_aes_batch(g16_ctx* ctx, size_t n, const uint8_t* keys, size_t key_len, const uint8_t* nonces,
                         const uint32_t* counters, const uint8_t* inputs, const uint8_t* rsm, uint8_t* proofs_out, uint8_t* ct_out) {
     int rc = g16_aes_batch_stage(ctx, n, keys, key_len, nonces, counters, inputs, rsm);
     if (rc) return rc;
     rc = g16_chacha_batch_run(ctx, nullptr);
-    if (rc) return rc;
-    return g16_chacha_batch_fetch(ctx, proofs_out, ct_out);
+    if (rc && rc != G16_ERR_UNSAT) return rc;
+    std::string keep = t_last_error;
+    int rc2 = g16_chacha_batch_fetch(ctx, proofs_out, ct_out);
+    if (rc2) return rc2;
+    t_last_error = keep;
+    return rc;
+}
+// status_out[i] for request i of the last batch run on this context: 0 = proved; bit 0 an unsatisfied constraint, bit 1 a
+// division by zero while solving (both: G16_ERR_UNSAT for that request), bit 2 an unsupported instruction.
+int g16_last_batch_status(g16_ctx* ctx, uint32_t* status_out, size_t n) {
+    return guarded([&] {
+        REQUIRE(ctx && status_out, "NULL argument");
+        if (ctx->shard_n.empty()) {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            REQUIRE(n <= ctx->cx->h_status.size(), "n exceeds the size of the last batch");
+            memcpy(status_out, ctx->cx->h_status.data(), n * sizeof(uint32_t));
+            return;
+        }
+        const size_t G = ctx->ndev();
+        REQUIRE(n <= ctx->staged_total, "n exceeds the size of the last batch");
+        for (size_t i = 0; i < n; i++) {
+            g16_ctx* d = ctx->dev(i % G);
+            std::lock_guard<std::mutex> lk(d->mu);
+            status_out[i] = i / G < d->cx->h_status.size() ? d->cx->h_status[i / G] : 0u;
+        }
+    });
 }
 int g16_set_schedule(g16_ctx* ctx, int pipeline, int sub_batch) {
     return guarded([&] {
         REQUIRE(ctx, "NULL argument");
         REQUIRE(sub_batch >= 0 && sub_batch <= (1 << 16), "sub-batch out of range");
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        Ctx& c = *ctx->cx;
-        c.pipeline = pipeline ? 1 : 0;
-        if (sub_batch > 0) c.sub_batch = (uint32_t)sub_batch;
+        for (size_t k = 0; k < ctx->ndev(); k++) {
+            std::lock_guard<std::mutex> lk(ctx->dev(k)->mu);
+            Ctx& c = *ctx->dev(k)->cx;
+            c.pipeline = pipeline ? 1 : 0;
+            if (sub_batch > 0) c.sub_batch = (uint32_t)sub_batch;
+        }
     });
 }
 int g16_last_stage_ms(const g16_ctx* ctx, float ms[8]) {
     return guarded([&] {
         REQUIRE(ctx && ms, "NULL argument");
+        std::lock_guard<std::mutex> lk(const_cast<g16_ctx*>(ctx)->mu);
         memcpy(ms, ctx->cx->stage_ms, sizeof(float) * 8);
     });
 }
@@ -306,7 +512,17 @@ int g16_last_stage_ms(const g16_ctx* ctx, float ms[8]) {
 int g16_last_counters(const g16_ctx* ctx, uint64_t out[8]) {
     return guarded([&] {
         REQUIRE(ctx && out, "NULL argument");
-        memcpy(out, ctx->cx->counters, sizeof(uint64_t) * 8);
+        g16_ctx* h = const_cast<g16_ctx*>(ctx);
+        {
+            std::lock_guard<std::mutex> lk(h->mu);
+            memcpy(out, ctx->cx->counters, sizeof(uint64_t) * 8);
+        }
+        if (!h->shard_n.empty())   // multi-device batch: work counters summed over the devices that took part
+            for (size_t k = 1; k < h->ndev(); k++) {
+                if (!h->shard_n[k]) continue;
+                std::lock_guard<std::mutex> lk(h->dev(k)->mu);
+                for (int j = 0; j < 7; j++) out[j] += h->dev(k)->cx->counters[j];
+            }
     });
 }
 
@@ -334,14 +550,14 @@ int g16_solve_ex(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, size_t
         ctx_ensure_batch(c, batch);
         c.d_witness.upload((const Fr*)witness, n_witness * batch, st);
         if (c.has_randomize) stage_masks(c, batch, masks_be);
-        G16_CUDA(cudaMemsetAsync(c.d_status.p, 0, 4, st));
+        G16_CUDA(cudaMemsetAsync(c.d_status.p, 0, batch * sizeof(uint32_t), st));
         G16_CUDA(cudaMemsetAsync(c.Aev.p, 0, batch * c.n_dom * sizeof(Fr), st));
         G16_CUDA(cudaMemsetAsync(c.Bev.p, 0, batch * c.n_dom * sizeof(Fr), st));
         G16_CUDA(cudaMemsetAsync(c.Cev.p, 0, batch * c.n_dom * sizeof(Fr), st));
         launch_witness_copy(c.d_witness.p, (uint32_t)n_witness, (uint32_t)batch, c.W.p, batch, st);
         ctx_solve(c, batch, 0, (uint32_t)batch, st, c.ws1b);
-        uint32_t status = 0;
-        c.d_status.download(&status, 1, st);
+        c.h_status.assign(batch, 0);
+        c.d_status.download(c.h_status.data(), batch, st);
         DevBuf<Fr> rows;
         if (W) {
             rows.alloc(batch * c.nb_wires);
@@ -354,6 +570,8 @@ int g16_solve_ex(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, size_t
             if (C) G16_CUDA(cudaMemcpyAsync(C + i * 4 * c.n_constraints, c.Cev.p + i * c.n_dom, (size_t)c.n_constraints * 32, cudaMemcpyDeviceToHost, st));
         }
         G16_CUDA(cudaStreamSynchronize(st));
+        uint32_t status = 0;
+        for (uint32_t v : c.h_status) status |= v;
         if (status & 4u) throw std::runtime_error("solver: unsupported hint");
         if (status & 3u) throw std::domain_error("witness does not satisfy the constraint system");
     });
@@ -592,7 +810,14 @@ int g16_verify_init(const uint8_t* vk, size_t vk_len, int device, g16_vctx** out
         *out = c.release();
     });
 }
-void g16_verify_free(g16_vctx* ctx) { delete ctx; }
+void g16_verify_free(g16_vctx* ctx) {
+    if (!ctx) return;
+    try {
+        cudaSetDevice(ctx->v->device);
+        delete ctx;
+    } catch (...) {
+    }
+}
 int g16_verify_info(const g16_vctx* ctx, uint64_t info[4]) {
     return guarded([&] {
         REQUIRE(ctx && info, "NULL argument");

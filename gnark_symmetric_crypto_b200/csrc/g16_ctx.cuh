@@ -67,7 +67,8 @@ struct Ctx {
     int staged_kind = 0;   // 0 generic witness, 1 chacha requests, 2 aes requests
     uint32_t staged_key_len = 0;
     DevBuf<uint8_t> d_keys, d_nonces, d_inputs, d_rs_be, d_ct, d_proofs;
-    DevBuf<uint32_t> d_counters, d_status;
+    DevBuf<uint32_t> d_counters, d_status;   // d_status: one word per witness of the batch (solver.cuh status bits)
+    std::vector<uint32_t> h_status;          // the same, on the host after the last run (g16_last_batch_status)
     DevBuf<Fr> d_rs, d_witness, W, Aev, Bev, Cev;
     MsmWorkspace<G1> ws1;    // Z query, main stream (lane 0)
     MsmWorkspace<G1> ws1c;   // Z query of lane 1 (pipelined schedule)
@@ -522,6 +523,7 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
         if (cx->tables_ready) { cx->tables_ready = false; ctx_build_tables(*cx); }
     }
     cx->d_status.alloc(1);
+    cx->h_status.assign(1, 0);
     cx->solver_graphs = solver_graph_cache_create();
     return cx;
 }
@@ -538,6 +540,7 @@ static void ctx_ensure_batch(Ctx& cx, size_t n) {
     cx.d_proofs.ensure(n * cx.proof_bytes());
     cx.d_ct.ensure(n * 64);
     cx.d_rs.ensure(2 * n);
+    cx.d_status.ensure(n);
     if (cx.n_commit) { cx.resCommit.ensure(n); cx.resPok.ensure(n); cx.commit_aff.ensure(n); }
 }
 
@@ -559,15 +562,16 @@ static size_t ctx_solve(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaStream_
     Fr* A = cx.Aev.p + sb * cx.n_dom;
     Fr* B = cx.Bev.p + sb * cx.n_dom;
     Fr* C = cx.Cev.p + sb * cx.n_dom;
+    uint32_t* status = cx.d_status.p + sb;
     if (!cx.n_commit)
-        return launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), cx.h_level_split2.data(), 0, cx.nlevels, rows, W, n, A, B, C, cx.d_status.p, st, cx.solver_graphs);
-    size_t launches = launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), cx.h_level_split2.data(), 0, cx.bsb_level + 1, rows, W, n, A, B, C, cx.d_status.p, st, cx.solver_graphs);
+        return launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), cx.h_level_split2.data(), 0, cx.nlevels, rows, W, n, A, B, C, status, st, cx.solver_graphs);
+    size_t launches = launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), cx.h_level_split2.data(), 0, cx.bsb_level + 1, rows, W, n, A, B, C, status, st, cx.solver_graphs);
     for (size_t o = 0; o < rows; o += cx.sub_batch) {
         uint32_t r = (uint32_t)((rows - o) < cx.sub_batch ? (rows - o) : cx.sub_batch);
         run_query_g1(wsc, st, cx.qPed, W + o, 1, n, true, r, cx.resCommit.p + sb + o, nullptr);
     }
     launch_bsb22_challenge(cx.resCommit.p + sb, rows, W, n, cx.commit_wire, cx.commit_aff.p + sb, st);
-    launches += 1 + launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), cx.h_level_split2.data(), cx.bsb_level + 1, cx.nlevels, rows, W, n, A, B, C, cx.d_status.p, st, cx.solver_graphs);
+    launches += 1 + launch_solver(sp, cx.h_level_off.data(), cx.h_level_split.data(), cx.h_level_split2.data(), cx.bsb_level + 1, cx.nlevels, rows, W, n, A, B, C, status, st, cx.solver_graphs);
     return launches;
 }
 
@@ -607,7 +611,7 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     cx.ws2.log_reset();
     const bool piped = cx.pipeline && n > cx.sub_batch;
     tm.mark(piped ? ST_COUNT : ST_SOLVE, st);   // pipelined: one interval that only counts towards the total
-    G16_CUDA(cudaMemsetAsync(cx.d_status.p, 0, 4, st));
+    G16_CUDA(cudaMemsetAsync(cx.d_status.p, 0, n * sizeof(uint32_t), st));
     G16_CUDA(cudaMemsetAsync(cx.Aev.p, 0, n * cx.n_dom * sizeof(Fr), st));
     G16_CUDA(cudaMemsetAsync(cx.Bev.p, 0, n * cx.n_dom * sizeof(Fr), st));
     G16_CUDA(cudaMemsetAsync(cx.Cev.p, 0, n * cx.n_dom * sizeof(Fr), st));
@@ -683,9 +687,11 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
         own += 1;
     }
     tm.mark(-1, st);
-    uint32_t status = 0;
-    cx.d_status.download(&status, 1, st);
+    cx.h_status.assign(n, 0);
+    cx.d_status.download(cx.h_status.data(), n, st);
     G16_CUDA(cudaStreamSynchronize(st));
+    uint32_t status = 0;
+    for (uint32_t v : cx.h_status) status |= v;
     float per[ST_COUNT];
     float total = tm.finish(per);
     for (int i = 0; i < ST_COUNT; i++) cx.stage_ms[i] = per[i];
@@ -703,7 +709,14 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     cx.counters[5] = n;
     cx.counters[7] = (uint64_t)cx.sub_batch | ((uint64_t)(piped ? 1 : 0) << 32) | ((uint64_t)(eval_z ? 1 : 0) << 33);
     if (status & 4u) throw std::runtime_error("solver: unsupported hint");
-    if (status & 3u) throw std::domain_error("witness does not satisfy the constraint system");
+    // Per-witness verdicts stay in h_status: the batch has run to completion, so the proofs of the satisfied witnesses are
+    // valid and can still be fetched (g16_chacha_batch_fetch zeroes the others); the call itself reports G16_ERR_UNSAT.
+    if (status & 3u) {
+        size_t bad = 0, first = n;
+        for (size_t i = 0; i < n; i++) if (cx.h_status[i] & 3u) { if (first == n) first = i; bad++; }
+        throw std::domain_error("witness does not satisfy the constraint system (" + std::to_string(bad) + " of " + std::to_string(n) +
+                                " requests, first at index " + std::to_string(first) + ")");
+    }
     return total;
 }
 

@@ -235,9 +235,12 @@ pairing_check_kernel(const LineRec* __restrict__ recs, size_t stride, uint32_t p
     }
     f12_mul(S, S.f, S.f, S.g);
     if (t == 0) {
-        bool in_fp6 = true;
+        // F == 0 also has vanishing odd coefficients, but it only arises from a degenerate Miller step on unvalidated input
+        // (a zero line: Fe::inv(0) = 0) and is never a product of pairings: rejected.
+        bool in_fp6 = true, nonzero = false;
         for (int i = 1; i < 12; i += 2) in_fp6 = in_fp6 && S.f[i].is_zero();
-        ok[chk] = in_fp6 ? 1 : 0;
+        for (int i = 0; i < 12; i += 2) nonzero = nonzero || !S.f[i].is_zero();
+        ok[chk] = (in_fp6 && nonzero) ? 1 : 0;
     }
 }
 

@@ -30,14 +30,21 @@ FD void fp_exponent(int which, uint32_t e[8]) {
     for (int i = 0; i < 8; i++) e[i] = (t[i] >> sh) | (i < 7 ? (t[i + 1] << (32 - sh)) : 0u);
 }
 
-// one compressed point -> affine Montgomery. Returns 0, or error bits: 1 = not on the curve, 2 = bad flag bits
+// one compressed point -> affine Montgomery. Returns 0, or error bits: 1 = not on the curve, 2 = bad flag bits,
+// 4 = a coordinate encoded as an integer >= p (SetBytesCanonical), 8 = infinity flag with non-zero payload
 // (gnark-crypto ecc/bn254/marshal.go: 0b10 smallest y, 0b11 largest y, 0b01 infinity, 0b00 = uncompressed, not accepted here)
 FD uint32_t decompress_g1_point(const uint8_t* b, G1Affine& out) {
     out = G1Affine::inf();
     uint8_t flag = b[0] & 0xC0;
-    if (flag == 0x40) return 0;
+    if (flag == 0x40) {
+        uint32_t o = b[0] & 0x3F;
+        for (int i = 1; i < 32; i++) o |= b[i];
+        return o ? 8u : 0u;
+    }
     if (flag == 0x00) return 2;
-    Fp x = fp_from_be32(b, true);
+    bool nc = false;
+    Fp x = fp_from_be32(b, true, &nc);
+    if (nc) return 4;
     Fp rhs = x.sqr() * x + fp_three();
     uint32_t e[8];
     fp_exponent(0, e);
@@ -51,9 +58,15 @@ FD uint32_t decompress_g1_point(const uint8_t* b, G1Affine& out) {
 FD uint32_t decompress_g2_point(const uint8_t* b, G2Affine& out) {
     out = G2Affine::inf();
     uint8_t flag = b[0] & 0xC0;
-    if (flag == 0x40) return 0;
+    if (flag == 0x40) {
+        uint32_t o = b[0] & 0x3F;
+        for (int i = 1; i < 64; i++) o |= b[i];
+        return o ? 8u : 0u;
+    }
     if (flag == 0x00) return 2;
-    Fp2 x = {fp_from_be32(b + 32, false), fp_from_be32(b, true)};   // X.A1 || X.A0
+    bool nc = false;
+    Fp2 x = {fp_from_be32(b + 32, false, &nc), fp_from_be32(b, true, &nc)};   // X.A1 || X.A0
+    if (nc) return 4;
     Fp2 a = x.sqr() * x + g2_coeff_b();
     Fp2 y;
     if (a.is_zero()) {

@@ -6,13 +6,21 @@
 
 namespace g16 {
 
-FD Fp fp_from_be32(const uint8_t* b, bool mask_flags) {
+// *noncanonical (optional) is set when the encoded integer is >= p: gnark-crypto's point decoders read coordinates with
+// fp.Element.SetBytesCanonical and reject such encodings (x and x + p would otherwise decode to the same point, i.e. two
+// byte strings for one proof); to_mont alone would reduce them silently.
+FD Fp fp_from_be32(const uint8_t* b, bool mask_flags, bool* noncanonical = nullptr) {
     Fp v;
     for (int i = 0; i < 8; i++) {
         const uint8_t* q = b + 28 - 4 * i;
         v.l[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
     }
     if (mask_flags) v.l[7] &= 0x3FFFFFFFu;
+    if (noncanonical) {
+        uint32_t t[8], m[8];
+        for (int i = 0; i < 8; i++) m[i] = FpParams::mod(i);
+        if (!sub8(t, v.l, m)) *noncanonical = true;   // no borrow <=> v >= p
+    }
     return v.to_mont();
 }
 FD void fp_to_be32(const Fp& m, uint8_t* b) {

@@ -208,7 +208,7 @@ solver_level_kernel(SolverProgram sp, uint32_t lo, uint32_t hi, uint32_t batch, 
     if (inst >= batch || k >= hi) return;
     if (sp.randomize) sp.randomize += inst;   // sp is a by-value kernel parameter: per-thread view of the mask array
     solve_instruction(sp, sp.level_instr[k], W + inst, w_stride, A + (size_t)inst * sp.n_dom,
-                      B + (size_t)inst * sp.n_dom, C + (size_t)inst * sp.n_dom, status);
+                      B + (size_t)inst * sp.n_dom, C + (size_t)inst * sp.n_dom, status + inst);   // one status word per witness
 }
 
 #if !defined(G16_EMU)
@@ -265,6 +265,7 @@ __device__ __forceinline__ void solve_item_warp(SolverProgram sp, uint32_t ins, 
     const uint32_t lane = threadIdx.x;
     if (sp.randomize) sp.randomize += inst;
     W += inst;
+    status += inst;   // one status word per witness
     A += (size_t)inst * sp.n_dom; B += (size_t)inst * sp.n_dom; C += (size_t)inst * sp.n_dom;
     const size_t ws = w_stride;
     const InsMeta m = sp.meta[ins];
@@ -405,6 +406,7 @@ solver_count_kernel(SolverProgram sp, uint32_t lo, uint32_t hi, uint32_t batch, 
     const uint32_t tid = threadIdx.x, inst = blockIdx.y;
     const uint32_t ins = sp.level_instr[lo + blockIdx.x];
     W += inst;
+    status += inst;
     const uint32_t* ix = sp.count_index + sp.meta[ins].lookup_tab;
     const uint32_t nq = ix[0], row_pos0 = ix[1], row_stride_words = ix[2], nrows = ix[3];
     if (nq == 0xFFFFFFFFu) {

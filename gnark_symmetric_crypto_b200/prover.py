@@ -98,9 +98,39 @@ def Prove(params: bytes) -> bytes:
         out = C.string_at(r.r0, r.r1)
     finally:
         L.Free(r.r0)
+    _raise_if_panic(out)
+    return out
+
+
+def _raise_if_panic(out: bytes):
+    """libprove.go:33-43: a recovered panic comes back as json.Marshal(value) — a JSON string for string panics
+    (log.Panicf, fmt.Sprintf), the marshalled error VALUE (an object without "proof") for panic(err)."""
     if out[:1] == b'"':
         raise RuntimeError(json.loads(out))
-    return out
+    if out[:1] != b"{" or b'"proof"' not in out[:16]:
+        raise RuntimeError("prover panicked with error value " + out.decode(errors="replace"))
+
+
+def ProveBatch(params_list) -> list:
+    """The batched twin of Prove: a list of InputParams JSON byte strings (or dicts) -> a list with,
+    per request and in order, the OutputParams JSON bytes or a RuntimeError instance for a request Prove would panic on."""
+    L = _lib.load()
+    items = [json.loads(p) if isinstance(p, (bytes, bytearray, str)) else p for p in params_list]
+    s, keep = _slice(json.dumps(items).encode())
+    r = L.ProveBatch(s)
+    try:
+        out = C.string_at(r.r0, r.r1)
+    finally:
+        L.Free(r.r0)
+    if out[:1] != b"[":
+        _raise_if_panic(out)
+    res = []
+    for item in json.loads(out):
+        if isinstance(item, dict) and "proof" in item:
+            res.append(json.dumps(item).encode())
+        else:
+            res.append(RuntimeError(item if isinstance(item, str) else "prover panicked with error value " + json.dumps(item)))
+    return res
 
 
 @dataclass
@@ -130,12 +160,20 @@ def Verify(params: bytes) -> bool:
 
 
 class Groth16Context:
-    """One (pk, r1cs) pair resident on one GPU: the inner seam under gnark's groth16.Prove."""
+    """One (pk, r1cs) pair resident on one GPU — or, with `devices=[...]`, on every GPU of the list (g16_init_multi):
+    batches are then sharded request i -> devices[i mod G], proved concurrently and gathered in input order.
+    The inner seam under gnark's groth16.Prove."""
 
-    def __init__(self, pk: bytes, r1cs: bytes, device: int = 0):
+    def __init__(self, pk: bytes, r1cs: bytes, device: int = 0, devices=None):
         self._L = _lib.load()
         self._h = C.c_void_p()
-        _check(self._L.g16_init(pk, len(pk), r1cs, len(r1cs), device, C.byref(self._h)))
+        if devices is None:
+            _check(self._L.g16_init(pk, len(pk), r1cs, len(r1cs), device, C.byref(self._h)))
+            self.devices = [device]
+        else:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            _check(self._L.g16_init_multi(pk, len(pk), r1cs, len(r1cs), arr, len(devices), C.byref(self._h)))
+            self.devices = [int(d) for d in devices]
         info = np.zeros(16, dtype=np.uint64)
         _check(self._L.g16_info(self._h, _p64(info)))
         (self.n, self.nA, self.nB, self.nZ, self.nK, self.nB2, self.nb_wires, self.nb_public, self.nb_secret,
@@ -244,6 +282,12 @@ class Groth16Context:
 
     def fetch(self, proofs: np.ndarray, cts: np.ndarray):
         _check(self._L.g16_chacha_batch_fetch(self._h, _p8(proofs), _p8(cts)))
+
+    def batch_status(self, n: int) -> np.ndarray:
+        """Per-request status words of the last batch (0 = proved; bit 0 unsatisfied constraint, bit 1 division by zero)."""
+        st = np.zeros(n, dtype=np.uint32)
+        _check(self._L.g16_last_batch_status(self._h, st.ctypes.data_as(u32p), n))
+        return st
 
     def set_schedule(self, pipeline: bool, sub_batch: int = 0):
         """pipeline=True: sub-batches alternate between two streams (throughput schedule, total time only);

@@ -49,6 +49,18 @@ int g16_device_count(int* n);
  * ------------------------------------------------------------------------------------------------------------------ */
 int g16_init(const uint8_t* pk, size_t pk_len, const uint8_t* r1cs, size_t r1cs_len, int device, g16_ctx** out);
 void g16_free(g16_ctx* ctx);
+/* Multi-GPU handle (SURVEY 8b `g16_init(..., devices[], n, &ctx)`, 8e): the same key resident on every device of the list,
+ * one CUDA context + host thread per device. Independent proofs are the sharding unit: the batch entry points below send
+ * request i to devices[i mod n], run the devices concurrently and gather proofs and ciphertexts in input order. There is no
+ * inter-GPU traffic and no collective. A batch of one request runs on devices[0]. A device index may be listed more than
+ * once (two contexts on one GPU). g16_prove_witness and the stage-level entry points use devices[0]. */
+int g16_init_multi(const uint8_t* pk, size_t pk_len, const uint8_t* r1cs, size_t r1cs_len, const int* devices,
+                   size_t n_devices, g16_ctx** out);
+/* *n_out = number of devices of the handle; devices_out[0..min(cap, n)) = their CUDA indices (may be NULL) */
+int g16_ctx_devices(const g16_ctx* ctx, int* devices_out, size_t cap, size_t* n_out);
+/* borrowed single-device handle of slot k (0 = the handle itself) for callers that schedule the devices themselves, as the
+ * Prove batcher does (one worker per GPU over a shared queue); owned by `ctx`, never pass it to g16_free */
+int g16_ctx_device_handle(g16_ctx* ctx, size_t k, g16_ctx** out);
 
 /* info[0..15]: 0 domain size n, 1 |G1.A|, 2 |G1.B|, 3 |G1.Z|, 4 |G1.K|, 5 |G2.B|, 6 nbWires, 7 nbPublic (incl. ONE),
  * 8 nbSecret, 9 nbConstraints, 10 nbInstructions, 11 nbLevels, 12 nbCommitments, 13 proof bytes, 14 device, 15 reserved */
@@ -66,6 +78,11 @@ int g16_prove_witness(g16_ctx* ctx, const uint64_t* witness, size_t n_witness, c
  * keys n*32, nonces n*12, counters n (host order), inputs n*64, rs n*64 (or NULL) -> proofs n*164, ciphertexts n*64. */
 int g16_prove_chacha_batch(g16_ctx* ctx, size_t n, const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters,
                            const uint8_t* inputs, const uint8_t* rs, uint8_t* proofs_out, uint8_t* ct_out);
+
+/* Requests that the circuit rejects (an unsatisfiable witness, e.g. an AES counter whose 4-block range wraps) do not stop
+ * the batch: every other proof is produced, the rejected slots are zero-filled, the call returns G16_ERR_UNSAT and
+ * status_out[i] (bit 0: unsatisfied constraint, bit 1: division by zero in the solver) tells which requests failed. */
+int g16_last_batch_status(g16_ctx* ctx, uint32_t* status_out, size_t n);
 
 /* The same batch split into its three phases so a benchmark can time the device part with inputs already resident in
  * HBM: stage (H2D) -> run (all kernels, returns after the stream drained; device time in *ms if non-NULL) -> fetch (D2H). */
@@ -201,12 +218,22 @@ int g16_imad_chain_rate(double* wide_carry_mads_per_s);
 typedef struct { void* data; long long len; long long cap; } GoSlice_g16;
 typedef struct { void* r0; long long r1; } Prove_return_g16;
 void enforce_binding(void);                                                        /* libprove.go:17-18 */
+/* Devices: env G16_DEVICES = comma-separated CUDA indices or "all" (default: G16_DEVICE, else 0). With more than one device
+ * the key is loaded on each and concurrent Prove calls are served by one batching worker per GPU over a shared queue. */
 unsigned char InitAlgorithm(unsigned char algorithmID, GoSlice_g16 provingKey, GoSlice_g16 r1cs);   /* libprove.go:20-23 */
 void Free(void* pointer);                                                          /* libprove.go:25-28 */
 Prove_return_g16 Prove(GoSlice_g16 params);                                        /* libprove.go:30-47 */
 /* verifier side, libraries/verifier/libverify.go:14-17: Verify(params JSON {"cipher","proof","publicSignals"}) -> bool.
  * The reference embeds vk.chacha20 / vk.aes128 / vk.aes256 with go:embed (impl/verify_impl.go:26-62); this library takes the
  * same bytes once per cipher through InitVerifier (algorithm ids as InitAlgorithm). */
+/* SURVEY 8f rank 3, beside Prove (which is unchanged): params = a JSON array of InputParams objects (provers.go:53-59), the
+ * result = a JSON array with one element per request, in order: the OutputParams object Prove would return
+ * (prove_impl.go:49-52) or, for a request Prove would have panicked on, the JSON-encoded error string. Requests of any mix
+ * of initialised ciphers; each cipher's share is proved as one batch (on every GPU of G16_DEVICES). A payload that is not
+ * a JSON array comes back as one JSON string (the panic convention of libprove.go:33-43). Release with Free. */
+Prove_return_g16 ProveBatch(GoSlice_g16 params);
+/* counters of the Prove batcher of one cipher: out[0] batches run, out[1] requests proved, out[2] devices serving it */
+int g16_libprove_stats(int algorithmID, uint64_t out[3]);
 unsigned char InitVerifier(unsigned char algorithmID, GoSlice_g16 verifyingKey);
 unsigned char Verify(GoSlice_g16 params);
 

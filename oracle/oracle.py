@@ -31,16 +31,36 @@ u8p = C.POINTER(C.c_uint8)
 
 def build(force: bool = False) -> Path:
     so = _HERE / "_build" / "liboracle.so"
+    v3 = _HERE / "_build" / "liboracle_v3.so"
     srcs = [_HERE / n for n in ("oracle_core.cpp", "oracle_groth16.cpp", "bn254_field.hpp", "bn254_curve.hpp")]
-    if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs if s.exists()):
+    if force or not so.exists() or not v3.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs if s.exists()):
         subprocess.check_call(["make", "-C", str(_HERE), "-s"])
     return so
 
 
+def _cpu_has(*flags) -> bool:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                have = set(line.split(":", 1)[1].split())
+                return all(f in have for f in flags)
+    except OSError:
+        pass
+    return False
+
+
+BUILD_VARIANT = "x86-64-v2"
+
+
 def lib():
-    global _LIB
+    global _LIB, BUILD_VARIANT
     if _LIB is None:
         so = build()
+        v3 = so.with_name("liboracle_v3.so")
+        # the faster build (BMI2 mulx, ADX, AVX2) when this host supports it; ORACLE_PORTABLE=1 forces the portable one
+        if v3.exists() and not os.environ.get("ORACLE_PORTABLE") and _cpu_has("avx2", "bmi2", "adx", "fma", "movbe", "abm"):
+            so = v3
+            BUILD_VARIANT = "x86-64-v3+adx"
         L = C.CDLL(str(so))
         L.orc_pk_parse.restype = C.c_void_p
         L.orc_pk_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_int]

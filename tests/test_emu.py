@@ -189,21 +189,52 @@ def test_malformed_keys_are_rejected(emu, pk_bytes, r1cs_bytes):
     assert emu.g16_init(None, 0, r1cs_bytes, len(r1cs_bytes), 0, C.byref(h)) == 1
 
 
-def test_libprove_json_layer(emu):
-    """Error behaviour of the outer ABI (libprove.go:30-47, prove_impl.go:116-143) without any initialised cipher."""
+def _call_json(fn, free, payload: bytes):
     import json
+    buf = (C.c_uint8 * max(len(payload), 1)).from_buffer_copy(payload or b"\0")
+    r = fn(_lib.GoSlice(C.cast(buf, C.c_void_p), len(payload), len(payload)))
+    out = C.string_at(r.r0, r.r1)
+    free(r.r0)
+    return json.loads(out)
 
-    def prove(payload: bytes):
-        buf = (C.c_uint8 * len(payload)).from_buffer_copy(payload)
-        r = emu.Prove(_lib.GoSlice(C.cast(buf, C.c_void_p), len(payload), len(payload)))
-        out = C.string_at(r.r0, r.r1)
-        emu.Free(r.r0)
-        return json.loads(out)
 
+def test_libprove_json_layer(emu):
+    """Error behaviour of the outer ABI (libprove.go:30-47, prove_impl.go:116-143) without any initialised cipher. A string
+    panic (log.Panicf, fmt.Sprintf) comes back as a JSON string, panic(err) as the marshalled error VALUE: an object."""
+    prove = lambda b: _call_json(emu.Prove, emu.Free, b)
     assert "could not find prover" in prove(b'{"cipher":"aes-256-ctr1","key":[1],"nonce":[1],"counter":1,"input":[1]}')
     assert "not initialized" in prove(b'{"cipher":"chacha20","key":"AAEC","nonce":[],"counter":1,"input":[]}')
-    assert isinstance(prove(b"{not json"), str)
-    assert "counter" in prove(b'{"cipher":"chacha20","counter":[0,1]}')   # core_test.go:122 passes an array: unmarshal error
+    assert prove(b"{not json") == {"Offset": 2}                        # *json.SyntaxError: only Offset is exported
+    assert prove(b"") == {"Offset": 0}
+    err = prove(b'{"cipher":"chacha20","counter":[0,1]}')            # core_test.go:122 passes an array: *json.UnmarshalTypeError
+    assert err["Field"] == "counter" and err["Struct"] == "InputParams" and err["Value"] == "array"
+    # encoding/json hands unsigned fields to strconv.ParseUint: exponents, fractions, signs and hex are type errors
+    for lit in (b"1e3", b"1.0", b"-1", b"4294967296"):
+        assert prove(b'{"cipher":"chacha20","counter":' + lit + b'}')["Field"] == "counter", lit
+    assert "Offset" in prove(b'{"cipher":"chacha20","counter":0x10}')   # not JSON at all
+    assert prove(b'{"cipher":"chacha20","key":[256]}')["Field"] == "key"
+    assert "Offset" in prove(b'{"cipher":"chacha20"} trailing')
+    assert "Offset" in prove(b'{"cipher":"chacha20","counter":12')      # input ends inside a value: no read past the slice
+    assert "Offset" in prove(b'{"cipher":"chacha20","counter":tru')
+    # base64 as base64.StdEncoding decodes it: padding is mandatory and only at the end
+    assert isinstance(prove(b'{"cipher":"chacha20","key":"AAE"}'), int)          # CorruptInputError marshals as its int64 value
+    assert isinstance(prove(b'{"cipher":"chacha20","key":"AA=A"}'), int)
+    assert "not initialized" in prove(b'{"cipher":"chacha20","key":"AAE=","nonce":null}')
+    # field names match case-insensitively, \u escapes decode to UTF-8, unknown fields are skipped
+    assert "not initialized" in prove(b'{"CIPHER":"chacha20","Key":[1],"extra":{"a":[1,2,{"b":null}]},"x":"\\u00e9"}')
+    assert prove('{"cipher":"ch\\u0061cha20\\u00e9"}'.encode()) == "could not find prover forchacha20\u00e9"
+
+
+def test_libprove_prove_batch_json_layer(emu):
+    """ProveBatch: per-request results in order; without initialised ciphers every request reports what
+    Prove would report. A payload that is not an array fails as one value, like one json.Unmarshal."""
+    pb = lambda b: _call_json(emu.ProveBatch, emu.Free, b)
+    assert pb(b"[]") == []
+    out = pb(b'[{"cipher":"chacha20","key":[],"nonce":[],"counter":1,"input":[]},{"cipher":"nope"},{"cipher":"aes-128-ctr"}]')
+    assert len(out) == 3 and "not initialized" in out[0] and "could not find prover" in out[1] and "not initialized" in out[2]
+    assert pb(b'{"cipher":"chacha20"}') == {}
+    assert pb(b'[{"cipher":"chacha20"},') == {"Offset": 23}
+    assert "Field" in pb(b'[{"cipher":"chacha20","counter":"7"}]')
 
 
 def test_aes_witness_and_bsb22_hash(emu, oracle):
@@ -273,6 +304,15 @@ def test_verifier_orchestration(emu, oracle, kat):
     ok(emu, emu.g16_verify_batch(h, 1, p8(pr), pub.ctypes.data_as(C.c_void_p), 1, p8(out), None))
     assert out[0] == 1
     assert emu.g16_verify_batch(h, 0, p8(pr), pub.ctypes.data_as(C.c_void_p), 1, p8(out), None) == 1   # G16_ERR_ARG
+    # gnark-crypto decodes coordinates with SetBytesCanonical: x + p names the same point but is not a valid encoding.
+    # The A0 half of Bs.x (bytes 64..96) carries no flag bits, so x + p < 2^255 always fits.
+    x = int.from_bytes(kat["proof"][64:96], "big")
+    forged = bytearray(kat["proof"])
+    forged[64:96] = (x + oracle.P_MOD).to_bytes(32, "big")
+    both = np.frombuffer(bytes(forged) + kat["proof"], dtype=np.uint8).copy()
+    out2 = np.zeros(2, dtype=np.uint8)
+    ok(emu, emu.g16_verify_batch(h, 2, p8(both), np.concatenate([pub, pub]).ctypes.data_as(C.c_void_p), 1, p8(out2), None))
+    assert out2.tolist() == [0, 1]
     emu.g16_verify_free(h)
     bad = C.c_void_p()
     assert emu.g16_verify_init(vk[:-3], len(vk) - 3, 0, C.byref(bad)) == 2   # G16_ERR_PARSE

@@ -1,0 +1,244 @@
+"""GPU tests added in round 2: BASELINE config 5 at its full sizes (MSM 2^22 / 2^24 against the field-only oracle, the
+8-range point split combined on the host), the multi-device handle (sharding request i -> device i mod G, exercised on one
+GPU by listing it twice), per-request verdicts of a batch, the ProveBatch export, and the canonical-encoding checks of the
+verifier's point decoder. Everything goes through the C-ABI; bit-exact."""
+import json
+import struct
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import batch_inputs, aes_keys
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gnark_symmetric_crypto_b200 as G
+    return G
+
+
+# ---------------------------------------------------------------------------------------------- config 5, full sizes
+def _tiled_msm_inputs(oracle, n, seed, distinct=1 << 12):
+    """P_i = a_i G1, uniform scalars; expected = (sum a_i s_i mod r) G1, an O(N) field-only oracle.
+    The a_i are tiled from `distinct` values so that the points cost 4096 CPU scalar products, and the big sum is grouped
+    per distinct point: sum_d a_d (sum_{i -> d} s_i), the inner sums taken on 32-bit limb columns with numpy."""
+    rng = np.random.default_rng(seed)
+    a = oracle.rand_field(rng, 1, distinct)
+    base = oracle.g1_fixed_base(a)
+    idx = rng.integers(0, distinct, n)
+    sc = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    sc[:, 3] &= np.uint64((1 << 60) - 1)                                  # < r
+    limbs = sc.view(np.uint32).reshape(n, 8).astype(np.uint64)            # little-endian 32-bit limbs
+    col = np.zeros((distinct, 8), dtype=np.uint64)
+    np.add.at(col, idx, limbs)                                            # <= 2^24 terms of 32 bits: fits 64 bits
+    a_int = oracle.limbs_to_ints(a)
+    tot = 0
+    for d in range(distinct):
+        s_d = sum(int(col[d, k]) << (32 * k) for k in range(8))
+        tot += a_int[d] * s_d
+    return base, idx, sc, tot % oracle.R_MOD
+
+
+@pytest.mark.parametrize("lg", [22, 24])
+def test_msm_full_size_against_field_only_oracle(G, oracle, lg):
+    """BASELINE config 5 at 2^22 and 2^24 points, one-shot (no tables) and, at 2^22, fixed-base."""
+    n = 1 << lg
+    base, idx, sc, tot = _tiled_msm_inputs(oracle, n, 50 + lg)
+    want = oracle.g1_mul(oracle.g1_gen(), tot)
+    pts = base[idx]
+    plan = G.MsmPlan(1, pts)
+    plan.set_scalars(sc)
+    got, ms = plan.run()
+    plan.close()
+    assert np.array_equal(got, want)
+    if lg == 22:
+        plan = G.MsmPlan(1, pts, precompute=True)
+        plan.set_scalars(sc)
+        got, ms = plan.run()
+        plan.close()
+        assert np.array_equal(got, want)
+
+
+def test_msm_point_range_split_combined_on_host(G, oracle):
+    """a single MSM split by point range into 8 partial MSMs (what 8 GPUs would each compute), the 8 partial
+    points added on the host side of the ABI (g16_group_op). One GPU runs the 8 ranges one after the other."""
+    from bench import shard_range
+    n, parts = 1 << 22, 8
+    base, idx, sc, tot = _tiled_msm_inputs(oracle, n, 77)
+    want = oracle.g1_mul(oracle.g1_gen(), tot)
+    acc = None
+    for g in range(parts):
+        lo, hi = shard_range(n, g, parts)
+        plan = G.MsmPlan(1, base[idx[lo:hi]])
+        plan.set_scalars(sc[lo:hi])
+        part, _ = plan.run()
+        plan.close()
+        acc = part if acc is None else G.group_op(1, "add", acc.reshape(1, 8), part.reshape(1, 8))[0]
+    assert np.array_equal(acc, want)
+
+
+# ---------------------------------------------------------------------------------------------- multi-device handle
+def test_multi_device_handle_shards_and_gathers_in_order(G, gpu_ctx, pk_bytes, r1cs_bytes):
+    """g16_init_multi with the same GPU listed twice: request i -> slot i mod 2, both slots run concurrently from their own
+    host threads, proofs and ciphertexts come back in input order and equal the single-device results byte for byte."""
+    n = 37                                                   # odd: the two shards differ in size
+    keys, nonces, ctrs, ins, rs = batch_inputs(n, b"g16-b200-multi")
+    ref_p, ref_c = gpu_ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)
+    multi = G.Groth16Context(pk_bytes, r1cs_bytes, devices=[0, 0])
+    try:
+        assert multi.devices == [0, 0]
+        p, c = multi.prove_chacha_batch(keys, nonces, ctrs, ins, rs)
+        assert p == ref_p and c == ref_c
+        assert multi.counters()["proofs"] == n               # work counters are summed over the devices
+        p1, c1 = multi.prove_chacha_batch(keys[3:4], nonces[3:4], ctrs[3:4], ins[3:4], rs[3:4])   # one request: device slot 0 alone
+        assert p1[0] == ref_p[3] and c1[0] == ref_c[3]
+        p2, _ = multi.prove_chacha_batch(keys[:2], nonces[:2], ctrs[:2], ins[:2], rs[:2])
+        assert p2 == ref_p[:2]
+        assert not multi.batch_status(2).any()
+    finally:
+        multi.close()
+
+
+def test_libprove_serves_concurrent_calls_from_every_device(G, oracle, pk_bytes, r1cs_bytes, monkeypatch):
+    """G16_DEVICES=0,0: InitAlgorithm loads the key twice and starts one batching worker per device slot over the shared
+    queue; every caller still gets the proof of its own request."""
+    from gnark_symmetric_crypto_b200 import _lib
+    L = _lib.load()
+    L.g16_libprove_reset.restype = None
+    L.g16_libprove_reset()
+    monkeypatch.setenv("G16_DEVICES", "0,0")
+    monkeypatch.setenv("G16_PREWARM", "64")
+    try:
+        assert G.InitAlgorithm(G.CHACHA20, pk_bytes, r1cs_bytes) is True
+        st = np.zeros(3, dtype=np.uint64)
+        assert L.g16_libprove_stats(0, st.ctypes.data_as(_lib.u64p)) == 0 and int(st[2]) == 2
+        rng = np.random.default_rng(99)
+        reqs = [(rng.bytes(32), rng.bytes(12), int(rng.integers(0, 1 << 32)), rng.bytes(64)) for _ in range(64)]
+        outs = [None] * len(reqs)
+
+        def worker(t):
+            k, no, c, pt = reqs[t]
+            outs[t] = G.OutputParams.from_json(G.Prove(G.InputParams("chacha20", k, no, c, pt).to_json()))
+        th = [threading.Thread(target=worker, args=(t,)) for t in range(len(reqs))]
+        [x.start() for x in th]; [x.join() for x in th]
+        for (k, no, c, pt), o in zip(reqs, outs):
+            assert o is not None and o.public_signals == oracle.chacha20_xor(k, no, c, pt) and len(o.proof_json) == 164
+        assert L.g16_libprove_stats(0, st.ctypes.data_as(_lib.u64p)) == 0 and int(st[1]) == len(reqs)
+    finally:
+        L.g16_libprove_reset()
+
+
+# ---------------------------------------------------------------------------------------------- per-request verdicts
+def test_unsatisfiable_request_fails_alone(G, oracle, aes128_oracle):
+    """One AES request whose counter range wraps (counter > 0xFFFFFFFB violates the circuit's AssertIsLessOrEqual,
+    circuits/aesV2/aes128.go:50-53) among good ones: the batch runs ONCE, the call reports G16_ERR_UNSAT, the per-request
+    status names the offender, every other proof is the oracle's."""
+    pk, vk, r1 = aes_keys(128)
+    ctx = G.Groth16Context(pk, r1)
+    try:
+        rng = np.random.default_rng(21)
+        n, bad = 12, 7
+        keys = [rng.bytes(16) for _ in range(n)]; nonces = [rng.bytes(12) for _ in range(n)]
+        ctrs = [int(x) for x in rng.integers(0, 1 << 31, n)]; ins = [rng.bytes(64) for _ in range(n)]
+        ctrs[bad] = 0xFFFFFFFD
+        rsm = [b"".join(int(x).to_bytes(32, "big") for x in rng.integers(1, 1 << 62, 3)) for _ in range(n)]
+        k = np.frombuffer(b"".join(keys), dtype=np.uint8).copy(); no = np.frombuffer(b"".join(nonces), dtype=np.uint8).copy()
+        i = np.frombuffer(b"".join(ins), dtype=np.uint8).copy(); c = np.asarray(ctrs, dtype=np.uint32)
+        r = np.frombuffer(b"".join(rsm), dtype=np.uint8).copy()
+        proofs = np.zeros(n * 196, dtype=np.uint8); cts = np.zeros(n * 64, dtype=np.uint8)
+        from gnark_symmetric_crypto_b200._lib import u8p, u32p
+        p8 = lambda a: a.ctypes.data_as(u8p)
+        rc = ctx._L.g16_prove_aes_batch(ctx._h, n, p8(k), 16, p8(no), c.ctypes.data_as(u32p), p8(i), p8(r), p8(proofs), p8(cts))
+        assert rc == 4 and b"1 of 12" in ctx._L.g16_last_error()         # G16_ERR_UNSAT
+        st = ctx.batch_status(n)
+        assert [j for j in range(n) if st[j]] == [bad]
+        assert not proofs[bad * 196:(bad + 1) * 196].any()
+        for j in (0, bad - 1, bad + 1, n - 1):
+            rr, ss, mm = (int.from_bytes(rsm[j][32 * t:32 * t + 32], "big") for t in range(3))
+            want, ct = aes128_oracle.prove(keys[j], nonces[j], ctrs[j], ins[j], rr, ss, mm)
+            assert proofs[j * 196:(j + 1) * 196].tobytes() == want and cts[j * 64:(j + 1) * 64].tobytes() == ct, j
+    finally:
+        ctx.close()
+
+
+def test_prove_rejects_unprovable_aes_requests_on_the_host(G):
+    """Requests the circuit cannot accept never enter a batch: the counter check and the key-size/cipher check answer
+    immediately with an error-value payload (an object, as json.Marshal(err) gives in libprove.go:36-41)."""
+    from gnark_symmetric_crypto_b200 import _lib
+    L = _lib.load()
+    L.g16_libprove_reset.restype = None
+    L.g16_libprove_reset()
+    pk, vk, r1 = aes_keys(128)
+    try:
+        assert G.InitAlgorithm(G.AES_128, pk, r1) is True
+        good = G.InputParams("aes-128-ctr", bytes(16), bytes(12), 0xFFFFFFFB, bytes(64))
+        out = G.OutputParams.from_json(G.Prove(good.to_json()))
+        assert len(out.proof_json) == 196
+        st = np.zeros(3, dtype=np.uint64)
+        assert L.g16_libprove_stats(1, st.ctypes.data_as(_lib.u64p)) == 0
+        proved_before = int(st[1])
+        with pytest.raises(RuntimeError, match="error value"):
+            G.Prove(G.InputParams("aes-128-ctr", bytes(16), bytes(12), 0xFFFFFFFC, bytes(64)).to_json())
+        with pytest.raises(RuntimeError, match="error value"):
+            G.Prove(G.InputParams("aes-128-ctr", bytes(32), bytes(12), 1, bytes(64)).to_json())
+        with pytest.raises(RuntimeError, match="key length must be 16 or 32"):
+            G.Prove(G.InputParams("aes-128-ctr", bytes(24), bytes(12), 1, bytes(64)).to_json())
+        assert L.g16_libprove_stats(1, st.ctypes.data_as(_lib.u64p)) == 0 and int(st[1]) == proved_before   # nothing was queued
+    finally:
+        L.g16_libprove_reset()
+
+
+# ---------------------------------------------------------------------------------------------- ProveBatch
+def test_prove_batch_export(G, oracle, oracle_vk, pk_bytes, r1cs_bytes):
+    """ProveBatch beside Prove: one JSON array in, one JSON array out, order kept, bad requests answered
+    in place with what Prove would have returned, good ones verifier-accepted under the reference's vk.chacha20."""
+    assert G.InitAlgorithm(G.CHACHA20, pk_bytes, r1cs_bytes) is True
+    rng = np.random.default_rng(5150)
+    reqs = [G.InputParams("chacha20", rng.bytes(32), rng.bytes(12), int(rng.integers(0, 1 << 32)), rng.bytes(64)) for _ in range(9)]
+    payload = [json.loads(r.to_json()) for r in reqs]
+    payload.insert(4, {"cipher": "chacha20", "key": [1, 2], "nonce": [], "counter": 0, "input": []})
+    payload.insert(7, {"cipher": "rot13"})
+    res = G.ProveBatch(payload)
+    assert len(res) == 11
+    assert isinstance(res[4], RuntimeError) and "key length must be 32" in str(res[4])
+    assert isinstance(res[7], RuntimeError) and "could not find prover" in str(res[7])
+    good = [x for j, x in enumerate(res) if j not in (4, 7)]
+    for r, o in zip(reqs, good):
+        out = G.OutputParams.from_json(o)
+        assert out.public_signals == oracle.chacha20_xor(r.key, r.nonce, r.counter, r.input)
+        signals = out.public_signals + r.nonce + struct.pack("<I", r.counter) + r.input
+        assert oracle_vk.verify(out.proof_json, oracle.chacha_public_from_signals(signals))
+    assert G.ProveBatch([]) == []
+
+
+# ---------------------------------------------------------------------------------------------- canonical encodings
+def test_verifier_rejects_noncanonical_coordinates(G, oracle, kat):
+    """gnark-crypto's G1/G2 decoders use fp.Element.SetBytesCanonical: a coordinate encoded as x + p is not a valid proof
+    encoding, although it reduces to the same point. Ar.x / Krs.x carry two flag bits (x + p must stay below 2^254 to be
+    expressible: tried on whichever of the two fits), both halves of Bs.x are tried; infinity with a non-zero payload too."""
+    vk = open("tests/golden/vk.chacha20", "rb").read()
+    ver = G.Groth16Verifier(vk)
+    inputs, _ = oracle.chacha_assignment(kat["key"], kat["nonce"], kat["counter"], kat["input"])
+    pub = inputs[1:1153]
+    P = oracle.P_MOD
+    proof = kat["proof"]
+    forged = []
+    for off, masked in ((0, True), (96, True), (32, True), (64, False)):   # Ar.x, Krs.x, Bs.x.A1 (flag byte), Bs.x.A0
+        raw = proof[off:off + 32]
+        flags = raw[0] & 0xC0 if masked else 0
+        x = int.from_bytes(bytes([raw[0] & 0x3F]) + raw[1:], "big") if masked else int.from_bytes(raw, "big")
+        if x + P >= (1 << (254 if masked else 256)):
+            continue
+        enc = bytearray((x + P).to_bytes(32, "big"))
+        enc[0] |= flags
+        f = bytearray(proof); f[off:off + 32] = enc
+        forged.append(bytes(f))
+    assert len(forged) >= 2                                   # the unmasked Bs half always fits
+    inf = bytearray(proof); inf[96:128] = bytes([0x40]) + bytes(30) + b"\x01"   # "infinity" Krs with a stray payload byte
+    forged.append(bytes(inf))
+    verdicts = ver.verify_batch([proof] + forged, [pub] * (1 + len(forged)))
+    assert verdicts.tolist() == [True] + [False] * len(forged)
+    ver.close()
