@@ -38,6 +38,7 @@ BATCH = 1024
 METRIC = "ChaCha20-V3 Groth16 proofs/sec"
 UNIT = "proofs/s"
 IMAD_PER_MADD_G1 = 2640      # 10 modmul x 264 IMAD
+BA_ADD_L0_TRAFFIC = None     # bytes per launch of the dominant kernel, from the ncu --set full capture (filled in from profiles/)
 WORKLOAD = "batched ChaCha20-V3 Groth16 BN254 proofs, 1024 synthetic key/nonce/counter/input requests per GPU (BASELINE config 4)"
 R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617   # BN254 group order
 
@@ -308,7 +309,7 @@ def run_gpu(args):
     # ---------------- per-kernel view: stage timers exist only in the single-stream schedule (the default). When the
     # pipelined schedule was benchmarked (G16_PIPELINE=1) the same step is replayed on one stream for the roofline.
     stages = {}
-    madds = acc_launches = 0
+    madds = acc_launches = z_slots = z_levels = z_buckets = 0
     if rank == 0:
         ctx.set_schedule(False, 0 if not sched["pipelined"] else 512)
         ctx.run()
@@ -319,6 +320,7 @@ def run_gpu(args):
                 stages[kk] = stages.get(kk, 0.0) + v
             c2 = ctx.counters()
             madds += c2["g1_madds_main_stream"]; acc_launches += c2["g1_acc_launches"]
+            z_slots += c2.get("z_sorted_slots", 0); z_levels = c2.get("z_batch_affine_levels", 0); z_buckets += c2.get("z_buckets", 0)
         ctx.fetch(proofs, cts)
         assert np.array_equal(proofs, ref_proofs), "pipelined and single-stream schedules disagree"
         ctx.set_schedule(sched["pipelined"], sched["sub_batch"])
@@ -554,6 +556,16 @@ def run_gpu(args):
         # the wire-driven queries run concurrently on a side stream and are NOT counted: a conservative "achieved".
         achieved = (madds * IMAD_PER_MADD_G1) / (acc_ms / 1e3) / 1e12 if acc_ms else None
         peak = imad["imad_per_s"] / 1e12
+        # Products the accumulation actually executes per bucket addition. With K batch-affine levels (csrc/msm_ba.cuh) the sorted
+        # slots S (entries + padding to 2^K per bucket) go through K pairwise levels at 6 + 3/32 lane-products per pair
+        # (1 prefix + 2 back-substitution + 3 for the affine addition + the thread totals), then S / 2^K group sums through the XYZZ
+        # mixed addition (10 products, the first point of every bucket is a copy). Without it every entry is one XYZZ addition.
+        if z_levels and madds:
+            pairs = sum(z_slots >> (l + 1) for l in range(z_levels))
+            executed_products = pairs * (6 + 3 / 32) + max((z_slots >> z_levels) - z_buckets, 0) * 10
+        else:
+            executed_products = madds * 10
+        products_per_addition = executed_products / madds if madds else None
         # compute_h: 7 transforms of n = 2^15 + the pointwise quotient per proof. Algorithmic bytes 576 n, algorithmic
         # IMAD 264 (7 (n/2) log2 n + 3 n). Reported against HBM as the north star asks; the binding roof is IMAD.
         n_dom = ctx.n
@@ -595,16 +607,25 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(proofs.nbytes + cts.nbytes)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel<G1>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "imad",
+                         "kernel": ("msm_ba_add_kernel (dominant: %d batch-affine levels, with msm_ba_den_kernel / msm_ba_inv_kernel) + msm_accumulate_kernel<G1>"
+                                    % z_levels) if z_levels else "msm_accumulate_kernel<G1>",
+                         "achieved": achieved, "peak": peak,
                          "unit": "TIMAD/s", "frac": (achieved / peak) if achieved else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch (Z query of a 512-proof sub-batch) from the
-                         # ncu --set full capture in profiles/ncu_full_r01.txt; algorithmic bytes of that launch: 2.28 GB sorted
-                         # entries + 1.07 GB bucket sums + 1.18 GB chunk-edge partials = 4.5 GB
-                         "traffic": 4.303e9 if (sched["sub_batch"] == 512 and BATCH == 1024) else None,
-                         "traffic_unit": "bytes per launch (profiles/ncu_full_r01.txt)",
-                         "note": "achieved = Z-query G1 mixed additions x 2640 algorithmic 32-bit IMAD / accumulate-stage time (CUDA events "
-                                 "on the launching stream, sum over launches, same schedule and inputs as the timed region, "
-                                 "taken in the steps that follow it); "
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (msm_ba_add_kernel, level 0 of the Z query of
+                         # a 512-proof sub-batch) from the ncu --set full capture in profiles/ncu_msm_ba_add_r02.txt
+                         "traffic": BA_ADD_L0_TRAFFIC if (z_levels == 3 and sched["sub_batch"] == 512 and BATCH == 1024) else None,
+                         "traffic_unit": "bytes per launch (profiles/ncu_msm_ba_add_r02.txt)",
+                         "executed_products_per_addition": products_per_addition,
+                         "algorithmic_products_per_addition": 10,
+                         "executed_modmul_per_s": (executed_products / (acc_ms / 1e3)) if acc_ms else None,
+                         "executed_frac_of_modmul_peak": (executed_products / (acc_ms / 1e3) / imad["modmul_per_s"]) if acc_ms else None,
+                         "note": "achieved = Z-query bucket additions x 2640 ALGORITHMIC 32-bit IMAD (SURVEY 8d: XYZZ mixed addition, 10 products) "
+                                 "/ accumulate-stage time (CUDA events on the launching stream, sum over launches, same schedule and inputs as "
+                                 "the timed region, taken in the steps that follow it). The stage executes fewer products than the algorithmic "
+                                 "count (executed_products_per_addition: batch-affine additions with a shared inversion, gnark's own "
+                                 "multiexp_affine.go algorithm), so frac measures time against the SURVEY work definition, and "
+                                 "executed_frac_of_modmul_peak how busy the multiplier is with what is actually run. "
                                  "peak = mad.lo.u32 rate measured in this run (not in MEASURED_PEAKS.json); HBM is not the bound "
                                  "(SURVEY finding 8)",
                          "imad_wide_peak": imad["imad_wide_per_s"] / 1e12, "modmul_per_s": imad["modmul_per_s"],

@@ -3,4 +3,4 @@ reclaimprotocol/gnark-symmetric-crypto. The compute path is the CUDA library lib
 package does not load it, the first call does, and a missing library is an ImportError (no CPU fallback)."""
 from . import _lib  # noqa: F401
 from .prover import (AES_128, AES_256, CHACHA20, Groth16Context, Groth16Verifier, InitAlgorithm, InitVerifier, ProveBatch, InputParams, InputVerifyParams, MsmPlan, OutputParams,  # noqa: F401
-                     Prove, ProverError, Verify, aes_witness, bsb22_challenge, decompress, field_op, g2_subgroup_check, group_op, imad_peak, msm, ntt, ntt_bench, pairing_check)
+                     Prove, ProverError, Setup, Verify, aes_witness, bsb22_challenge, decompress, field_op, g2_subgroup_check, group_op, imad_peak, msm, ntt, ntt_bench, pairing_check)

@@ -48,6 +48,7 @@ EXPORTS = {
     "g16_solve_ex": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_size_t, u8p, u64p, u64p, u64p, u64p]),
     "g16_aes_witness": (C.c_int, [u8p, C.c_size_t, u8p, u32p, u8p, C.c_size_t, u8p, u64p]),
     "g16_bsb22_challenge": (C.c_int, [u64p, C.c_size_t, u64p]),
+    "g16_setup": (C.c_int, [C.c_char_p, C.c_size_t, u8p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "g16_verify_init": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
     "g16_verify_info": (C.c_int, [C.c_void_p, u64p]),
     "g16_verify_batch": (C.c_int, [C.c_void_p, C.c_size_t, u8p, C.c_void_p, C.c_int, u8p, C.POINTER(C.c_float)]),
@@ -57,6 +58,7 @@ EXPORTS = {
     "g16_set_schedule": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "g16_last_stage_ms": (C.c_int, [C.c_void_p, f32p]),
     "g16_last_counters": (C.c_int, [C.c_void_p, u64p]),
+    "g16_last_counters_ex": (C.c_int, [C.c_void_p, u64p]),
     "g16_field_op": (C.c_int, [C.c_int, C.c_int, u64p, u64p, u64p, C.c_size_t]),
     "g16_group_op": (C.c_int, [C.c_int, C.c_int, u64p, u64p, u64p, C.c_size_t]),
     "g16_decompress": (C.c_int, [C.c_int, u8p, u64p, C.c_size_t]),

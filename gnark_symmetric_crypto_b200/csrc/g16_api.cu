@@ -21,14 +21,41 @@ __attribute__((constructor)) static void g16_eager_module_loading() { setenv("CU
 // One handle = the context of one GPU (cx) plus, for a multi-device handle (g16_init_multi), the handles of the other
 // devices of the list. Independent proofs are the sharding unit: request i of a batch goes to device i mod G,
 // every device runs its own pipeline from its own host thread, results are gathered in input order; no collective.
-struct g16_ctx {
+// `mu` guards one entry point at a time on the device context; `seq_mu` is held across the stage -> run -> fetch sequence of
+// the one-call batch entry points, so that callers sharing a device (the multi-device handle used by ProveBatch, the per-device
+// handles used by the Prove batcher's workers) never interleave their phases. (The split-phase API used by benchmarks is
+// sequenced by its caller.)
+struct DevCore {
     std::unique_ptr<Ctx> cx;
-    std::mutex mu;
+    std::mutex mu, seq_mu;
+};
+struct g16_ctx {
+    std::shared_ptr<DevCore> core = std::make_shared<DevCore>();
+    std::unique_ptr<Ctx>& cx = core->cx;
+    std::mutex& mu = core->mu;
     std::vector<std::unique_ptr<g16_ctx>> extra;   // devices[1..] of a multi-device handle
+    std::unique_ptr<g16_ctx> view0;                // single-device handle of devices[0] (shares this handle's core)
     std::vector<size_t> shard_n;                   // requests staged on each device by the last multi-device stage
     size_t staged_total = 0;
+    g16_ctx() {}
+    explicit g16_ctx(std::shared_ptr<DevCore> c) : core(std::move(c)) {}
     size_t ndev() const { return 1 + extra.size(); }
-    g16_ctx* dev(size_t k) { return k == 0 ? this : extra[k - 1].get(); }
+    // single-device handle of slot k: for slot 0 of a multi-device handle a view that shares the core but never shards
+    g16_ctx* dev(size_t k) {
+        if (k > 0) return extra[k - 1].get();
+        if (extra.empty()) return this;
+        if (!view0) view0.reset(new g16_ctx(core));
+        return view0.get();
+    }
+};
+// locks the phase sequence of every device a batch of n requests will touch (slot order: no deadlock between callers)
+struct SeqLock {
+    std::vector<std::unique_lock<std::mutex>> held;
+    SeqLock(g16_ctx* ctx, size_t n) {
+        if (!ctx) return;
+        const size_t G = (ctx->ndev() > 1 && n >= 2) ? ctx->ndev() : 1;
+        for (size_t k = 0; k < G; k++) held.emplace_back(ctx->dev(k)->core->seq_mu);
+    }
 };
 
 struct g16_vctx {
@@ -234,6 +261,7 @@ int g16_init_multi(const uint8_t* pk, size_t pk_len, const uint8_t* r1cs, size_t
             if (errs[k]) { release_all(); std::rethrow_exception(errs[k]); }
         std::unique_ptr<g16_ctx> head = std::move(hs[0]);
         for (size_t k = 1; k < n_devices; k++) head->extra.push_back(std::move(hs[k]));
+        head->dev(0);   // create the slot-0 view now (not lazily from concurrent callers)
         *out = head.release();
     });
 }
@@ -447,6 +475,7 @@ int g16_chacha_batch_fetch(g16_ctx* ctx, uint8_t* proofs_out, uint8_t* ct_out) {
 // that exists (the slots of the failed requests are zero); g16_last_batch_status tells which ones failed.
 int g16_prove_chacha_batch(g16_ctx* ctx, size_t n, const uint8_t* keys, const uint8_t* nonces, const uint32_t* counters,
                            const uint8_t* inputs, const uint8_t* rs, uint8_t* proofs_out, uint8_t* ct_out) {
+    SeqLock seq(ctx, n);
     int rc = g16_chacha_batch_stage(ctx, n, keys, nonces, counters, inputs, rs);
     if (rc) return rc;
     rc = g16_chacha_batch_run(ctx, nullptr);
@@ -459,6 +488,7 @@ int g16_prove_chacha_batch(g16_ctx* ctx, size_t n, const uint8_t* keys, const ui
 }
 int g16_prove_aes_batch(g16_ctx* ctx, size_t n, const uint8_t* keys, size_t key_len, const uint8_t* nonces,
                         const uint32_t* counters, const uint8_t* inputs, const uint8_t* rsm, uint8_t* proofs_out, uint8_t* ct_out) {
+    SeqLock seq(ctx, n);
     int rc = g16_aes_batch_stage(ctx, n, keys, key_len, nonces, counters, inputs, rsm);
     if (rc) return rc;
     rc = g16_chacha_batch_run(ctx, nullptr);
@@ -523,6 +553,15 @@ int g16_last_counters(const g16_ctx* ctx, uint64_t out[8]) {
                 std::lock_guard<std::mutex> lk(h->dev(k)->mu);
                 for (int j = 0; j < 7; j++) out[j] += h->dev(k)->cx->counters[j];
             }
+    });
+}
+
+int g16_last_counters_ex(const g16_ctx* ctx, uint64_t out[16]) {
+    return guarded([&] {
+        REQUIRE(ctx && out, "NULL argument");
+        g16_ctx* h = const_cast<g16_ctx*>(ctx);
+        std::lock_guard<std::mutex> lk(h->mu);
+        memcpy(out, ctx->cx->counters, sizeof(uint64_t) * 16);
     });
 }
 
@@ -797,6 +836,40 @@ int g16_msm(int group, const uint64_t* points, const uint64_t* scalars, int scal
     g16_msm_plan_free(p);
     t_last_error = keep;
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ setup
+int g16_setup(const uint8_t* r1cs, size_t r1cs_len, const uint8_t* trapdoor_be, int device, uint8_t** pk_out, size_t* pk_len,
+              uint8_t** vk_out, size_t* vk_len) {
+    return guarded([&] {
+        REQUIRE(r1cs && r1cs_len && pk_out && pk_len && vk_out && vk_len, "NULL argument");
+        *pk_out = *vk_out = nullptr;
+        *pk_len = *vk_len = 0;
+        require_device();
+        G16_CUDA(cudaSetDevice(device));
+        uint8_t td[192];
+        if (trapdoor_be) memcpy(td, trapdoor_be, 192);
+        else random_scalars_be(td, 6);   // gnark draws the toxic waste from crypto/rand (zero has probability 2^-254)
+        std::vector<uint8_t> pk, vk;
+        cudaStream_t st = nullptr;
+        G16_CUDA(cudaStreamCreate(&st));
+        try {
+            setup_run(r1cs, r1cs_len, td, pk, vk, st);
+        } catch (...) {
+            cudaStreamDestroy(st);
+            volatile uint8_t* p = td; for (int i = 0; i < 192; i++) p[i] = 0;
+            throw;
+        }
+        cudaStreamDestroy(st);
+        { volatile uint8_t* p = td; for (int i = 0; i < 192; i++) p[i] = 0; }
+        uint8_t* a = (uint8_t*)malloc(pk.size() ? pk.size() : 1);
+        uint8_t* b = (uint8_t*)malloc(vk.size() ? vk.size() : 1);
+        if (!a || !b) { free(a); free(b); throw std::bad_alloc(); }
+        memcpy(a, pk.data(), pk.size());
+        memcpy(b, vk.data(), vk.size());
+        *pk_out = a; *pk_len = pk.size();
+        *vk_out = b; *vk_len = vk.size();
+    });
 }
 
 // ------------------------------------------------------------------------------------------------ verifier

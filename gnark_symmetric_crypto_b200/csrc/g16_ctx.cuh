@@ -84,7 +84,7 @@ struct Ctx {
     StageTimer timer;
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     size_t launches = 0;
-    uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t counters[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t sub_batch = 512;
     bool tables_ready = false;
     SolverGraphCache* solver_graphs = nullptr;
@@ -102,6 +102,7 @@ struct Ctx {
         if (stream) cudaStreamDestroy(stream);
     }
     size_t proof_bytes() const { return n_commit ? 196 : 164; }
+    uint64_t nZ_buckets_total(size_t n) const { return (uint64_t)n << (qZ.c - 1); }   // bucket sets of the Z query: one per proof
 };
 
 static inline int env_int(const char* name, int dflt) {
@@ -707,6 +708,9 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     cx.counters[3] = cx.ws2.log_n;
     cx.counters[4] = cx.launches;
     cx.counters[5] = n;
+    cx.counters[8] = cx.ws1.log_sum(st, 1) + cx.ws1c.log_sum(cx.stream3, 1);   // sorted slots of the Z query (entries + batch-affine padding)
+    cx.counters[9] = (uint64_t)cx.ws1.last_K;                                   // batch-affine levels of the Z query
+    cx.counters[10] = (uint64_t)cx.nZ_buckets_total(n);
     cx.counters[7] = (uint64_t)cx.sub_batch | ((uint64_t)(piped ? 1 : 0) << 32) | ((uint64_t)(eval_z ? 1 : 0) << 33);
     if (status & 4u) throw std::runtime_error("solver: unsupported hint");
     // Per-witness verdicts stay in h_status: the batch has run to completion, so the proofs of the satisfied witnesses are

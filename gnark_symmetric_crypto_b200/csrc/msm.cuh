@@ -18,6 +18,7 @@
 #pragma once
 #include "msm_types.hpp"
 #include <cstdlib>
+#include <type_traits>
 
 namespace g16 {
 
@@ -54,12 +55,14 @@ FD int recode_digit(const Recoded& r, int w, int c, int& carry) {
     return d;
 }
 
-// One thread per (row, point). pass 0: histogram ; pass 1: scatter into the sorted entry array.
+// One thread per (row, point). pass 0: histogram ; pass 1: scatter into the sorted entry array ; pass 2: scatter for the
+// batch-affine path (msm_ba.cuh): runs are padded to multiples of 2^ba_shift slots, a slot holds only the point reference
+// (refs[pos]), and the first slot of every group of 2^ba_shift writes the group's key (bucket id, group index) to `entries`.
 // scalar of (row r, point i) = scalars[r*row_stride + e*elem_stride], e = map ? map[i] : i. Consecutive threads walk the
 // unit-stride dimension (points for row-major h vectors, rows for the wire-major witness array).
 static __global__ void msm_digits_kernel(MsmShape sh, const Fr* __restrict__ scalars, size_t row_stride, size_t elem_stride,
                                   const uint32_t* __restrict__ map, int is_mont, int pass, uint32_t* __restrict__ counts,
-                                  uint2* __restrict__ entries) {
+                                  uint2* __restrict__ entries, uint32_t* __restrict__ refs = nullptr, int ba_shift = 0) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)sh.n * sh.rows) return;
     uint32_t row, i;
@@ -82,7 +85,12 @@ static __global__ void msm_digits_kernel(MsmShape sh, const Fr* __restrict__ sca
         } else {
             uint32_t pos = atomicAdd(&counts[b], 1u);   // counts holds the running write cursor (= exclusive scan)
             uint32_t ref = sh.precomp ? (uint32_t)w * sh.n + i : i;
-            entries[pos] = make_uint2(b, (ref << 1) | neg);
+            if (pass == 1) {
+                entries[pos] = make_uint2(b, (ref << 1) | neg);
+            } else {
+                refs[pos] = (ref << 1) | neg;
+                if ((pos & ((1u << ba_shift) - 1u)) == 0) entries[pos >> ba_shift] = make_uint2(b, (pos >> ba_shift) << 1);
+            }
         }
     }
 }
@@ -91,26 +99,39 @@ static __global__ void msm_digits_kernel(MsmShape sh, const Fr* __restrict__ sca
 // three-kernel scan: tile sums -> scan of tile sums (single block) -> rescan tiles. Tile = 256 threads x 8 items.
 #define SCAN_T 256
 #define SCAN_I 8
-static __global__ void scan_tile_sums(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ tile_sums) {
+// pad_mask = 2^K - 1 rounds every count up to a multiple of 2^K before it is summed (batch-affine path: padded runs);
+// raw_sums (optional) receives the unpadded tile sums, i.e. the number of real entries.
+static __global__ void scan_tile_sums(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ tile_sums, uint32_t pad_mask = 0,
+                                      uint32_t* __restrict__ raw_sums = nullptr) {
     __shared__ uint32_t sm[SCAN_T];
+    __shared__ uint32_t sr[SCAN_T];
     size_t base = (size_t)blockIdx.x * SCAN_T * SCAN_I;
-    uint32_t s = 0;
+    uint32_t s = 0, r = 0;
     for (int k = 0; k < SCAN_I; k++) {
         size_t idx = base + (size_t)k * SCAN_T + threadIdx.x;
-        if (idx < n) s += in[idx];
+        if (idx < n) { uint32_t v = in[idx]; r += v; s += (v + pad_mask) & ~pad_mask; }
     }
     sm[threadIdx.x] = s;
+    sr[threadIdx.x] = r;
     __syncthreads();
     for (int off = SCAN_T / 2; off > 0; off >>= 1) {
-        if ((int)threadIdx.x < off) sm[threadIdx.x] += sm[threadIdx.x + off];
+        if ((int)threadIdx.x < off) { sm[threadIdx.x] += sm[threadIdx.x + off]; sr[threadIdx.x] += sr[threadIdx.x + off]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = sm[0];
+    if (threadIdx.x == 0) { tile_sums[blockIdx.x] = sm[0]; if (raw_sums) raw_sums[blockIdx.x] = sr[0]; }
 }
-// single block: in-place exclusive scan of `m` tile sums; writes the grand total to *total
-static __global__ void scan_of_sums(uint32_t* __restrict__ tile_sums, size_t m, uint32_t* __restrict__ total) {
+// single block: in-place exclusive scan of `m` tile sums; writes total[0] = the grand total (sorted slots),
+// total[1] = the sum of raw_sums (real entries; = total[0] without padding), total[2] = total[0] >> ba_shift
+static __global__ void scan_of_sums(uint32_t* __restrict__ tile_sums, size_t m, uint32_t* __restrict__ total,
+                                    const uint32_t* __restrict__ raw_sums = nullptr, int ba_shift = 0) {
     __shared__ uint32_t sm[SCAN_T];
     __shared__ uint32_t carry;
+    __shared__ uint32_t raw[SCAN_T];
+    {
+        uint32_t r = 0;
+        if (raw_sums) for (size_t i = threadIdx.x; i < m; i += SCAN_T) r += raw_sums[i];
+        raw[threadIdx.x] = r;
+    }
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (size_t base = 0; base < m; base += SCAN_T) {
@@ -131,17 +152,23 @@ static __global__ void scan_of_sums(uint32_t* __restrict__ tile_sums, size_t m, 
         if (threadIdx.x == SCAN_T - 1) carry = c0 + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total = carry;
+    if (threadIdx.x == 0) {
+        uint32_t r = 0;
+        for (int i = 0; i < SCAN_T; i++) r += raw[i];
+        total[0] = carry;
+        total[1] = raw_sums ? r : carry;
+        total[2] = carry >> ba_shift;
+    }
 }
 // each tile: exclusive scan of its SCAN_T*SCAN_I items (thread-contiguous layout) + tile offset ; out may alias in
 static __global__ void scan_tiles(const uint32_t* __restrict__ in, size_t n, const uint32_t* __restrict__ tile_offs,
-                           uint32_t* __restrict__ out) {
+                           uint32_t* __restrict__ out, uint32_t pad_mask = 0) {
     __shared__ uint32_t sm[SCAN_T];
     size_t base = (size_t)blockIdx.x * SCAN_T * SCAN_I + (size_t)threadIdx.x * SCAN_I;
     uint32_t v[SCAN_I];
     uint32_t s = 0;
     for (int k = 0; k < SCAN_I; k++) {
-        v[k] = (base + k < n) ? in[base + k] : 0;
+        v[k] = (base + k < n) ? ((in[base + k] + pad_mask) & ~pad_mask) : 0;
         s += v[k];
     }
     sm[threadIdx.x] = s;
@@ -386,6 +413,14 @@ __global__ void msm_precompute_kernel(const typename C::A* __restrict__ pts, uin
     }
 }
 
+// the batch-affine levels exist for G1 only (k_msm_ba.cu)
+template <class C> constexpr bool msm_ba_available() { return std::is_same<C, G1>::value; }
+static inline void msm_ba_run(MsmWorkspace<G1>& ws, const G1Affine* bases, size_t max_slots, int K, cudaStream_t stream) {
+    G1Affine* lvl[MSM_BA_MAX_LEVELS] = {ws.ba_lvl[0].p, ws.ba_lvl[1].p, ws.ba_lvl[2].p};
+    msm_ba_levels(bases, ws.ba_refs.p, ws.total.p, max_slots, K, lvl, ws.ba_scratch.p, stream);
+}
+static inline void msm_ba_run(MsmWorkspace<G2>&, const G2Affine*, size_t, int, cudaStream_t) {}
+
 // ------------------------------------------------------------------------------------------------ host driver
 // Runs the whole pipeline on `stream`; result XYZZ per row is left in ws.result (device). No host synchronisation.
 template <class C>
@@ -396,22 +431,48 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     const size_t max_entries = (size_t)sh.rows * sh.n * sh.nwin;
     if (nbuckets >= 0xFFFFFFF0ull || max_entries >= 0xFFFFFFF0ull || (size_t)sh.n * sh.nwin >= (1ull << 31))
         throw std::runtime_error("msm: problem too large for 32-bit keys");
+    // Batch-affine path (msm_ba.cuh; G1 only): K pairwise affine levels in front of the XYZZ accumulation when the problem is
+    // large enough to amortise three more launches and the buckets are long enough for the padding to 2^K slots to stay small
+    // (nominal run length = entries per bucket for uniform digits: K = 3 from 24 on, K = 2 from 8 on). G16_MSM_BA=0 disables it,
+    // G16_MSM_BA_K=1..3 forces K.
+    int K = 0;
+    if (msm_ba_available<C>()) {
+        static const int ba_on = [] { const char* v = getenv("G16_MSM_BA"); return v && *v ? atoi(v) : 1; }();
+        static const int ba_k = [] { const char* v = getenv("G16_MSM_BA_K"); return v && *v ? atoi(v) : 0; }();
+        static const long ba_min = [] { const char* v = getenv("G16_MSM_BA_MIN"); return v && *v ? atol(v) : (1l << 21); }();
+        const double run = (double)max_entries / (double)nbuckets;
+        if (ba_on && (long)max_entries >= ba_min) K = ba_k > 0 ? (ba_k > MSM_BA_MAX_LEVELS ? MSM_BA_MAX_LEVELS : ba_k) : (run >= 24.0 ? 3 : (run >= 8.0 ? 2 : 0));
+    }
+    const uint32_t pad_mask = (1u << K) - 1u;
+    // sorted slots: every non-empty bucket is padded by at most 2^K - 1 null slots
+    size_t max_slots = max_entries;
+    if (K) {
+        const size_t a = max_entries + (size_t)pad_mask * nbuckets, b = max_entries << K;
+        max_slots = a < b ? a : b;
+        if (max_slots >= 0xFFFFFFF0ull) throw std::runtime_error("msm: problem too large for 32-bit slot positions");
+    }
+    const size_t acc_entries = max_slots >> K;   // what the XYZZ accumulation walks: entries, or one group sum per 2^K slots
     int L = chunk_len;
     if (L <= 0) {
         // enough chunks to fill the machine a few times over, but not shorter than 8 / longer than 64 entries
         size_t want_threads = 148 * 512 * 4;
-        size_t l = max_entries / want_threads;
+        size_t l = acc_entries / want_threads;
         static const int lmax = [] { const char* v = getenv("G16_MSM_LMAX"); return v && *v ? atoi(v) : 64; }();
         L = l < 8 ? 8 : (l > (size_t)lmax ? lmax : (int)l);
     }
-    const size_t max_chunks = (max_entries + L - 1) / L;
+    const size_t max_chunks = (acc_entries + L - 1) / L;
     const size_t ntiles = (nbuckets + SCAN_T * SCAN_I - 1) / (SCAN_T * SCAN_I);
 
     ws.counts.ensure(nbuckets);
-    ws.tile_sums.ensure(ntiles);
-    ws.total.ensure(1);
-    ws.entries.ensure(max_entries);
+    ws.tile_sums.ensure(2 * ntiles);   // padded tile sums, then the raw ones
+    ws.total.ensure(8);
+    ws.entries.ensure(acc_entries);
     ws.buckets.ensure(nbuckets);
+    if (K) {
+        ws.ba_refs.ensure(max_slots);
+        for (int l = 0; l < K; l++) ws.ba_lvl[l].ensure(max_slots >> (l + 1));
+        ws.ba_scratch.ensure(msm_ba_scratch_elems(max_slots));
+    }
     const size_t n_l0 = 2 * max_chunks;                                              // level-0 partial sequence
     const size_t n_l1 = 2 * ((n_l0 + MSM_MERGE_C - 1) / MSM_MERGE_C);
     ws.part_val[0].ensure(n_l0);
@@ -426,20 +487,36 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     const size_t nthreads = (size_t)sh.n * sh.rows;
     G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, elem_stride, map, is_mont, 0,
                ws.counts.p, ws.entries.p);
-    G16_LAUNCH(scan_tile_sums, (unsigned)ntiles, SCAN_T, 0, stream, true, ws.counts.p, nbuckets, ws.tile_sums.p);
-    G16_LAUNCH(scan_of_sums, 1, SCAN_T, 0, stream, true, ws.tile_sums.p, ntiles, ws.total.p);
-    G16_LAUNCH(scan_tiles, (unsigned)ntiles, SCAN_T, 0, stream, true, ws.counts.p, nbuckets, ws.tile_sums.p, ws.counts.p);
-    G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, elem_stride, map, is_mont, 1,
-               ws.counts.p, ws.entries.p);
-    G16_CHECK_LAUNCH();
-    if (tm) tm->mark(ST_MSM_ACC, stream);
-    {
+    uint32_t* raw_sums = ws.tile_sums.p + ntiles;
+    G16_LAUNCH(scan_tile_sums, (unsigned)ntiles, SCAN_T, 0, stream, true, ws.counts.p, nbuckets, ws.tile_sums.p, pad_mask, raw_sums);
+    G16_LAUNCH(scan_of_sums, 1, SCAN_T, 0, stream, true, ws.tile_sums.p, ntiles, ws.total.p, (const uint32_t*)raw_sums, K);
+    G16_LAUNCH(scan_tiles, (unsigned)ntiles, SCAN_T, 0, stream, true, ws.counts.p, nbuckets, ws.tile_sums.p, ws.counts.p, pad_mask);
+    // the XYZZ accumulation (and the merge levels after it) walk ws.entries with the live length at `acc_total`
+    const uint32_t* acc_total = ws.total.p + (K ? 2 : 0);
+    if (!K) {
+        G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, elem_stride, map, is_mont, 1,
+                   ws.counts.p, ws.entries.p);
+        G16_CHECK_LAUNCH();
+        if (tm) tm->mark(ST_MSM_ACC, stream);
         auto k = msm_accumulate_kernel<C>;
-        G16_LAUNCH(k, div_up(max_chunks, 128), 128, 0, stream, false, bases, ws.entries.p, ws.total.p, L, ws.buckets.p,
+        G16_LAUNCH(k, div_up(max_chunks, 128), 128, 0, stream, false, bases, ws.entries.p, acc_total, L, ws.buckets.p,
                    ws.part_val[0].p, ws.part_key[0].p);
+        ws.launches += 6;
+    } else {
+        G16_CUDA(cudaMemsetAsync(ws.ba_refs.p, 0xFF, max_slots * sizeof(uint32_t), stream));   // padding slots stay null references
+        G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, elem_stride, map, is_mont, 2,
+                   ws.counts.p, ws.entries.p, ws.ba_refs.p, K);
+        G16_CHECK_LAUNCH();
+        if (tm) tm->mark(ST_MSM_ACC, stream);
+        if (getenv("G16_MSM_BA_TRACE")) fprintf(stderr, "[msm] batch-affine K=%d rows=%u n=%u c=%d max_slots=%zu\n", K, sh.rows, sh.n, sh.c, max_slots);
+        msm_ba_run(ws, bases, max_slots, K, stream);
+        // one group sum per 2^K slots is left: the sorted-run accumulation over (bucket, group) keys finishes the buckets
+        auto k = msm_accumulate_kernel<C>;
+        G16_LAUNCH(k, div_up(max_chunks, 128), 128, 0, stream, false, (const typename C::A*)ws.ba_lvl[K - 1].p, ws.entries.p, acc_total, L,
+                   ws.buckets.p, ws.part_val[0].p, ws.part_key[0].p);
+        ws.launches += 6 + 3 * K;
     }
     if (tm) tm->mark(ST_MSM_REDUCE, stream);
-    ws.launches += 6;
     {
         // merge tree over the partial sequence; grids are sized for the upper bound, threads past the live length exit
         size_t n_up = n_l0;
@@ -447,7 +524,7 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
         while (n_up > 64) {
             size_t slices = (n_up + MSM_MERGE_C - 1) / MSM_MERGE_C;
             auto k = msm_merge_level_kernel<C>;
-            G16_LAUNCH(k, div_up(slices, 128), 128, 0, stream, false, ws.total.p, L, level, ws.part_key[pp].p,
+            G16_LAUNCH(k, div_up(slices, 128), 128, 0, stream, false, acc_total, L, level, ws.part_key[pp].p,
                        ws.part_val[pp].p, ws.part_key[pp ^ 1].p, ws.part_val[pp ^ 1].p, ws.buckets.p);
             n_up = 2 * slices;
             level++;
@@ -455,19 +532,21 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
             ws.launches++;
         }
         auto k = msm_merge_final_kernel<C>;
-        G16_LAUNCH(k, div_up(n_up, 128), 128, 0, stream, false, ws.total.p, L, level, ws.part_key[pp].p, ws.part_val[pp].p,
+        G16_LAUNCH(k, div_up(n_up, 128), 128, 0, stream, false, acc_total, L, level, ws.part_key[pp].p, ws.part_val[pp].p,
                    ws.buckets.p);
         ws.launches++;
     }
     G16_CHECK_LAUNCH();
-    if (ws.entry_log.n < ws.log_n + 1) {   // grow the log (rare; keeps old values)
-        DevBuf<uint32_t> bigger((ws.log_n + 1) * 2 + 64);
-        if (ws.log_n) G16_CUDA(cudaMemcpyAsync(bigger.p, ws.entry_log.p, ws.log_n * 4, cudaMemcpyDeviceToDevice, stream));
+    if (ws.entry_log.n < 2 * (ws.log_n + 1)) {   // grow the log (rare; keeps old values)
+        DevBuf<uint32_t> bigger((ws.log_n + 1) * 4 + 64);
+        if (ws.log_n) G16_CUDA(cudaMemcpyAsync(bigger.p, ws.entry_log.p, ws.log_n * 8, cudaMemcpyDeviceToDevice, stream));
         G16_CUDA(cudaStreamSynchronize(stream));
         ws.entry_log = std::move(bigger);
     }
-    G16_CUDA(cudaMemcpyAsync(ws.entry_log.p + ws.log_n, ws.total.p, 4, cudaMemcpyDeviceToDevice, stream));
+    G16_CUDA(cudaMemcpyAsync(ws.entry_log.p + 2 * ws.log_n, ws.total.p + 1, 4, cudaMemcpyDeviceToDevice, stream));      // entries = additions
+    G16_CUDA(cudaMemcpyAsync(ws.entry_log.p + 2 * ws.log_n + 1, ws.total.p, 4, cudaMemcpyDeviceToDevice, stream));     // sorted slots
     ws.log_n++;
+    ws.last_K = K;
     // reduction tree. Arity 32 minimises the work (2 + 3/32 additions per bucket) and is used whenever its first level
     // has enough nodes to fill the machine; a small problem (a single proof: 16384 buckets -> 512 nodes) is bound by the
     // serial chain inside a node instead (2 x arity additions per level), so it gets arity 4 and more, shorter levels.

@@ -23,21 +23,27 @@ static const int MSM_TREE_LOG_G_SMALL = 2;                              // arity
 template <class C>
 struct MsmWorkspace {
     typedef typename C::X X;
-    DevBuf<uint32_t> counts, tile_sums, total, part_key[2];
+    DevBuf<uint32_t> counts, tile_sums, total, part_key[2];   // total: [0] sorted slots, [1] entries (= additions), [2] slots >> K
     DevBuf<uint2> entries;
     DevBuf<X> buckets, part_val[2], lvlR[2], lvlV[2], result;
+    // batch-affine path (G1, msm_ba.cuh): padded point references, one level buffer per pairwise level, running products
+    DevBuf<uint32_t> ba_refs;
+    DevBuf<typename C::A> ba_lvl[3];
+    DevBuf<typename C::F> ba_scratch;
     size_t launches = 0;
-    // number of sorted entries (= mixed additions of the accumulate kernel) of every run since log_reset()
+    // per run since log_reset(): two words — the number of entries (= bucket additions, the algorithmic work) and the number of
+    // sorted slots (entries + the padding of the batch-affine path; equal without it)
     DevBuf<uint32_t> entry_log;
     size_t log_n = 0;
+    int last_K = 0;   // batch-affine levels of the last run (0 = XYZZ accumulation only)
     void log_reset() { log_n = 0; }
-    uint64_t log_sum(cudaStream_t st) {   // synchronises the stream
+    uint64_t log_sum(cudaStream_t st, int word = 0) {   // synchronises the stream; word 0 = entries, 1 = slots
         if (!log_n) return 0;
-        std::vector<uint32_t> h(log_n);
-        entry_log.download(h.data(), log_n, st);
+        std::vector<uint32_t> h(2 * log_n);
+        entry_log.download(h.data(), 2 * log_n, st);
         G16_CUDA(cudaStreamSynchronize(st));
         uint64_t s = 0;
-        for (uint32_t v : h) s += v;
+        for (size_t i = 0; i < log_n; i++) s += h[2 * i + word];
         return s;
     }
 };
@@ -76,6 +82,11 @@ void xyzz_add_g1(G1XYZZ* a, const G1XYZZ* b, uint32_t n, cudaStream_t stream);  
 void group_dft_g1(const G1Affine* Z, uint32_t nZ, int lg, const Fr* scale, int negate, const Fr* tw_inv, G1XYZZ* work,
                   uint32_t n_out, G1Affine* out, cudaStream_t stream);
 void xyzz_to_affine_g1(const G1XYZZ* in, uint32_t n, G1Affine* out, cudaStream_t stream);
+// batch-affine pairwise levels (k_msm_ba.cu): K rounds of "slot 2q + slot 2q+1 -> slot q", one shared inversion per 1024 pairs
+static const int MSM_BA_MAX_LEVELS = 3;
+size_t msm_ba_scratch_elems(size_t max_slots);
+void msm_ba_levels(const G1Affine* bases, const uint32_t* refs, const uint32_t* total_slots, size_t max_slots, int K,
+                   G1Affine* const* lvl, Fp* scratch, cudaStream_t stream);
 void xyzz_to_affine_g2(const G2XYZZ* in, uint32_t n, G2Affine* out, cudaStream_t stream);
 
 }  // namespace g16

@@ -47,6 +47,10 @@ struct AssemblyScratch {
     DevBuf<G1XYZZ> Ar, Bs1, nrsd, win_tab;   // win_tab: 15 window multiples per variable-base half-product (4 per proof)
 };
 
+// Groth16 Setup (k_setup.cu): r1cs bytes + trapdoor (6 x 32-byte big-endian: tau alpha beta gamma delta sigma) -> pk / vk bytes
+void setup_run(const uint8_t* r1cs_bytes, size_t r1cs_len, const uint8_t* trapdoor_be, std::vector<uint8_t>& pk, std::vector<uint8_t>& vk,
+               cudaStream_t st);
+
 // all pointers are device pointers
 void launch_decompress_g1(const uint8_t* in, uint32_t n, G1Affine* out, uint32_t* err, cudaStream_t st);
 void launch_decompress_g2(const uint8_t* in, uint32_t n, G2Affine* out, uint32_t* err, cudaStream_t st);

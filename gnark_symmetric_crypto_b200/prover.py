@@ -159,6 +159,26 @@ def Verify(params: bytes) -> bool:
     return bool(L.Verify(s))
 
 
+def Setup(r1cs: bytes, trapdoor=None, device: int = 0):
+    """keygen.go:359-435 (groth16.Setup + WriteTo) on the GPU: -> (pk bytes, vk bytes) in the layouts InitAlgorithm /
+    InitVerifier read. trapdoor: six ints (tau, alpha, beta, gamma, delta, sigma) for reproducible keys, or None to draw
+    the toxic waste from the OS CSPRNG inside the library (what gnark does)."""
+    L = _lib.load()
+    td = None
+    if trapdoor is not None:
+        if len(trapdoor) != 6:
+            raise ValueError("trapdoor = (tau, alpha, beta, gamma, delta, sigma)")
+        td = np.frombuffer(b"".join(int(x).to_bytes(32, "big") for x in trapdoor), dtype=np.uint8).copy()
+    pk, vk = C.c_void_p(), C.c_void_p()
+    npk, nvk = C.c_size_t(0), C.c_size_t(0)
+    _check(L.g16_setup(r1cs, len(r1cs), _p8(td) if td is not None else None, device, C.byref(pk), C.byref(npk), C.byref(vk), C.byref(nvk)))
+    try:
+        return C.string_at(pk, npk.value), C.string_at(vk, nvk.value)
+    finally:
+        L.Free(pk)
+        L.Free(vk)
+
+
 class Groth16Context:
     """One (pk, r1cs) pair resident on one GPU — or, with `devices=[...]`, on every GPU of the list (g16_init_multi):
     batches are then sharded request i -> devices[i mod G], proved concurrently and gathered in input order.
@@ -308,6 +328,11 @@ class Groth16Context:
         out["sub_batch"] = int(c[7]) & 0xFFFFFFFF
         out["pipelined"] = bool((int(c[7]) >> 32) & 1)
         out["eval_basis_z"] = bool((int(c[7]) >> 33) & 1)   # Z query over the evaluation-basis tables (4 transforms, no H)
+        e = np.zeros(16, dtype=np.uint64)
+        _check(self._L.g16_last_counters_ex(self._h, _p64(e)))
+        out["z_sorted_slots"] = int(e[8])     # Z-query entries + batch-affine padding
+        out["z_batch_affine_levels"] = int(e[9])
+        out["z_buckets"] = int(e[10])
         return out
 
     # ---- stage-level

@@ -121,6 +121,10 @@ int g16_last_stage_ms(const g16_ctx* ctx, float ms[8]);
  * 6 the part of [0] that belongs to the Z query (what the stage timers of the pipeline = 0 schedule bracket),
  * 7 sub-batch size | (1 << 32 if the pipelined schedule ran) | (1 << 33 if the Z query ran over the evaluation basis) */
 int g16_last_counters(const g16_ctx* ctx, uint64_t out[8]);
+/* the same eight, then (device 0 of a multi-device handle): 8 sorted slots of the Z query = [6] plus the null slots that pad
+ * every bucket's run to a multiple of 2^K for the batch-affine levels, 9 K = number of batch-affine levels the Z query ran
+ * (0: XYZZ accumulation only), 10 bucket sets x buckets of the Z query, 11..15 reserved */
+int g16_last_counters_ex(const g16_ctx* ctx, uint64_t out[16]);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * stage-level entry points (parity tests against the oracle; standalone MSM / NTT sweeps of BASELINE config 5)
@@ -132,6 +136,15 @@ int g16_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64
 int g16_group_op(int group, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 /* decompression of gnark-crypto compressed points (32 / 64 bytes each) -> affine Montgomery */
 int g16_decompress(int group, const uint8_t* in, uint64_t* out, size_t n);
+
+/* ---- Setup. Replaces keygen.go:359-435 (groth16.Setup(r1cs) + ProvingKey.WriteTo / VerifyingKey.WriteTo)
+ * for a constraint system in gnark's serialization (r1cs.chacha20 / r1cs.aes128 / r1cs.aes256): the QAP is evaluated at the
+ * trapdoor on the host, every group element of the two keys is a fixed-base product on the GPU, the keys come back in the
+ * layouts InitAlgorithm / InitVerifier read. trapdoor_be = tau | alpha | beta | gamma | delta | sigma (6 x 32-byte big-endian,
+ * reduced, non-zero; sigma is the Pedersen trapdoor of the BSB22 commitment key) or NULL to draw it from the OS CSPRNG as gnark
+ * does. *pk_out / *vk_out are malloc'd: release them with Free. */
+int g16_setup(const uint8_t* r1cs, size_t r1cs_len, const uint8_t* trapdoor_be, int device, uint8_t** pk_out, size_t* pk_len,
+              uint8_t** vk_out, size_t* vk_len);
 
 /* ---- verifier: groth16.Verify for batches of proofs of one verifying key.
  * Replaces gnark v0.11.0 backend/groth16/bn254/verify.go Verify + VerifyingKey.ReadFrom as used by

@@ -94,8 +94,10 @@ AES_RSM = (int("11" * 20, 16), int("22" * 20, 16), int("33" * 20, 16))
 @pytest.fixture(scope="session")
 def emu():
     """TEST-ONLY host-emulation build of the product sources (tests/emu). Never reachable through the package API."""
-    subprocess.check_call(["make", "-C", str(ROOT / "tests" / "emu"), "-j", str(os.cpu_count() or 1), "-s"])
     from gnark_symmetric_crypto_b200 import _lib
+    if os.environ.get("G16_EMU_SO"):   # scripts/emu_sanitize.sh: the ASan / TSan build of the same sources
+        return _lib.bind(ROOT / os.environ["G16_EMU_SO"])
+    subprocess.check_call(["make", "-C", str(ROOT / "tests" / "emu"), "-j", str(os.cpu_count() or 1), "-s"])
     return _lib.bind(ROOT / "tests" / "emu" / "_build" / "libg16emu.so")
 
 
