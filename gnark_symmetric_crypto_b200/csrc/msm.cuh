@@ -95,6 +95,132 @@ static __global__ void msm_digits_kernel(MsmShape sh, const Fr* __restrict__ sca
     }
 }
 
+// ------------------------------------------------------------------------------------------------ per-row sort in shared memory
+// The same counting sort for batches whose rows share one bucket set (fixed-base tables) of at most 2^14 buckets: ONE block
+// per row keeps the row's histogram / write cursors in shared memory, so the two passes cost shared-memory atomics instead of
+// one L2 atomic per entry (the global version is bound by the L2's atomic throughput: 285 M RED + 285 M ATOM per 512-proof Z
+// query). Pass 0 leaves the row's counts in hist_g and its slot / entry totals in row_tot; a one-block scan turns the row
+// totals into row bases; pass 1 rebuilds the cursors from hist_g (padded counts for the batch-affine path) and scatters.
+// The order of the entries inside a bucket differs from the global version; bucket SUMS do not depend on it.
+// MEASURED ON B200 AND NOT THE DEFAULT (G16_MSM_ROWSORT=1 enables it): shared-memory atomics on random buckets are no faster in
+// aggregate than the L2's (148 SMs x one returning ATOMS per ~4 cycles = 72 G/s against 95 G/s measured for the L2 path), and
+// 512 blocks of 1024 threads leave a ragged second wave: sort stage 28.0 vs 13.7 ms per 1024 proofs (round 1 had found the
+// same with a different kernel). Kept because it is exercised by the tests and documents the dead end.
+static const int ROWSORT_T = 1024;
+template <int PASS>
+static __global__ void __launch_bounds__(ROWSORT_T)
+msm_rowsort_kernel(MsmShape sh, const Fr* __restrict__ scalars, size_t row_stride, size_t elem_stride, const uint32_t* __restrict__ map,
+                   int is_mont, uint32_t pad_mask, uint32_t* __restrict__ hist_g, uint32_t* __restrict__ row_tot,
+                   const uint32_t* __restrict__ row_base, uint2* __restrict__ entries, uint32_t* __restrict__ refs, int ba_shift) {
+#if defined(G16_EMU)
+    uint32_t* h = reinterpret_cast<uint32_t*>(cuemu::g_dyn_smem);
+#else
+    extern __shared__ uint32_t h[];
+#endif
+    __shared__ uint32_t part[ROWSORT_T];
+    __shared__ uint32_t part2[ROWSORT_T];
+    const uint32_t row = blockIdx.x, t = threadIdx.x, nbk = (uint32_t)sh.nbk;
+    const uint32_t ipt = (nbk + ROWSORT_T - 1) / ROWSORT_T;   // buckets per thread in the scans
+    const uint32_t b0 = t * ipt < nbk ? t * ipt : nbk, b1 = b0 + ipt < nbk ? b0 + ipt : nbk;
+    uint32_t* hg = hist_g + (size_t)row * nbk;
+    if (PASS == 0) {
+        for (uint32_t b = t; b < nbk; b += ROWSORT_T) h[b] = 0;
+    } else {
+        uint32_t s = 0;
+        for (uint32_t b = b0; b < b1; b++) s += (hg[b] + pad_mask) & ~pad_mask;
+        part[t] = s;
+        __syncthreads();
+        for (int off = 1; off < ROWSORT_T; off <<= 1) {   // Hillis-Steele inclusive scan of the per-thread sums
+            uint32_t add = (int)t >= off ? part[t - off] : 0;
+            __syncthreads();
+            part[t] += add;
+            __syncthreads();
+        }
+        uint32_t run = row_base[row] + part[t] - s;
+        for (uint32_t b = b0; b < b1; b++) {
+            h[b] = run;
+            run += (hg[b] + pad_mask) & ~pad_mask;
+        }
+    }
+    __syncthreads();
+    const uint32_t gb = row * nbk;   // first global bucket id of the row
+    for (uint32_t i = t; i < sh.n; i += ROWSORT_T) {
+        const size_t sidx = (size_t)row * row_stride + (size_t)(map ? map[i] : i) * elem_stride;
+        Fr raw = scalars[sidx];
+        if (raw.is_zero()) continue;
+        Recoded r = recode_load(scalars, sidx, is_mont);
+        int carry = 0;
+        for (int w = 0; w < sh.nwin; w++) {
+            int d = recode_digit(r, w, sh.c, carry);
+            if (d == 0) continue;
+            const uint32_t neg = r.neg ^ (d < 0 ? 1u : 0u);
+            const uint32_t lb = (uint32_t)(d < 0 ? -d : d) - 1u;
+            if (PASS == 0) {
+                atomicAdd(&h[lb], 1u);
+            } else {
+                const uint32_t pos = atomicAdd(&h[lb], 1u);
+                const uint32_t ref = (uint32_t)w * sh.n + i;
+                if (!refs) {
+                    entries[pos] = make_uint2(gb + lb, (ref << 1) | neg);
+                } else {
+                    refs[pos] = (ref << 1) | neg;
+                    if ((pos & ((1u << ba_shift) - 1u)) == 0) entries[pos >> ba_shift] = make_uint2(gb + lb, (pos >> ba_shift) << 1);
+                }
+            }
+        }
+    }
+    if (PASS == 0) {
+        __syncthreads();
+        uint32_t sp = 0, sr = 0;
+        for (uint32_t b = b0; b < b1; b++) { uint32_t v = h[b]; hg[b] = v; sr += v; sp += (v + pad_mask) & ~pad_mask; }
+        part[t] = sp;
+        part2[t] = sr;
+        __syncthreads();
+        for (int off = ROWSORT_T / 2; off > 0; off >>= 1) {
+            if ((int)t < off) { part[t] += part[t + off]; part2[t] += part2[t + off]; }
+            __syncthreads();
+        }
+        if (t == 0) { row_tot[2 * row] = part[0]; row_tot[2 * row + 1] = part2[0]; }
+    }
+}
+// one block: row_base = exclusive scan of the rows' slot totals; total[0] = slots, total[1] = entries, total[2] = slots >> ba_shift
+static __global__ void __launch_bounds__(ROWSORT_T)
+msm_rowscan_kernel(const uint32_t* __restrict__ row_tot, uint32_t rows, uint32_t* __restrict__ row_base, uint32_t* __restrict__ total,
+                   int ba_shift) {
+    __shared__ uint32_t sm[ROWSORT_T];
+    __shared__ uint32_t sr[ROWSORT_T];
+    __shared__ uint32_t carry;
+    const uint32_t t = threadIdx.x;
+    if (t == 0) carry = 0;
+    uint32_t raw = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < rows; base += ROWSORT_T) {
+        const uint32_t idx = base + t;
+        const uint32_t v = idx < rows ? row_tot[2 * idx] : 0;
+        raw += idx < rows ? row_tot[2 * idx + 1] : 0;
+        sm[t] = v;
+        __syncthreads();
+        for (int off = 1; off < ROWSORT_T; off <<= 1) {
+            uint32_t add = (int)t >= off ? sm[t - off] : 0;
+            __syncthreads();
+            sm[t] += add;
+            __syncthreads();
+        }
+        const uint32_t c0 = carry, incl = sm[t];
+        if (idx < rows) row_base[idx] = c0 + incl - v;
+        __syncthreads();
+        if (t == ROWSORT_T - 1) carry = c0 + incl;
+        __syncthreads();
+    }
+    sr[t] = raw;
+    __syncthreads();
+    for (int off = ROWSORT_T / 2; off > 0; off >>= 1) {
+        if ((int)t < off) sr[t] += sr[t + off];
+        __syncthreads();
+    }
+    if (t == 0) { total[0] = carry; total[1] = sr[0]; total[2] = carry >> ba_shift; }
+}
+
 // ------------------------------------------------------------------------------------------------ exclusive scan (u32)
 // three-kernel scan: tile sums -> scan of tile sums (single block) -> rescan tiles. Tile = 256 threads x 8 items.
 #define SCAN_T 256
@@ -464,7 +590,7 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     const size_t ntiles = (nbuckets + SCAN_T * SCAN_I - 1) / (SCAN_T * SCAN_I);
 
     ws.counts.ensure(nbuckets);
-    ws.tile_sums.ensure(2 * ntiles);   // padded tile sums, then the raw ones
+    ws.tile_sums.ensure(2 * ntiles + 3 * (size_t)sh.rows);   // padded tile sums, then the raw ones (or the per-row totals / bases)
     ws.total.ensure(8);
     ws.entries.ensure(acc_entries);
     ws.buckets.ensure(nbuckets);
@@ -482,20 +608,48 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     ws.result.ensure(sh.rows);
 
     if (tm) tm->mark(ST_MSM_SORT, stream);
-    G16_CUDA(cudaMemsetAsync(ws.counts.p, 0, nbuckets * sizeof(uint32_t), stream));
     G16_CUDA(cudaMemsetAsync(ws.buckets.p, 0, nbuckets * sizeof(X), stream));
     const size_t nthreads = (size_t)sh.n * sh.rows;
-    G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, elem_stride, map, is_mont, 0,
-               ws.counts.p, ws.entries.p);
-    uint32_t* raw_sums = ws.tile_sums.p + ntiles;
-    G16_LAUNCH(scan_tile_sums, (unsigned)ntiles, SCAN_T, 0, stream, true, ws.counts.p, nbuckets, ws.tile_sums.p, pad_mask, raw_sums);
-    G16_LAUNCH(scan_of_sums, 1, SCAN_T, 0, stream, true, ws.tile_sums.p, ntiles, ws.total.p, (const uint32_t*)raw_sums, K);
-    G16_LAUNCH(scan_tiles, (unsigned)ntiles, SCAN_T, 0, stream, true, ws.counts.p, nbuckets, ws.tile_sums.p, ws.counts.p, pad_mask);
+    // per-row sort in shared memory: batches over fixed-base tables with <= 2^14 buckets per row (G16_MSM_ROWSORT: 0 (default)
+    // never, 1 from 32 rows on, 2 whenever the shape allows — the switch the small-case tests use)
+    static const int rowsort_mode = [] { const char* v = getenv("G16_MSM_ROWSORT"); return v && *v ? atoi(v) : 0; }();
+    const size_t rowsort_smem = (size_t)sh.nbk * sizeof(uint32_t);
+    const bool rowsort = sh.precomp && rowsort_smem <= 65536 && rowsort_mode > 0 && (rowsort_mode > 1 || sh.rows >= 32);
+    uint32_t* row_tot = ws.tile_sums.p;                  // 2 words per row
+    uint32_t* row_base = ws.tile_sums.p + 2 * (size_t)sh.rows;
+    if (rowsort) {
+        ws.tile_sums.ensure(3 * (size_t)sh.rows + 2 * ntiles);
+        row_tot = ws.tile_sums.p;
+        row_base = ws.tile_sums.p + 2 * (size_t)sh.rows;
+#if !defined(G16_EMU)
+        static bool attr_done = false;   // > 48 KB of dynamic shared memory needs the opt-in (once per process and kernel)
+        if (!attr_done) {
+            G16_CUDA(cudaFuncSetAttribute(msm_rowsort_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+            G16_CUDA(cudaFuncSetAttribute(msm_rowsort_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+            attr_done = true;
+        }
+#endif
+        G16_LAUNCH(msm_rowsort_kernel<0>, sh.rows, ROWSORT_T, rowsort_smem, stream, true, sh, scalars, row_stride, elem_stride, map, is_mont, pad_mask,
+                   ws.counts.p, row_tot, (const uint32_t*)row_base, ws.entries.p, (uint32_t*)nullptr, K);
+        G16_LAUNCH(msm_rowscan_kernel, 1, ROWSORT_T, 0, stream, true, (const uint32_t*)row_tot, sh.rows, row_base, ws.total.p, K);
+    } else {
+        G16_CUDA(cudaMemsetAsync(ws.counts.p, 0, nbuckets * sizeof(uint32_t), stream));
+        G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, elem_stride, map, is_mont, 0,
+                   ws.counts.p, ws.entries.p);
+        uint32_t* raw_sums = ws.tile_sums.p + ntiles;
+        G16_LAUNCH(scan_tile_sums, (unsigned)ntiles, SCAN_T, 0, stream, true, ws.counts.p, nbuckets, ws.tile_sums.p, pad_mask, raw_sums);
+        G16_LAUNCH(scan_of_sums, 1, SCAN_T, 0, stream, true, ws.tile_sums.p, ntiles, ws.total.p, (const uint32_t*)raw_sums, K);
+        G16_LAUNCH(scan_tiles, (unsigned)ntiles, SCAN_T, 0, stream, true, ws.counts.p, nbuckets, ws.tile_sums.p, ws.counts.p, pad_mask);
+    }
     // the XYZZ accumulation (and the merge levels after it) walk ws.entries with the live length at `acc_total`
     const uint32_t* acc_total = ws.total.p + (K ? 2 : 0);
     if (!K) {
-        G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, elem_stride, map, is_mont, 1,
-                   ws.counts.p, ws.entries.p);
+        if (rowsort)
+            G16_LAUNCH(msm_rowsort_kernel<1>, sh.rows, ROWSORT_T, rowsort_smem, stream, true, sh, scalars, row_stride, elem_stride, map, is_mont, pad_mask,
+                       ws.counts.p, row_tot, (const uint32_t*)row_base, ws.entries.p, (uint32_t*)nullptr, 0);
+        else
+            G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, elem_stride, map, is_mont, 1,
+                       ws.counts.p, ws.entries.p);
         G16_CHECK_LAUNCH();
         if (tm) tm->mark(ST_MSM_ACC, stream);
         auto k = msm_accumulate_kernel<C>;
@@ -504,8 +658,12 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
         ws.launches += 6;
     } else {
         G16_CUDA(cudaMemsetAsync(ws.ba_refs.p, 0xFF, max_slots * sizeof(uint32_t), stream));   // padding slots stay null references
-        G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, elem_stride, map, is_mont, 2,
-                   ws.counts.p, ws.entries.p, ws.ba_refs.p, K);
+        if (rowsort)
+            G16_LAUNCH(msm_rowsort_kernel<1>, sh.rows, ROWSORT_T, rowsort_smem, stream, true, sh, scalars, row_stride, elem_stride, map, is_mont, pad_mask,
+                       ws.counts.p, row_tot, (const uint32_t*)row_base, ws.entries.p, ws.ba_refs.p, K);
+        else
+            G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, elem_stride, map, is_mont, 2,
+                       ws.counts.p, ws.entries.p, ws.ba_refs.p, K);
         G16_CHECK_LAUNCH();
         if (tm) tm->mark(ST_MSM_ACC, stream);
         if (getenv("G16_MSM_BA_TRACE")) fprintf(stderr, "[msm] batch-affine K=%d rows=%u n=%u c=%d max_slots=%zu\n", K, sh.rows, sh.n, sh.c, max_slots);

@@ -91,6 +91,26 @@ def test_msm_g1(emu, oracle, n, c):
     assert np.array_equal(out, ref)
 
 
+def test_msm_fixed_base_plan(emu, oracle):
+    """Fixed-base mode (tables 2^(cw) P_i, one bucket set): the shape the prover's pk queries use. Run by
+    tests/test_emu_variants.py once more with the per-row shared-memory sort and the batch-affine levels forced on."""
+    rng = np.random.default_rng(31)
+    n = 400
+    pts = oracle.g1_fixed_base(oracle.rand_field(rng, 1, n)); pts[7] = 0; pts[9] = pts[8]
+    for window in (6, 9):
+        h = C.c_void_p()
+        ok(emu, emu.g16_msm_plan_create(1, p64(pts), n, window, 0, C.byref(h)))
+        ok(emu, emu.g16_msm_plan_precompute(h, window))
+        for rep in range(2):
+            sc = oracle.rand_field(rng, 1, n); sc[3] = 0; sc[8] = sc[9]
+            sc[20:90] = oracle.ints_to_limbs([1] * 70); sc[90:120] = oracle.ints_to_limbs([oracle.R_MOD - 1] * 30)
+            ok(emu, emu.g16_msm_plan_set_scalars(h, p64(sc), 0))
+            out = np.empty(8, dtype=np.uint64)
+            ok(emu, emu.g16_msm_plan_run(h, p64(out), None))
+            assert np.array_equal(out, oracle.g1_msm(pts, sc)), (window, rep)
+        emu.g16_msm_plan_free(h)
+
+
 def test_msm_edge_cases(emu, oracle):
     rng = np.random.default_rng(2)
     pts = oracle.g1_fixed_base(oracle.rand_field(rng, 1, 50))

@@ -245,19 +245,27 @@ def test_verifier_rejects_noncanonical_coordinates(G, oracle, kat):
     ver.close()
 
 
-# ---------------------------------------------------------------------------------------------- batch-affine accumulation
-@pytest.mark.parametrize("k", [1, 2, 3])
-def test_batch_affine_levels_forced_on_small_and_edge_cases(k):
+# ---------------------------------------------------------------------------------------------- batch-affine accumulation, row sort
+@pytest.mark.parametrize("env", [
+    {"G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "1"},
+    {"G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "2"},
+    {"G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "3"},
+    {"G16_MSM_ROWSORT": "2"},
+    {"G16_MSM_ROWSORT": "2", "G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "3"},
+    {"G16_MSM_ROWSORT": "0", "G16_MSM_BA": "0"},
+], ids=["batch_affine_k1", "batch_affine_k2", "batch_affine_k3", "rowsort", "rowsort_batch_affine_k3", "round1_paths"])
+def test_msm_paths_forced_on_small_and_edge_cases(env):
     """The batch-affine pairwise levels (csrc/msm_ba.cuh; gnark's own bucket-addition algorithm, multiexp_affine.go:35-176)
-    normally start at 2^21 entries. Here they are forced (G16_MSM_BA_MIN=1, K = 1, 2, 3) onto the existing small MSM parity
-    tests — sizes 1 to 2^16 against the oracle, zeros, +-1 runs, duplicate points (the doubling branch), P + (-P), points at
-    infinity, fixed-base tables — in a child process (the switches are read once per process)."""
+    normally start at 2^21 entries and the per-row shared-memory sort at 32 rows. Here they are forced onto the existing small
+    MSM parity tests — sizes 1 to 2^16 against the oracle, zeros, +-1 runs, duplicate points (the doubling branch), P + (-P),
+    points at infinity, fixed-base tables, the KAT proof and a 37-request batch — in a child process (the switches are read
+    once per process). The last variant switches both off: the round-1 paths stay correct."""
     import subprocess
     import sys
-    env = dict(os.environ, G16_MSM_BA_MIN="1", G16_MSM_BA_K=str(k))
-    out = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu.py", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
-                          "-k", "test_msm_g1 or test_msm_g2_and_edges or test_msm_plan_with_precomputed_tables or test_kat_proof"],
-                         capture_output=True, text=True, env=env, timeout=1200)
+    out = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu.py", "tests/test_gpu_round2.py", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                          "-k", "test_msm_g1 or test_msm_g2_and_edges or test_msm_plan_with_precomputed_tables or test_kat_proof "
+                                "or test_multi_device_handle"],
+                         capture_output=True, text=True, env=dict(os.environ, **env), timeout=1200)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert " passed" in out.stdout
 
