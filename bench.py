@@ -264,6 +264,9 @@ def run_gpu(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+        # host-side barrier (gloo) for the section in which rank 0 alone drives every GPU from one process: a rank waiting in an
+        # NCCL barrier keeps a spinning kernel on its GPU, and two processes on one GPU time-slice
+        cpu_group = dist.new_group(backend="gloo")
 
     def barrier():
         if dist is not None:
@@ -378,22 +381,27 @@ def run_gpu(args):
             off += 4 + 32 * cnt
         nz = struct.unpack(">I", pk[off:off + 4])[0]
         zpts = G.decompress(1, pk[off + 4:off + 4 + 32 * nz])
-        lg = 22
-        nn = 1 << lg
+        # config-5 sweep: 2^16, 2^20 and 2^22 points (the 2^24 point is the split MSM below); the headline pair is 2^22
+        msm_line = {"sizes": []}
         rng = np.random.default_rng(5)
-        pts = zpts[rng.integers(0, nz, nn)]
-        sc = rng.integers(0, 1 << 63, size=(nn, 4), dtype=np.int64).astype(np.uint64)
-        sc[:, 3] &= np.uint64((1 << 60) - 1)                # < r
-        adds = min(((254 + cc - 1) // cc) * (nn + (1 << cc)) for cc in range(4, 25))   # SURVEY 8d adds_alg(N)
-        msm_line = {"log2n": lg, "adds_alg": adds}
-        for mode in ("one_shot", "fixed_base"):
-            plan = G.MsmPlan(1, pts, precompute=(mode == "fixed_base"), device=local)
-            plan.set_scalars(sc)
-            plan.run()
-            best = min(float(plan.run()[1][0]) for _ in range(3))
-            plan.close()
-            msm_line[mode] = {"ms": best, "Gpts_per_s": nn / best / 1e6,
-                              "frac_of_imad_peak": adds * IMAD_PER_MADD_G1 / (best / 1e3) / imad["imad_per_s"]}
+        for lg in (16, 20, 22):
+            nn = 1 << lg
+            pts = zpts[rng.integers(0, nz, nn)]
+            sc = rng.integers(0, 1 << 63, size=(nn, 4), dtype=np.int64).astype(np.uint64)
+            sc[:, 3] &= np.uint64((1 << 60) - 1)                # < r
+            adds = min(((254 + cc - 1) // cc) * (nn + (1 << cc)) for cc in range(4, 25))   # SURVEY 8d adds_alg(N)
+            rec = {"log2n": lg, "adds_alg": adds}
+            for mode in ("one_shot", "fixed_base"):
+                plan = G.MsmPlan(1, pts, precompute=(mode == "fixed_base"), device=local)
+                plan.set_scalars(sc)
+                plan.run()
+                best = min(float(plan.run()[1][0]) for _ in range(3))
+                plan.close()
+                rec[mode] = {"ms": best, "Gpts_per_s": nn / best / 1e6,
+                             "frac_of_imad_peak": adds * IMAD_PER_MADD_G1 / (best / 1e3) / imad["imad_per_s"]}
+            msm_line["sizes"].append(rec)
+            if lg == 22:
+                msm_line.update(rec)
         del pts, sc
     barrier()
 
@@ -519,10 +527,12 @@ def run_gpu(args):
             m_ms = (time.perf_counter() - t0) * 1e3
             # request i of the N x 1024 stream with i < 1024 is request i of the headline batch: same proof bytes
             assert np.array_equal(mproofs.reshape(mn, -1)[:n], ref_proofs.reshape(n, -1)), "multi-device handle disagrees with the single-device batch"
+            torch.cuda.synchronize(dev)
             lib_multi = {"devices": world, "requests_per_call": mn, "value": mn * args.steps / (m_ms / 1e3), "unit": UNIT,
                          "ms_per_call": m_ms / args.steps,
                          "path": "one process: g16_init_multi + g16_prove_chacha_batch (host buffers in, proofs out; request i -> device i mod N, one host thread per device)"}
             mctx.close()
+        dist.barrier(group=cpu_group)   # the other ranks wait here on the CPU, their GPUs idle
         barrier()
 
     # ---------------- single-request latency (BASELINE config 1: what one libprove Prove call costs), rank 0 only

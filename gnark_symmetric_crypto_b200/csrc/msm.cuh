@@ -489,6 +489,72 @@ msm_tree_kernel(const typename C::X* __restrict__ in_R, const typename C::X* __r
     out_R[gid] = run;
     out_V[gid] = tot;
 }
+// The same node for SMALL problems (a single request, a standalone MSM of <= 2^18 points), where the time is the depth of the
+// dependency chain and not the work: ONE BLOCK computes one node of up to TB children in logarithmic depth — a suffix scan of the
+// children's R in shared memory (S_k = sum_{j >= k} R_j, log2 TB steps), then a tree sum of the S_k (sum_k S_k = sum_k (k+1) R_k,
+// the weights 1..g of a level-1 node; without S_0 the weights 0..g-1 of an upper node) — instead of one thread walking 2 g
+// dependent additions. 16384 buckets: 2 launches, ~45 dependent additions, against 6 launches and ~70 for arity 4.
+template <class C, int LEVEL1, int TB>
+__global__ void __launch_bounds__(TB)
+msm_tree_block_kernel(const typename C::X* __restrict__ in_R, const typename C::X* __restrict__ in_V, uint32_t n_in, uint32_t n_out,
+                      int log_span_child, typename C::X* __restrict__ out_R, typename C::X* __restrict__ out_V) {
+    typedef typename C::X X;
+#if defined(G16_EMU)
+    X* sm = reinterpret_cast<X*>(cuemu::g_dyn_smem);
+#else
+    extern __shared__ uint4 sm_raw[];
+    X* sm = reinterpret_cast<X*>(sm_raw);
+#endif
+    const uint32_t t = threadIdx.x;
+    const uint32_t seg = blockIdx.x / n_out, node = blockIdx.x % n_out;
+    const uint32_t lo = node * TB;
+    const uint32_t g = lo + TB < n_in ? TB : n_in - lo;   // children [lo, lo + g)
+    const X* R = in_R + (size_t)seg * n_in + lo;
+    X v = t < g ? R[t] : X::inf();
+    sm[t] = v;
+    __syncthreads();
+    for (uint32_t d = 1; d < TB; d <<= 1) {   // suffix scan
+        X o = t + d < TB ? sm[t + d] : X::inf();
+        __syncthreads();
+        v.add(o);
+        sm[t] = v;
+        __syncthreads();
+    }
+    const X run = sm[0];                      // sum of all children
+    __syncthreads();
+    if (!LEVEL1 && t == 0) sm[0] = X::inf();  // upper levels: child k has weight k, so S_0 does not count
+    __syncthreads();
+    for (uint32_t s2 = TB / 2; s2 >= 1; s2 >>= 1) {   // tree sum of the suffix sums
+        X a;
+        if (t < s2) { a = sm[t]; a.add(sm[t + s2]); }
+        __syncthreads();
+        if (t < s2) sm[t] = a;
+        __syncthreads();
+    }
+    X tot = sm[0];
+    if (!LEVEL1) {
+        __syncthreads();
+        const X* V = in_V + (size_t)seg * n_in + lo;
+        sm[t] = t < g ? V[t] : X::inf();      // plus the children's own weighted sums
+        __syncthreads();
+        for (uint32_t s2 = TB / 2; s2 >= 1; s2 >>= 1) {
+            X a;
+            if (t < s2) { a = sm[t]; a.add(sm[t + s2]); }
+            __syncthreads();
+            if (t < s2) sm[t] = a;
+            __syncthreads();
+        }
+        if (t == 0) {
+            for (int d = 0; d < log_span_child; d++) tot = tot.dbl();
+            tot.add(sm[0]);
+        }
+    }
+    if (t == 0) {
+        out_R[blockIdx.x] = run;
+        out_V[blockIdx.x] = tot;
+    }
+}
+
 template <class C, int LOG_G>
 static void msm_tree_launch(bool level1, size_t nodes, cudaStream_t stream, const typename C::X* inR, const typename C::X* inV,
                             uint32_t n_in, uint32_t n_out, uint32_t segs, int log_span, typename C::X* outR, typename C::X* outV) {
@@ -538,6 +604,10 @@ __global__ void msm_precompute_kernel(const typename C::A* __restrict__ pts, uin
         table[(size_t)w * n + i] = acc.to_affine();
     }
 }
+
+// arity of the block-parallel tree node: 256 children for G1 (32 KB of shared memory), 128 for G2 (32 KB)
+template <class C> struct MsmTreeBlock { static const int LOG_TB = 8, TB = 256; };
+template <> struct MsmTreeBlock<G2> { static const int LOG_TB = 7, TB = 128; };
 
 // the batch-affine levels exist for G1 only (k_msm_ba.cu)
 template <class C> constexpr bool msm_ba_available() { return std::is_same<C, G1>::value; }
@@ -714,16 +784,39 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     // 3.8 -> 2.7 ms); a batch keeps arity 32 below a wide first level (measured: 16.6 vs 17.4 ms per 1024 proofs).
     const bool tree_dynamic = sh.rows == 1;
     int log_g = ((size_t)segs * ((n_in + MSM_TREE_G - 1) / MSM_TREE_G) < (size_t)148 * 256) ? MSM_TREE_LOG_G_SMALL : MSM_TREE_LOG_G;
+    // small problems: block-parallel nodes of arity MSM_TREE_TB (log-depth) instead of thread-serial nodes of arity 4
+    static const int tree_block = [] { const char* v = getenv("G16_MSM_TREE_BLOCK"); return v && *v ? atoi(v) : 1; }();
+    const bool use_block = tree_block && log_g == MSM_TREE_LOG_G_SMALL;
+    const int TBK = MsmTreeBlock<C>::TB;
     const X* inR = ws.buckets.p;
     const X* inV = nullptr;
     int level = 1, log_span = 0, pp = 0;
     while (true) {
         if (tree_dynamic)   // re-decide per level: the upper levels of a wide tree are small problems too
             log_g = ((size_t)segs * ((n_in + MSM_TREE_G - 1) / MSM_TREE_G) < (size_t)148 * 256) ? MSM_TREE_LOG_G_SMALL : MSM_TREE_LOG_G;
+        const bool block_level = (use_block || (tree_dynamic && tree_block)) && log_g == MSM_TREE_LOG_G_SMALL;
+        if (block_level) log_g = MsmTreeBlock<C>::LOG_TB;
         uint32_t n_out = (n_in + (1u << log_g) - 1) >> log_g;
         ws.lvlR[pp].ensure((size_t)segs * n_out);
         ws.lvlV[pp].ensure((size_t)segs * n_out);
-        if (log_g == MSM_TREE_LOG_G)
+        if (block_level) {
+            const size_t smem = (size_t)TBK * sizeof(X);
+#if !defined(G16_EMU)
+            static bool attr_done = false;
+            if (!attr_done && smem > 48 * 1024) {
+                G16_CUDA(cudaFuncSetAttribute(msm_tree_block_kernel<C, 1, MsmTreeBlock<C>::TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                G16_CUDA(cudaFuncSetAttribute(msm_tree_block_kernel<C, 0, MsmTreeBlock<C>::TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_done = true;
+            }
+#endif
+            if (level == 1) {
+                auto k = msm_tree_block_kernel<C, 1, MsmTreeBlock<C>::TB>;
+                G16_LAUNCH(k, segs * n_out, TBK, smem, stream, true, inR, inV, n_in, n_out, log_span, ws.lvlR[pp].p, ws.lvlV[pp].p);
+            } else {
+                auto k = msm_tree_block_kernel<C, 0, MsmTreeBlock<C>::TB>;
+                G16_LAUNCH(k, segs * n_out, TBK, smem, stream, true, inR, inV, n_in, n_out, log_span, ws.lvlR[pp].p, ws.lvlV[pp].p);
+            }
+        } else if (log_g == MSM_TREE_LOG_G)
             msm_tree_launch<C, MSM_TREE_LOG_G>(level == 1, (size_t)segs * n_out, stream, inR, inV, n_in, n_out, segs, log_span,
                                                ws.lvlR[pp].p, ws.lvlV[pp].p);
         else
