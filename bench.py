@@ -549,6 +549,44 @@ def run_gpu(args):
                   "path": "g16_prove_chacha_batch, n = 1, host buffers in, proof bytes out (wall clock)"}
     barrier()
 
+    # ---------------- BASELINE configs 2 and 3: the AES-128 / AES-256 V2 circuits (lookup tables, BSB22 commitment, domain 2^17).
+    # The reference ships no pk.aes*, so the key pair comes from the library's own Setup (g16_setup: gnark's groth16.Setup on the
+    # GPU, fresh toxic waste); every proof of the timed batch is checked by the GPU verifier under the matching vk. Rank 0 only.
+    aes_line = None
+    if rank == 0 and not args.no_aes:
+        aes_line = {"note": "keys from g16_setup on the shipped r1cs.aes128/256 (the reference ships no pk.aes*); UNPINNED against gnark "
+                            "(tools/pin_aes, tests/test_external_pin.py)", "batch": args.aes_batch}
+        nb = args.aes_batch
+        for bits in (128, 256):
+            r1a = (ROOT / "tests" / "golden" / f"r1cs.aes{bits}").read_bytes()
+            t0 = time.perf_counter()
+            pk_a, vk_a = G.Setup(r1a, device=local)
+            setup_s = time.perf_counter() - t0
+            actx = G.Groth16Context(pk_a, r1a, device=local)
+            rng = np.random.default_rng(bits)
+            klen = bits // 8
+            ak = [bytes(rng.integers(0, 256, klen, dtype=np.uint8)) for _ in range(nb)]
+            an = [bytes(rng.integers(0, 256, 12, dtype=np.uint8)) for _ in range(nb)]
+            ac = [int(x) for x in rng.integers(0, 1 << 31, nb)]
+            ai = [bytes(rng.integers(0, 256, 64, dtype=np.uint8)) for _ in range(nb)]
+            actx.prove_aes_batch(ak, an, ac, ai)
+            actx.prove_aes_batch(ak, an, ac, ai)
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                aproofs, acts = actx.prove_aes_batch(ak, an, ac, ai)
+            wall_ms = (time.perf_counter() - t0) * 1e3 / reps
+            ast = actx.stage_ms()
+            aver = G.Groth16Verifier(vk_a, device=local)
+            pubs = [list(an[j]) + [ac[j]] + list(ai[j]) + list(acts[j]) for j in range(nb)]
+            acc = int(aver.verify_batch(aproofs, pubs).sum())
+            assert acc == nb, f"AES-{bits}: {nb - acc} of {nb} proofs rejected by the GPU verifier"
+            aes_line[f"aes{bits}"] = {"value": nb / (wall_ms / 1e3), "unit": UNIT, "ms_per_batch_e2e": wall_ms, "device_ms": ast["total"],
+                                      "stages_ms": {kk: v for kk, v in ast.items() if kk != "launches"}, "verified": acc,
+                                      "setup_s": setup_s, "domain": actx.n, "proof_bytes": actx.proof_bytes}
+            aver.close(); actx.close()
+            del pk_a, vk_a
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -652,6 +690,7 @@ def run_gpu(args):
             "library_multi_gpu": lib_multi,
             "verified": verified,
             "single_request": single,
+            "aes": aes_line,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
@@ -670,6 +709,8 @@ def main():
     ap.add_argument("--no-msm", action="store_true", help="skip the standalone 2^22-point MSM line and the 2^24 point-range split")
     ap.add_argument("--no-strong", action="store_true", help="skip the fixed-total (1024 requests over all GPUs) reading of config 4")
     ap.add_argument("--no-lib-multi", action="store_true", help="skip the one-process multi-GPU library measurement (N > 1 only)")
+    ap.add_argument("--no-aes", action="store_true", help="skip the AES-128 / AES-256 lines (Setup + a 256-proof batch each)")
+    ap.add_argument("--aes-batch", type=int, default=256)
     ap.add_argument("--split-log", type=int, default=24, help="log2 of the point-range-split MSM size")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -30,10 +30,18 @@
 #define FD __host__ __device__ __forceinline__
 // Cold translation units (-DG16_COLD: key loading, proof assembly, G2) keep the 180-instruction Montgomery product out
 // of line so that ptxas finishes in seconds; the hot kernels (G1 bucket accumulation, NTT) inline it.
-#if defined(G16_COLD) && !defined(G16_EMU)
+// The G2 MSM unit (-DG16_COLD_FP2) sits in between: the Fp product is inlined, but the Fp2 product and square that contain it
+// (3 and 2 Fp products) stay out of line — one call per 3 products instead of one per product, and ptxas still only sees a
+// G2 addition as ten calls (the fully inlined Fp2 group law did not finish compiling in 25 minutes).
+#if defined(G16_COLD_FP2) && !defined(G16_EMU)
+#define FD_MUL FD
+#define FD_MUL2 __host__ __device__ __noinline__
+#elif defined(G16_COLD) && !defined(G16_EMU)
 #define FD_MUL __host__ __device__ __noinline__
+#define FD_MUL2 FD
 #else
 #define FD_MUL FD
+#define FD_MUL2 FD
 #endif
 
 namespace g16 {
@@ -161,6 +169,76 @@ FD void mad4_shift(uint32_t t[8], uint32_t& lo0, const uint32_t e[8], uint32_t x
 #endif
 }
 
+// ---- variants for the dedicated squaring (Fe::sqr): the multiplicand of round i has no limbs below i, so the first K of the
+// four 64-bit slots of a block hold no product. For the chain without carry-in (mad4) the skipped slots vanish; for the
+// shifted chain (mad4_shift) they only pass the carry along (two ALU additions instead of two multiplier operations).
+template <int K>
+FD uint32_t mad4_from(uint32_t acc[8], uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t b) {
+    static_assert(K >= 0 && K <= 4, "K");
+    if (K == 0) return mad4(acc, x0, x1, x2, x3, b);
+    if (K == 4) return 0u;
+#if G16_ASM
+    uint32_t cout;
+    if (K == 1) {
+        asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\tmadc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+            "madc.lo.cc.u32 %2, %8, %10, %2;\n\tmadc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+            "madc.lo.cc.u32 %4, %9, %10, %4;\n\tmadc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+            "addc.u32 %6, 0, 0;"
+            : "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(cout)
+            : "r"(x1), "r"(x2), "r"(x3), "r"(b));
+    } else if (K == 2) {
+        asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\tmadc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+            "madc.lo.cc.u32 %2, %6, %7, %2;\n\tmadc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+            "addc.u32 %4, 0, 0;"
+            : "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(cout)
+            : "r"(x2), "r"(x3), "r"(b));
+    } else {
+        asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+            "addc.u32 %2, 0, 0;"
+            : "+r"(acc[6]), "+r"(acc[7]), "=r"(cout)
+            : "r"(x3), "r"(b));
+    }
+    return cout;
+#else
+    return mad4(acc, K > 0 ? 0u : x0, K > 1 ? 0u : x1, K > 2 ? 0u : x2, K > 3 ? 0u : x3, b);
+#endif
+}
+template <int K>
+FD void mad4_shift_from(uint32_t t[8], uint32_t& lo0, const uint32_t e[8], uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3,
+                        uint32_t b) {
+    static_assert(K >= 0 && K <= 3, "K");
+    if (K == 0) { mad4_shift(t, lo0, e, x0, x1, x2, x3, b); return; }
+#if G16_ASM
+    if (K == 1) {
+        asm("add.cc.u32 %8, %8, %9;\n\t"
+            "addc.cc.u32 %0, %10, 0;\n\taddc.cc.u32 %1, %11, 0;\n\t"
+            "madc.lo.cc.u32 %2, %16, %19, %12;\n\tmadc.hi.cc.u32 %3, %16, %19, %13;\n\t"
+            "madc.lo.cc.u32 %4, %17, %19, %14;\n\tmadc.hi.cc.u32 %5, %17, %19, %15;\n\t"
+            "madc.lo.cc.u32 %6, %18, %19, 0;\n\tmadc.hi.u32 %7, %18, %19, 0;"
+            : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "+r"(lo0)
+            : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(x1), "r"(x2), "r"(x3), "r"(b));
+    } else if (K == 2) {
+        asm("add.cc.u32 %8, %8, %9;\n\t"
+            "addc.cc.u32 %0, %10, 0;\n\taddc.cc.u32 %1, %11, 0;\n\t"
+            "addc.cc.u32 %2, %12, 0;\n\taddc.cc.u32 %3, %13, 0;\n\t"
+            "madc.lo.cc.u32 %4, %16, %18, %14;\n\tmadc.hi.cc.u32 %5, %16, %18, %15;\n\t"
+            "madc.lo.cc.u32 %6, %17, %18, 0;\n\tmadc.hi.u32 %7, %17, %18, 0;"
+            : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "+r"(lo0)
+            : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(x2), "r"(x3), "r"(b));
+    } else {
+        asm("add.cc.u32 %8, %8, %9;\n\t"
+            "addc.cc.u32 %0, %10, 0;\n\taddc.cc.u32 %1, %11, 0;\n\t"
+            "addc.cc.u32 %2, %12, 0;\n\taddc.cc.u32 %3, %13, 0;\n\t"
+            "addc.cc.u32 %4, %14, 0;\n\taddc.cc.u32 %5, %15, 0;\n\t"
+            "madc.lo.cc.u32 %6, %16, %17, 0;\n\tmadc.hi.u32 %7, %16, %17, 0;"
+            : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "+r"(lo0)
+            : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(x3), "r"(b));
+    }
+#else
+    mad4_shift(t, lo0, e, K > 0 ? 0u : x0, K > 1 ? 0u : x1, K > 2 ? 0u : x2, x3, b);
+#endif
+}
+
 // r = a + b (8 limbs), returns carry
 FD uint32_t add8(uint32_t r[8], const uint32_t a[8], const uint32_t b[8]) {
     uint32_t c;
@@ -269,7 +347,58 @@ struct alignas(16) Fe {
         r.reduce_once();
         return r;
     }
+    // Dedicated Montgomery squaring. a^2 = sum_i a_i 2^(32 i) * C_i with C_i = a_i 2^(32 i) + 2 (a div 2^(32 (i+1))) 2^(32 (i+1)):
+    // round i of the interleaved product multiplies a_i by a vector that has no limbs below i — the symmetric partial products
+    // are taken once, doubled — so 36 of the 64 operand products remain (the 64 of the reduction stay): 116 wide multiply-adds
+    // instead of 144. The limbs of C_i: a_i at i, a_(i+1) << 1 at i+1 (its top bit lives in the next limb), the limbs of 2a above.
+    // Same result as a * a (the value is (a^2 + M p) / 2^256 either way), bit for bit; G16_NO_SQR falls back to the product.
+#if defined(G16_NO_SQR)
     FD Fe sqr() const { return *this * *this; }
+#else
+    template <int I>
+    static FD void sqr_round(uint32_t E[8], uint32_t O[8], const uint32_t a[8], const uint32_t e[8], const uint32_t d[8]) {
+        // multiplicand limb j of round I
+#define G16_SQ_C(j) ((j) < I ? 0u : ((j) == I ? a[(j)] : ((j) == I + 1 ? e[(j)] : d[(j)])))
+        uint32_t t[8];
+        mad4_shift_from<I / 2>(t, O[0], E, G16_SQ_C(1), G16_SQ_C(3), G16_SQ_C(5), G16_SQ_C(7), a[I]);
+        t[7] += mad4_from<(I + 1) / 2>(O, G16_SQ_C(0), G16_SQ_C(2), G16_SQ_C(4), G16_SQ_C(6), a[I]);
+#undef G16_SQ_C
+        uint32_t m = O[0] * P::inv();
+        mad4(t, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+        t[7] += mad4(O, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { E[k] = O[k]; O[k] = t[k]; }
+    }
+    FD_MUL Fe sqr() const {
+        uint32_t e[8], d[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            e[j] = l[j] << 1;
+            d[j] = j ? (e[j] | (l[j - 1] >> 31)) : e[j];
+        }
+        uint32_t E[8], O[8];
+        // round 0: C_0 = (a_0, a_1 << 1, limbs 2.. of 2a)
+        mul4(E, l[0], d[2], d[4], d[6], l[0]);
+        mul4(O, e[1], d[3], d[5], d[7], l[0]);
+        uint32_t m = E[0] * P::inv();
+        mad4(O, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+        O[7] += mad4(E, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m);
+        sqr_round<1>(E, O, l, e, d);
+        sqr_round<2>(E, O, l, e, d);
+        sqr_round<3>(E, O, l, e, d);
+        sqr_round<4>(E, O, l, e, d);
+        sqr_round<5>(E, O, l, e, d);
+        sqr_round<6>(E, O, l, e, d);
+        sqr_round<7>(E, O, l, e, d);
+        Fe r;
+        uint32_t sh[8];
+        for (int k = 0; k < 7; k++) sh[k] = E[k + 1];
+        sh[7] = 0;
+        add8(r.l, O, sh);
+        r.reduce_once();
+        return r;
+    }
+#endif
 
     // Montgomery <-> canonical
     FD Fe to_mont() const { return *this * r2(); }
@@ -364,12 +493,12 @@ struct Fp2 {
     FD Fp2 neg() const { return {a0.neg(), a1.neg()}; }
     FD Fp2 dbl() const { return {a0.dbl(), a1.dbl()}; }
     FD Fp2 conj() const { return {a0, a1.neg()}; }
-    friend FD Fp2 operator*(const Fp2& a, const Fp2& b) {   // Karatsuba, 3 Fp products
+    friend FD_MUL2 Fp2 operator*(const Fp2& a, const Fp2& b) {   // Karatsuba, 3 Fp products
         Fp t0 = a.a0 * b.a0, t1 = a.a1 * b.a1;
         Fp t2 = (a.a0 + a.a1) * (b.a0 + b.a1);
         return {t0 - t1, t2 - t0 - t1};
     }
-    FD Fp2 sqr() const {   // (a0+a1)(a0-a1), 2 a0 a1
+    FD_MUL2 Fp2 sqr() const {   // (a0+a1)(a0-a1), 2 a0 a1
         Fp s = a0 + a1, d = a0 - a1, p = a0 * a1;
         return {s * d, p.dbl()};
     }

@@ -86,6 +86,7 @@ struct Ctx {
     size_t launches = 0;
     uint64_t counters[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t sub_batch = 512;
+    bool split_solve = false;          // G16_SPLIT_SOLVE=1: later sub-batches are solved on the side stream (ctx_run_batch)
     bool tables_ready = false;
     SolverGraphCache* solver_graphs = nullptr;
 
@@ -232,6 +233,7 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     cx->eval_z = env_int("G16_EVAL_Z", -1);
     cx->eval_z_min = (uint32_t)env_int("G16_EVAL_Z_MIN", 128);
     if (cx->sub_batch == 0) cx->sub_batch = 1;
+    cx->split_solve = env_int("G16_SPLIT_SOLVE", 0) != 0;
 
     PkFile pk = parse_pk(pk_bytes, pk_len);
     R1csFile cs = parse_r1cs(r1cs_bytes, r1cs_len);
@@ -631,12 +633,29 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     if (!piped) {
         // one main stream with stage timers: solve everything, then per sub-batch H and the Z query; the wire-driven
         // queries run on a side stream and fill the SM slots that the long H / Z kernels leave idle.
-        own += ctx_solve(cx, n, 0, (uint32_t)n, st, cx.ws1b);
+        // G16_SPLIT_SOLVE=1: only the first sub-batch is solved on the main stream; the later ones are solved on the side
+        // stream while the main stream already runs the transforms and the Z query of the one before (the solver is a chain
+        // of ~160 short level kernels: latency, not throughput). MEASURED ON B200 AND NOT THE DEFAULT: the solve interval
+        // shrinks (6.85 -> 4.38 ms per 1024 proofs) but the side stream's wire queries start later and the same SM time is
+        // taken out of the accumulate / reduce intervals instead: 145.6 vs 145.3 ms per step.
+        const bool split_solve = n > cx.sub_batch && cx.split_solve;
+        const uint32_t rows0 = split_solve ? (uint32_t)cx.sub_batch : (uint32_t)n;
+        own += ctx_solve(cx, n, 0, rows0, st, cx.ws1b);
         G16_CUDA(cudaEventRecord(cx.ev_fork, st));
         G16_CUDA(cudaStreamWaitEvent(st2, cx.ev_fork, 0));
+        if (split_solve) {
+            size_t k = 0;
+            for (size_t sb = cx.sub_batch; sb < n; sb += cx.sub_batch, k++) {
+                uint32_t rows = (uint32_t)((n - sb) < cx.sub_batch ? (n - sb) : cx.sub_batch);
+                own += ctx_solve(cx, n, sb, rows, st2, cx.ws1b);
+                if (cx.ev_solved.size() <= k) { cudaEvent_t e; G16_CUDA(cudaEventCreate(&e)); cx.ev_solved.push_back(e); }
+                G16_CUDA(cudaEventRecord(cx.ev_solved[k], st2));
+            }
+        }
         for (size_t sb = 0; sb < n; sb += cx.sub_batch) {
             uint32_t rows = (uint32_t)((n - sb) < cx.sub_batch ? (n - sb) : cx.sub_batch);
             Fr* a = cx.Aev.p + sb * cx.n_dom;
+            if (split_solve && sb > 0) G16_CUDA(cudaStreamWaitEvent(st, cx.ev_solved[sb / cx.sub_batch - 1], 0));
             tm.mark(ST_H, st);
             if (eval_z) {
                 compute_d_run(cx.dom, a, cx.Bev.p + sb * cx.n_dom, cx.n_dom, rows, st);

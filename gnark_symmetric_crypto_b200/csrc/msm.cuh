@@ -29,8 +29,7 @@ struct Recoded {
     uint32_t neg;
 };
 
-FD Recoded recode_load(const Fr* scalars, size_t idx, int is_mont) {
-    Fr v = scalars[idx];
+FD Recoded recode_value(Fr v, int is_mont) {
     if (is_mont) v = v.from_mont();
     // s > (r-1)/2  ->  s = r - s, negate the point
     uint32_t h[8], t[8];
@@ -71,10 +70,22 @@ static __global__ void msm_digits_kernel(MsmShape sh, const Fr* __restrict__ sca
     size_t sidx = (size_t)row * row_stride + (size_t)(map ? map[i] : i) * elem_stride;
     Fr raw = scalars[sidx];
     if (raw.is_zero()) return;
-    Recoded r = recode_load(scalars, sidx, is_mont);
+    // Montgomery +1 / -1 need no conversion: one digit of magnitude 1 in window 0. The wire-driven queries of a bit-level
+    // circuit meet almost nothing else, and their scalars are wire-major (a warp = one wire of 32 proofs), so whole warps take
+    // this path: the from_mont products were most of the time of those launches (14 M threads per query and pass).
+    int unit = 0;
+    if (is_mont) unit = raw == Fr::one() ? 1 : (raw == Fr::modulus_minus(Fr::one()) ? 2 : 0);
+    Recoded r;
+    if (unit) {
+        for (int k = 0; k < 9; k++) r.s[k] = k == 0 ? 1u : 0u;
+        r.neg = unit == 2 ? 1u : 0u;
+    } else {
+        r = recode_value(raw, is_mont);
+    }
+    const int nwin = unit ? 1 : sh.nwin;
     int carry = 0;
     uint32_t base = row * sh.buckets_per_row();
-    for (int w = 0; w < sh.nwin; w++) {
+    for (int w = 0; w < nwin; w++) {
         int d = recode_digit(r, w, sh.c, carry);
         if (d == 0) continue;
         uint32_t neg = r.neg ^ (d < 0 ? 1u : 0u);
@@ -148,7 +159,7 @@ msm_rowsort_kernel(MsmShape sh, const Fr* __restrict__ scalars, size_t row_strid
         const size_t sidx = (size_t)row * row_stride + (size_t)(map ? map[i] : i) * elem_stride;
         Fr raw = scalars[sidx];
         if (raw.is_zero()) continue;
-        Recoded r = recode_load(scalars, sidx, is_mont);
+        Recoded r = recode_value(raw, is_mont);
         int carry = 0;
         for (int w = 0; w < sh.nwin; w++) {
             int d = recode_digit(r, w, sh.c, carry);
@@ -786,6 +797,7 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     int log_g = ((size_t)segs * ((n_in + MSM_TREE_G - 1) / MSM_TREE_G) < (size_t)148 * 256) ? MSM_TREE_LOG_G_SMALL : MSM_TREE_LOG_G;
     // small problems: block-parallel nodes of arity MSM_TREE_TB (log-depth) instead of thread-serial nodes of arity 4
     static const int tree_block = [] { const char* v = getenv("G16_MSM_TREE_BLOCK"); return v && *v ? atoi(v) : 1; }();
+    static const int tree_block_max = [] { const char* v = getenv("G16_MSM_TREE_BLOCK_MAX"); return v && *v ? atoi(v) : 96; }();
     const bool use_block = tree_block && log_g == MSM_TREE_LOG_G_SMALL;
     const int TBK = MsmTreeBlock<C>::TB;
     const X* inR = ws.buckets.p;
@@ -794,9 +806,12 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     while (true) {
         if (tree_dynamic)   // re-decide per level: the upper levels of a wide tree are small problems too
             log_g = ((size_t)segs * ((n_in + MSM_TREE_G - 1) / MSM_TREE_G) < (size_t)148 * 256) ? MSM_TREE_LOG_G_SMALL : MSM_TREE_LOG_G;
-        const bool block_level = (use_block || (tree_dynamic && tree_block)) && log_g == MSM_TREE_LOG_G_SMALL;
-        if (block_level) log_g = MsmTreeBlock<C>::LOG_TB;
-        uint32_t n_out = (n_in + (1u << log_g) - 1) >> log_g;
+        // only while the level is a handful of blocks: a block node does ~4x the additions of a serial one (measured on B200:
+        // 2^20 points, 128+ blocks: reduce 1.65 -> 2.77 ms; a single request, 64 blocks: 1.04 -> 0.64 ms)
+        const bool block_level = (use_block || (tree_dynamic && tree_block)) && log_g == MSM_TREE_LOG_G_SMALL &&
+                                 (size_t)segs * ((n_in + TBK - 1) / TBK) <= (size_t)tree_block_max;
+        const int lg = block_level ? MsmTreeBlock<C>::LOG_TB : log_g;   // arity of THIS level (log_g stays the serial arity)
+        uint32_t n_out = (n_in + (1u << lg) - 1) >> lg;
         ws.lvlR[pp].ensure((size_t)segs * n_out);
         ws.lvlV[pp].ensure((size_t)segs * n_out);
         if (block_level) {
@@ -816,7 +831,7 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
                 auto k = msm_tree_block_kernel<C, 0, MsmTreeBlock<C>::TB>;
                 G16_LAUNCH(k, segs * n_out, TBK, smem, stream, true, inR, inV, n_in, n_out, log_span, ws.lvlR[pp].p, ws.lvlV[pp].p);
             }
-        } else if (log_g == MSM_TREE_LOG_G)
+        } else if (lg == MSM_TREE_LOG_G)
             msm_tree_launch<C, MSM_TREE_LOG_G>(level == 1, (size_t)segs * n_out, stream, inR, inV, n_in, n_out, segs, log_span,
                                                ws.lvlR[pp].p, ws.lvlV[pp].p);
         else
@@ -826,7 +841,7 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
         inR = ws.lvlR[pp].p;
         inV = ws.lvlV[pp].p;
         n_in = n_out;
-        log_span += log_g;
+        log_span += lg;
         level++;
         pp ^= 1;
         if (n_out == 1) break;

@@ -338,6 +338,26 @@ def test_verifier_orchestration(emu, oracle, kat):
     assert emu.g16_verify_init(vk[:-3], len(vk) - 3, 0, C.byref(bad)) == 2   # G16_ERR_PARSE
 
 
+def test_verifier_two_rows_take_a_two_level_bucket_tree(emu, aes128_oracle):
+    """Two AES proofs in one g16_verify_batch: the public-input MSM runs with rows = 2 over 4096 buckets whose contents are byte
+    values (not just bucket 1 as for the ChaCha bit inputs), so the bucket-reduction tree has two levels and every child of the
+    upper node counts. (Found on B200: the block-parallel tree kept its arity of 256 when it computed the size of a following
+    thread-serial level; only batches of >= 2 rows over > 256 buckets were affected.)"""
+    from conftest import aes_keys, AES_KAT, AES_RSM
+    _, vk, _ = aes_keys(128)
+    k = AES_KAT[128]
+    proof, ct, _ = aes128_oracle.prove(k["key"], k["nonce"], k["counter"], k["input"], *AES_RSM, detail=True)
+    vals = list(k["nonce"]) + [k["counter"]] + list(k["input"]) + list(ct)
+    pub = np.frombuffer(b"".join(int(x).to_bytes(32, "big") for x in vals) * 2, dtype=np.uint8).copy()
+    pr = np.frombuffer(bytes(proof) * 2, dtype=np.uint8).copy()
+    h = C.c_void_p()
+    ok(emu, emu.g16_verify_init(vk, len(vk), 0, C.byref(h)))
+    out = np.zeros(2, dtype=np.uint8)
+    ok(emu, emu.g16_verify_batch(h, 2, p8(pr), pub.ctypes.data_as(C.c_void_p), 1, p8(out), None))
+    assert out.tolist() == [1, 1]
+    emu.g16_verify_free(h)
+
+
 def test_libverify_json_layer(emu):
     """libverify.go:14-17 / verify_impl.go:64-82 without a key: every failure is `false`, nothing throws across the ABI."""
     from gnark_symmetric_crypto_b200._lib import GoSlice
