@@ -838,6 +838,55 @@ int g16_msm(int group, const uint64_t* points, const uint64_t* scalars, int scal
     return rc;
 }
 
+// Stage-level view of the combination-table path (k_bitq.cu) for the parity tests: per-witness subset sums of `n` points.
+// wires: [n][rows] Montgomery Fr, wire-major like the prover's witness array (wire i pairs with point i); every value must be
+// 0 or 1, anything else raises *exception_out (the sums are then meaningless, as in the prover, which falls back). out: `rows`
+// affine points. Groups of 8 consecutive points, 255 subset sums each, one table point per group and witness.
+int g16_bitq_sum(int group, const uint64_t* points, size_t n, const uint64_t* wires, size_t rows, uint64_t* out, uint32_t* exception_out) {
+    return guarded([&] {
+        REQUIRE(points && wires && out, "NULL argument");
+        REQUIRE(group == 1 || group == 2, "group must be 1 (G1) or 2 (G2)");
+        REQUIRE(n > 0 && n <= (1u << 22) && rows > 0 && rows <= (1u << 20), "size out of range");
+        require_device();
+        cudaStream_t st = nullptr;
+        const uint32_t groups = (uint32_t)((n + BITQ_K - 1) / BITQ_K);
+        std::vector<uint32_t> ident((size_t)groups * BITQ_K, BITQ_NONE);
+        for (size_t i = 0; i < n; i++) ident[i] = (uint32_t)i;
+        DevBuf<uint32_t> d_ident, d_exc(1);
+        DevBuf<Fr> d_w;
+        DevBuf<uint2> d_entries((size_t)rows * groups);
+        d_ident.upload(ident.data(), ident.size(), st);
+        d_w.upload(reinterpret_cast<const Fr*>(wires), n * rows, st);
+        d_exc.zero(st);
+        bitq_entries(d_w.p, rows, (uint32_t)rows, d_ident.p, groups, d_entries.p, d_exc.p, st);
+        if (group == 1) {
+            DevBuf<G1Affine> pts, table((size_t)groups << BITQ_K), aff(rows);
+            DevBuf<G1XYZZ> sums(rows);
+            MsmWorkspace<G1> ws;
+            pts.upload(reinterpret_cast<const G1Affine*>(points), n, st);
+            bitq_build_g1(pts.p, d_ident.p, groups, table.p, st);
+            msm_sum_rows_g1(ws, table.p, d_entries.p, (uint32_t)(rows * groups), (uint32_t)rows, sums.p, st);
+            xyzz_to_affine_g1(sums.p, (uint32_t)rows, aff.p, st);
+            aff.download(reinterpret_cast<G1Affine*>(out), rows, st);
+            G16_CUDA(cudaStreamSynchronize(st));
+        } else {
+            DevBuf<G2Affine> pts, table((size_t)groups << BITQ_K), aff(rows);
+            DevBuf<G2XYZZ> sums(rows);
+            MsmWorkspace<G2> ws;
+            pts.upload(reinterpret_cast<const G2Affine*>(points), n, st);
+            bitq_build_g2(pts.p, d_ident.p, groups, table.p, st);
+            msm_sum_rows_g2(ws, table.p, d_entries.p, (uint32_t)(rows * groups), (uint32_t)rows, sums.p, st);
+            xyzz_to_affine_g2(sums.p, (uint32_t)rows, aff.p, st);
+            aff.download(reinterpret_cast<G2Affine*>(out), rows, st);
+            G16_CUDA(cudaStreamSynchronize(st));
+        }
+        uint32_t exc = 0;
+        d_exc.download(&exc, 1, st);
+        G16_CUDA(cudaStreamSynchronize(st));
+        if (exception_out) *exception_out = exc;
+    });
+}
+
 // ------------------------------------------------------------------------------------------------ setup
 int g16_setup(const uint8_t* r1cs, size_t r1cs_len, const uint8_t* trapdoor_be, int device, uint8_t** pk_out, size_t* pk_len,
               uint8_t** vk_out, size_t* vk_len) {

@@ -20,6 +20,18 @@ struct PrecompQuery {
     int c = 0;
 };
 
+// Combination-table form of one wire-driven query (k_bitq.cu): the points whose wire is a bit, in groups of 8 with the table of
+// the 255 subset sums of every group, and the remaining points as a general sub-query over gathered window tables.
+struct BitQuery {
+    bool on = false;
+    uint32_t groups = 0;
+    DevBuf<uint32_t> grp_wires;     // 8 wire ids per group (BITQ_NONE pads the last one)
+    DevBuf<G1Affine> table1;        // [groups][256] subset sums on G1
+    DevBuf<G2Affine> table2;        // the same on G2 (B query only)
+    PrecompQuery rest;              // points that are not bits: general path (map = their wires, table = gathered windows)
+    DevBuf<G2Affine> rest_tab2;     // ... their G2 window tables (B query only)
+};
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -89,6 +101,23 @@ struct Ctx {
     bool split_solve = false;          // G16_SPLIT_SOLVE=1: later sub-batches are solved on the side stream (ctx_run_batch)
     bool tables_ready = false;
     SolverGraphCache* solver_graphs = nullptr;
+    // combination tables of the wire-driven queries (A, B1, K, B2). Which wires are bits is learned from the first
+    // bitq_min_rows witnesses (state 0), then the tables are built (state 1) and used for batches >= bitq_min_batch; every
+    // witness is checked against the classification, and an exception sends the batch through the general path again and
+    // switches the tables off for good (state 2). G16_BITQ=0 disables the path.
+    int bitq_state = 0;
+    bool bitq_built = false;
+    size_t bitq_rows_seen = 0;
+    uint32_t bitq_min_rows = 256, bitq_min_batch = 32;
+    std::vector<uint8_t> bit_mask;                 // host: wire -> 1 while every witness seen so far held 0 or 1
+    std::vector<uint32_t> h_mapA, h_mapB, h_mapK;
+    DevBuf<uint8_t> d_bit_flags;
+    DevBuf<uint32_t> d_bitq_exc;
+    DevBuf<uint2> bitq_entries;
+    DevBuf<G1XYZZ> bitq_tmp1;
+    DevBuf<G2XYZZ> bitq_tmp2;
+    BitQuery bqA, bqB, bqK;
+    bool bitq_test_exception = false;              // G16_BITQ_TEST_EXC=1: pretend one exception (tests of the fallback)
 
     ~Ctx() {
         solver_graph_cache_destroy(solver_graphs);
@@ -234,6 +263,10 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     cx->eval_z_min = (uint32_t)env_int("G16_EVAL_Z_MIN", 128);
     if (cx->sub_batch == 0) cx->sub_batch = 1;
     cx->split_solve = env_int("G16_SPLIT_SOLVE", 0) != 0;
+    cx->bitq_state = env_int("G16_BITQ", 1) ? 0 : 2;
+    cx->bitq_min_rows = (uint32_t)env_int("G16_BITQ_MIN_ROWS", 256);
+    cx->bitq_min_batch = (uint32_t)env_int("G16_BITQ_MIN_BATCH", 32);
+    cx->bitq_test_exception = env_int("G16_BITQ_TEST_EXC", 0) != 0;
 
     PkFile pk = parse_pk(pk_bytes, pk_len);
     R1csFile cs = parse_r1cs(r1cs_bytes, r1cs_len);
@@ -328,6 +361,7 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     }
     if (mapA.size() != pk.nA || mapB.size() != pk.nB) throw ParseError("pk: infinity masks do not match the query sizes");
     if (mapK.size() != pk.nK) throw ParseError("pk: len(G1.K) does not match the private wires of the r1cs");
+    cx->h_mapA = mapA; cx->h_mapB = mapB; cx->h_mapK = mapK;
     cx->qA.map.upload(mapA.data(), mapA.size(), st);
     cx->qB.map.upload(mapB.data(), mapB.size(), st);
     cx->qK.map.upload(mapK.data(), mapK.size(), st);
@@ -554,6 +588,64 @@ static void run_query_g1(MsmWorkspace<G1>& ws, cudaStream_t st, const PrecompQue
     G16_CUDA(cudaMemcpyAsync(out, ws.result.p, (size_t)rows * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
 }
 
+// ---- combination tables (k_bitq.cu)
+static void bitq_build_one(Ctx& cx, BitQuery& bq, const PrecompQuery& q, const std::vector<uint32_t>& map, const G1Affine* pts1,
+                           const G2Affine* pts2, const G2Affine* tab2, int c2, cudaStream_t st) {
+    auto nwin = [](int c) { return (254 + c - 1) / c; };
+    std::vector<uint32_t> bitpts, rest;
+    for (uint32_t i = 0; i < map.size(); i++) (cx.bit_mask[map[i]] ? bitpts : rest).push_back(i);
+    bq.on = bitpts.size() >= BITQ_K && 2 * bitpts.size() >= map.size();   // worth it only when most of the query is bits
+    if (!bq.on) return;
+    bq.groups = (uint32_t)((bitpts.size() + BITQ_K - 1) / BITQ_K);
+    std::vector<uint32_t> gw((size_t)bq.groups * BITQ_K, BITQ_NONE), gp((size_t)bq.groups * BITQ_K, BITQ_NONE);
+    for (size_t k = 0; k < bitpts.size(); k++) { gp[k] = bitpts[k]; gw[k] = map[bitpts[k]]; }
+    DevBuf<uint32_t> d_gp, d_rest;
+    d_gp.upload(gp.data(), gp.size(), st);
+    bq.grp_wires.upload(gw.data(), gw.size(), st);
+    bq.table1.alloc((size_t)bq.groups << BITQ_K);
+    bitq_build_g1(pts1, d_gp.p, bq.groups, bq.table1.p, st);
+    if (pts2) {
+        bq.table2.alloc((size_t)bq.groups << BITQ_K);
+        bitq_build_g2(pts2, d_gp.p, bq.groups, bq.table2.p, st);
+    }
+    bq.rest.n = (uint32_t)rest.size();
+    bq.rest.c = q.c;
+    if (!rest.empty()) {
+        std::vector<uint32_t> rmap(rest.size());
+        for (size_t k = 0; k < rest.size(); k++) rmap[k] = map[rest[k]];
+        bq.rest.map.upload(rmap.data(), rmap.size(), st);
+        d_rest.upload(rest.data(), rest.size(), st);
+        bq.rest.table.alloc(rest.size() * nwin(q.c));
+        bitq_gather_g1(q.table.p, q.n, nwin(q.c), d_rest.p, bq.rest.n, bq.rest.table.p, st);
+        if (tab2) {
+            bq.rest_tab2.alloc(rest.size() * nwin(c2));
+            bitq_gather_g2(tab2, q.n, nwin(c2), d_rest.p, bq.rest.n, bq.rest_tab2.p, st);
+        }
+    }
+    G16_CUDA(cudaStreamSynchronize(st));   // the host vectors and the temporaries above must outlive the copies
+}
+static void ctx_bitq_build(Ctx& cx) {
+    if (cx.bitq_built) return;
+    cudaStream_t st = cx.stream;
+    bitq_build_one(cx, cx.bqA, cx.qA, cx.h_mapA, cx.A.p, nullptr, nullptr, 0, st);
+    bitq_build_one(cx, cx.bqB, cx.qB, cx.h_mapB, cx.B.p, cx.B2.p, cx.tabB2.p, cx.cB2, st);
+    bitq_build_one(cx, cx.bqK, cx.qK, cx.h_mapK, cx.K.p, nullptr, nullptr, 0, st);
+    cx.d_bitq_exc.ensure(1);
+    cx.bitq_built = true;
+    if (!cx.bqA.on && !cx.bqB.on && !cx.bqK.on) cx.bitq_state = 2;   // not a bit-level circuit (AES): nothing to gain
+}
+// one G1 query through its combination table: general path over the non-bit points + one table point per group of bit wires
+static void run_query_bitq_g1(Ctx& cx, cudaStream_t st, const BitQuery& bq, const Fr* w, size_t n, uint32_t rows, bool fresh_entries,
+                              G1XYZZ* out) {
+    if (bq.rest.n) run_query_g1(cx.ws1b, st, bq.rest, w, 1, n, true, rows, out, nullptr);
+    else G16_CUDA(cudaMemsetAsync(out, 0, (size_t)rows * sizeof(G1XYZZ), st));
+    cx.bitq_entries.ensure((size_t)rows * bq.groups);
+    cx.bitq_tmp1.ensure(rows);
+    if (fresh_entries) bitq_entries(w, n, rows, bq.grp_wires.p, bq.groups, cx.bitq_entries.p, cx.d_bitq_exc.p, st);
+    msm_sum_rows_g1(cx.ws1b, bq.table1.p, cx.bitq_entries.p, rows * bq.groups, rows, cx.bitq_tmp1.p, st);
+    xyzz_add_g1(out, cx.bitq_tmp1.p, rows, st);
+}
+
 // Solves witnesses [sb, sb + rows) of the batch (W wire-major, stride n) on stream st. With a BSB22 commitment the level
 // schedule is cut after the level that holds the commitment hint: Pedersen MSM over the committed wires -> hash to field ->
 // challenge wire (gnark prove.go:84-108 overrides the hint the same way), then the remaining levels run. wsc: the MSM
@@ -583,12 +675,32 @@ static void ctx_wire_queries(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaSt
     const Fr* w = cx.W.p + sb;   // column offset into the wire-major array
     if (eval_z)   // C-evaluation half of the Z query: almost every scalar is 0 or +-1
         run_query_g1(cx.ws1b, st2, cx.qQc, cx.Cev.p + sb * cx.n_dom, cx.n_dom, 1, false, rows, cx.resZc.p + sb, nullptr);
-    run_query_g1(cx.ws1b, st2, cx.qA, w, 1, n, true, rows, cx.resA.p + sb, nullptr);
-    run_query_g1(cx.ws1b, st2, cx.qB, w, 1, n, true, rows, cx.resB1.p + sb, nullptr);
-    run_query_g1(cx.ws1b, st2, cx.qK, w, 1, n, true, rows, cx.resK.p + sb, nullptr);
-    MsmShape sh = msm_make_shape(cx.nB2, rows, cx.cB2, 1);
-    msm_run_g2(cx.ws2, sh, cx.tabB2.p, w, 1, n, cx.qB.map.p, 1, st2, nullptr);
-    G16_CUDA(cudaMemcpyAsync(cx.resB2.p + sb, cx.ws2.result.p, (size_t)rows * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st2));
+    const bool bitq = cx.bitq_state == 1 && cx.bitq_built && n >= cx.bitq_min_batch;
+    if (bitq && cx.bqA.on) run_query_bitq_g1(cx, st2, cx.bqA, w, n, rows, true, cx.resA.p + sb);
+    else run_query_g1(cx.ws1b, st2, cx.qA, w, 1, n, true, rows, cx.resA.p + sb, nullptr);
+    if (bitq && cx.bqB.on) {
+        const BitQuery& bq = cx.bqB;
+        run_query_bitq_g1(cx, st2, bq, w, n, rows, true, cx.resB1.p + sb);
+        // the G2 element of the same wires: same entries, the G2 table
+        G2XYZZ* out2 = cx.resB2.p + sb;
+        if (bq.rest.n) {
+            MsmShape sh = msm_make_shape(bq.rest.n, rows, cx.cB2, 1);
+            msm_run_g2(cx.ws2, sh, bq.rest_tab2.p, w, 1, n, bq.rest.map.p, 1, st2, nullptr);
+            G16_CUDA(cudaMemcpyAsync(out2, cx.ws2.result.p, (size_t)rows * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st2));
+        } else {
+            G16_CUDA(cudaMemsetAsync(out2, 0, (size_t)rows * sizeof(G2XYZZ), st2));
+        }
+        cx.bitq_tmp2.ensure(rows);
+        msm_sum_rows_g2(cx.ws2, bq.table2.p, cx.bitq_entries.p, rows * bq.groups, rows, cx.bitq_tmp2.p, st2);
+        xyzz_add_g2(out2, cx.bitq_tmp2.p, rows, st2);
+    } else {
+        run_query_g1(cx.ws1b, st2, cx.qB, w, 1, n, true, rows, cx.resB1.p + sb, nullptr);
+        MsmShape sh = msm_make_shape(cx.nB2, rows, cx.cB2, 1);
+        msm_run_g2(cx.ws2, sh, cx.tabB2.p, w, 1, n, cx.qB.map.p, 1, st2, nullptr);
+        G16_CUDA(cudaMemcpyAsync(cx.resB2.p + sb, cx.ws2.result.p, (size_t)rows * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st2));
+    }
+    if (bitq && cx.bqK.on) run_query_bitq_g1(cx, st2, cx.bqK, w, n, rows, true, cx.resK.p + sb);
+    else run_query_g1(cx.ws1b, st2, cx.qK, w, 1, n, true, rows, cx.resK.p + sb, nullptr);
     if (cx.n_commit)   // proof of knowledge of the commitment: same scalars over BasisExpSigma
         run_query_g1(cx.ws1b, st2, cx.qPedSigma, w, 1, n, true, rows, cx.resPok.p + sb, nullptr);
 }
@@ -599,6 +711,14 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     cudaStream_t st = cx.stream;
     ctx_build_tables(cx);
     ctx_ensure_batch(cx, n);
+    // combination tables of the wire-driven queries: built once the classification has seen enough witnesses
+    if (cx.bitq_state == 0 && !cx.bitq_built && cx.bitq_rows_seen >= cx.bitq_min_rows && n >= cx.bitq_min_batch) {
+        ctx_bitq_build(cx);
+        if (cx.bitq_state == 0) cx.bitq_state = 1;
+    }
+    const bool bitq_profiling = cx.bitq_state == 0 && !cx.bitq_built && cx.bitq_rows_seen < cx.bitq_min_rows;
+    const bool bitq_live = cx.bitq_state == 1 && cx.bitq_built && n >= cx.bitq_min_batch;
+    if (bitq_live) G16_CUDA(cudaMemsetAsync(cx.d_bitq_exc.p, 0, sizeof(uint32_t), st));
     // evaluation-basis Z query (no commitment circuits only: their C evaluations are mostly full-width)
     // Not for the commitment (AES) circuits: their C evaluations are largely full-width, measured 1 112 vs 1 090 proofs/s.
     // Not when the caller asked for the coefficients of H (g16_prove_witness_detail).
@@ -651,6 +771,11 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
                 if (cx.ev_solved.size() <= k) { cudaEvent_t e; G16_CUDA(cudaEventCreate(&e)); cx.ev_solved.push_back(e); }
                 G16_CUDA(cudaEventRecord(cx.ev_solved[k], st2));
             }
+        }
+        if (bitq_profiling) {   // which wires held only 0 / 1 in this batch (read back below, folded into cx.bit_mask)
+            cx.d_bit_flags.ensure(cx.nb_wires);
+            G16_CUDA(cudaMemsetAsync(cx.d_bit_flags.p, 1, cx.nb_wires, st2));
+            bitq_profile(cx.W.p, n, cx.nb_wires, (uint32_t)n, cx.d_bit_flags.p, st2);
         }
         for (size_t sb = 0; sb < n; sb += cx.sub_batch) {
             uint32_t rows = (uint32_t)((n - sb) < cx.sub_batch ? (n - sb) : cx.sub_batch);
@@ -720,6 +845,27 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     cx.stage_ms[7] = (float)cx.launches;
     G16_CUDA(cudaStreamSynchronize(st2));
     G16_CUDA(cudaStreamSynchronize(cx.stream3));
+    if (bitq_profiling && !piped && !(status & 7u)) {
+        std::vector<uint8_t> f(cx.nb_wires);
+        cx.d_bit_flags.download(f.data(), cx.nb_wires, st);
+        G16_CUDA(cudaStreamSynchronize(st));
+        if (cx.bit_mask.empty()) cx.bit_mask.assign(cx.nb_wires, 1);
+        for (uint32_t w = 0; w < cx.nb_wires; w++) cx.bit_mask[w] &= f[w];
+        cx.bitq_rows_seen += n;
+    }
+    if (bitq_live) {
+        uint32_t exc = 0;
+        cx.d_bitq_exc.download(&exc, 1, st);
+        G16_CUDA(cudaStreamSynchronize(st));
+        if (cx.bitq_test_exception) { exc = 1; cx.bitq_test_exception = false; }
+        if (exc) {
+            // a wire classified as a bit held something else: the table sums of this batch are wrong. Prove it again on the
+            // general path and stop using the tables (the classification was learned, not proved).
+            cx.bitq_state = 2;
+            return ctx_run_batch(cx, n, kind);
+        }
+    }
+    cx.counters[11] = (uint64_t)cx.bitq_state | ((uint64_t)(bitq_live ? 1 : 0) << 8) | ((uint64_t)cx.bqA.groups << 16) | ((uint64_t)cx.bqK.groups << 40);
     cx.counters[6] = cx.ws1.log_sum(st) + cx.ws1c.log_sum(cx.stream3);   // G1 mixed additions of the Z query (lanes)
     cx.counters[0] = cx.counters[6] + cx.ws1b.log_sum(st2);               // ... of all G1 queries
     cx.counters[1] = cx.ws2.log_sum(st2);   // G2 mixed additions

@@ -75,6 +75,10 @@ void group_dft_g1(const G1Affine* Z, uint32_t nZ, int lg, const Fr* scale, int n
     G16_LAUNCH(gdft_finish_kernel, div_up(n_out, 32), 32, 0, stream, false, (const G1XYZZ*)work, lg, n_out, out);
     G16_CHECK_LAUNCH();
 }
+void msm_sum_rows_g1(MsmWorkspace<G1>& ws, const G1Affine* bases, const uint2* entries, uint32_t n_entries, uint32_t rows,
+                     G1XYZZ* out, cudaStream_t stream) {
+    msm_sum_rows<G1>(ws, bases, entries, n_entries, rows, out, stream);
+}
 void xyzz_to_affine_g1(const G1XYZZ* in, uint32_t n, G1Affine* out, cudaStream_t stream) {
     auto k = xyzz_to_affine_kernel<G1>;
     G16_LAUNCH(k, div_up(n, 32), 32, 0, stream, false, in, n, out);

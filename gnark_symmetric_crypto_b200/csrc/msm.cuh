@@ -364,6 +364,7 @@ msm_accumulate_kernel(const typename C::A* __restrict__ bases, const uint2* __re
             acc = X::inf();
             cur = e.x;
         }
+        if (e.y == MSM_INVALID) continue;   // a slot without a point (combination-table queries: an all-zero group of wires)
         typename C::A p = load_point<C>(bases, e.y >> 1);
         acc.madd(p, (e.y & 1u) != 0);
     }
@@ -628,6 +629,57 @@ static inline void msm_ba_run(MsmWorkspace<G1>& ws, const G1Affine* bases, size_
 }
 static inline void msm_ba_run(MsmWorkspace<G2>&, const G2Affine*, size_t, int, cudaStream_t) {}
 
+// merge tree over the partial sequence the accumulate kernel left in ws.part_*[0] (n_l0 = its upper bound); complete runs land
+// in bucket_sums. Grids are sized for the upper bound, threads past the live length exit.
+template <class C>
+static void msm_merge_partials(MsmWorkspace<C>& ws, const uint32_t* acc_total, int L, size_t n_l0, typename C::X* bucket_sums,
+                               cudaStream_t stream) {
+    size_t n_up = n_l0;
+    int level = 0, pp = 0;
+    while (n_up > 64) {
+        size_t slices = (n_up + MSM_MERGE_C - 1) / MSM_MERGE_C;
+        auto k = msm_merge_level_kernel<C>;
+        G16_LAUNCH(k, div_up(slices, 128), 128, 0, stream, false, acc_total, L, level, ws.part_key[pp].p,
+                   ws.part_val[pp].p, ws.part_key[pp ^ 1].p, ws.part_val[pp ^ 1].p, bucket_sums);
+        n_up = 2 * slices;
+        level++;
+        pp ^= 1;
+        ws.launches++;
+    }
+    auto k = msm_merge_final_kernel<C>;
+    G16_LAUNCH(k, div_up(n_up, 128), 128, 0, stream, false, acc_total, L, level, ws.part_key[pp].p, ws.part_val[pp].p, bucket_sums);
+    ws.launches++;
+}
+
+static __global__ void msm_set_u32_kernel(uint32_t* p, uint32_t v) { *p = v; }
+
+// Plain sums of point references grouped by row — the accumulate and merge stages of the pipeline without digits, sort and
+// bucket tree: entries[j] = (row, ref), sorted by row; ref = (index into bases) << 1 | negate, MSM_INVALID = nothing.
+// out[row] = Sum bases[ref >> 1] (XYZZ; infinity for a row without points). Used by the combination-table form of the
+// wire-driven queries (msm_bitq.cuh), where every request has one "bucket".
+template <class C>
+void msm_sum_rows(MsmWorkspace<C>& ws, const typename C::A* bases, const uint2* entries, uint32_t n_entries, uint32_t rows,
+                  typename C::X* out, cudaStream_t stream) {
+    typedef typename C::X X;
+    size_t l = (size_t)n_entries / ((size_t)148 * 512 * 4);
+    const int L = l < 8 ? 8 : (l > 64 ? 64 : (int)l);
+    const size_t max_chunks = ((size_t)n_entries + L - 1) / L;
+    const size_t n_l0 = 2 * max_chunks, n_l1 = 2 * ((n_l0 + MSM_MERGE_C - 1) / MSM_MERGE_C);
+    ws.total.ensure(8);
+    ws.part_val[0].ensure(n_l0);
+    ws.part_key[0].ensure(n_l0);
+    ws.part_val[1].ensure(n_l1);
+    ws.part_key[1].ensure(n_l1);
+    G16_CUDA(cudaMemsetAsync(out, 0, (size_t)rows * sizeof(X), stream));
+    G16_LAUNCH(msm_set_u32_kernel, 1, 1, 0, stream, false, ws.total.p + 3, n_entries);
+    auto k = msm_accumulate_kernel<C>;
+    G16_LAUNCH(k, div_up(max_chunks, 128), 128, 0, stream, false, bases, entries, (const uint32_t*)(ws.total.p + 3), L, out,
+               ws.part_val[0].p, ws.part_key[0].p);
+    ws.launches += 2;
+    msm_merge_partials<C>(ws, ws.total.p + 3, L, n_l0, out, stream);
+    G16_CHECK_LAUNCH();
+}
+
 // ------------------------------------------------------------------------------------------------ host driver
 // Runs the whole pipeline on `stream`; result XYZZ per row is left in ws.result (device). No host synchronisation.
 template <class C>
@@ -756,25 +808,7 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
         ws.launches += 6 + 3 * K;
     }
     if (tm) tm->mark(ST_MSM_REDUCE, stream);
-    {
-        // merge tree over the partial sequence; grids are sized for the upper bound, threads past the live length exit
-        size_t n_up = n_l0;
-        int level = 0, pp = 0;
-        while (n_up > 64) {
-            size_t slices = (n_up + MSM_MERGE_C - 1) / MSM_MERGE_C;
-            auto k = msm_merge_level_kernel<C>;
-            G16_LAUNCH(k, div_up(slices, 128), 128, 0, stream, false, acc_total, L, level, ws.part_key[pp].p,
-                       ws.part_val[pp].p, ws.part_key[pp ^ 1].p, ws.part_val[pp ^ 1].p, ws.buckets.p);
-            n_up = 2 * slices;
-            level++;
-            pp ^= 1;
-            ws.launches++;
-        }
-        auto k = msm_merge_final_kernel<C>;
-        G16_LAUNCH(k, div_up(n_up, 128), 128, 0, stream, false, acc_total, L, level, ws.part_key[pp].p, ws.part_val[pp].p,
-                   ws.buckets.p);
-        ws.launches++;
-    }
+    msm_merge_partials<C>(ws, acc_total, L, n_l0, ws.buckets.p, stream);
     G16_CHECK_LAUNCH();
     if (ws.entry_log.n < 2 * (ws.log_n + 1)) {   // grow the log (rare; keeps old values)
         DevBuf<uint32_t> bigger((ws.log_n + 1) * 4 + 64);

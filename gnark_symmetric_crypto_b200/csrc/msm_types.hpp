@@ -88,5 +88,28 @@ size_t msm_ba_scratch_elems(size_t max_slots);
 void msm_ba_levels(const G1Affine* bases, const uint32_t* refs, const uint32_t* total_slots, size_t max_slots, int K,
                    G1Affine* const* lvl, Fp* scratch, cudaStream_t stream);
 void xyzz_to_affine_g2(const G2XYZZ* in, uint32_t n, G2Affine* out, cudaStream_t stream);
+void xyzz_add_g2(G2XYZZ* a, const G2XYZZ* b, uint32_t n, cudaStream_t stream);   // a[i] += b[i]
+// plain per-row sums of point references (msm.cuh msm_sum_rows): entries[j] = (row, index << 1 | negate), sorted by row,
+// MSM_INVALID = empty slot; out[row] = the sum (XYZZ)
+void msm_sum_rows_g1(MsmWorkspace<G1>& ws, const G1Affine* bases, const uint2* entries, uint32_t n_entries, uint32_t rows,
+                     G1XYZZ* out, cudaStream_t stream);
+void msm_sum_rows_g2(MsmWorkspace<G2>& ws, const G2Affine* bases, const uint2* entries, uint32_t n_entries, uint32_t rows,
+                     G2XYZZ* out, cudaStream_t stream);
+
+// ---- combination tables for wire-driven queries whose scalars are bits (k_bitq.cu)
+static const int BITQ_K = 8;                       // wires per group: 255 non-empty subset sums per group
+static const uint32_t BITQ_NONE = 0xFFFFFFFFu;     // padding of the last group
+// flags[w] = 0 unless wire w holds 0 or 1 (Montgomery) in every one of `rows` witnesses (flags must be preset to 1)
+void bitq_profile(const Fr* W, size_t wire_stride, uint32_t nb_wires, uint32_t rows, uint8_t* flags, cudaStream_t stream);
+// table[g * 256 + idx] = Sum_{j : idx bit j} pts[grp_pts[8 g + j]]  (affine; entry 0 unused)
+void bitq_build_g1(const G1Affine* pts, const uint32_t* grp_pts, uint32_t groups, G1Affine* table, cudaStream_t stream);
+void bitq_build_g2(const G2Affine* pts, const uint32_t* grp_pts, uint32_t groups, G2Affine* table, cudaStream_t stream);
+// entries[row * groups + g] = (row, table reference of the 8-bit pattern of group g in witness `row`), MSM_INVALID for the
+// empty pattern; *exception is set when a wire of a group holds something else than 0 or 1
+void bitq_entries(const Fr* W, size_t wire_stride, uint32_t rows, const uint32_t* grp_wires, uint32_t groups, uint2* entries,
+                  uint32_t* exception, cudaStream_t stream);
+// out[w * n_sub + j] = table[w * n + sub[j]]  (window tables of the points that stay on the general path)
+void bitq_gather_g1(const G1Affine* table, uint32_t n, int nwin, const uint32_t* sub, uint32_t n_sub, G1Affine* out, cudaStream_t stream);
+void bitq_gather_g2(const G2Affine* table, uint32_t n, int nwin, const uint32_t* sub, uint32_t n_sub, G2Affine* out, cudaStream_t stream);
 
 }  // namespace g16

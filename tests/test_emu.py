@@ -129,6 +129,41 @@ def test_msm_edge_cases(emu, oracle):
     assert np.array_equal(out2, oracle.g2_msm(p2, s2))
 
 
+def _bitq_case(L, oracle, group, n, rows, seed):
+    """Combination-table sums (csrc/k_bitq.cu) against the oracle's MSM on the same 0 / 1 scalars."""
+    rng = np.random.default_rng(seed)
+    pts = (oracle.g1_fixed_base if group == 1 else oracle.g2_fixed_base)(oracle.rand_field(rng, 1, n))
+    if n > 20:
+        pts[3] = pts[2]      # equal points inside one group: a subset sum that is a doubling
+        pts[9] = 0           # the point at infinity as a table operand
+    bits = rng.integers(0, 2, size=(n, rows))
+    bits[:, 0] = 0           # a witness without any set bit: infinity
+    if rows > 1:
+        bits[:, 1] = 1       # every bit set
+    one = oracle.to_mont(1, oracle.ints_to_limbs([1]))[0]
+    wires = np.zeros((n, rows, 4), dtype=np.uint64)
+    wires[bits == 1] = one
+    w = 8 if group == 1 else 16
+    out = np.zeros((rows, w), dtype=np.uint64)
+    exc = C.c_uint32(7)
+    ok(L, L.g16_bitq_sum(group, p64(pts), n, p64(wires), rows, p64(out), C.byref(exc)))
+    assert exc.value == 0
+    msm = oracle.g1_msm if group == 1 else oracle.g2_msm
+    for r in range(rows):
+        sc = np.zeros((n, 4), dtype=np.uint64); sc[:, 0] = bits[:, r]
+        assert np.array_equal(out[r], msm(pts, sc)), (group, r)
+    assert not out[0].any()
+    # a wire that is not a bit is reported, never silently used
+    wires[n // 2, rows - 1] = oracle.to_mont(1, oracle.ints_to_limbs([2]))[0]
+    ok(L, L.g16_bitq_sum(group, p64(pts), n, p64(wires), rows, p64(out), C.byref(exc)))
+    assert exc.value == 1
+
+
+@pytest.mark.parametrize("group,n,rows", [(1, 1, 1), (1, 8, 3), (1, 77, 5), (1, 300, 40), (2, 50, 4)])
+def test_bit_wire_combination_tables(emu, oracle, group, n, rows):
+    _bitq_case(emu, oracle, group, n, rows, 1000 * group + n)
+
+
 @pytest.mark.parametrize("n", [2, 8, 256, 4096])
 def test_ntt(emu, oracle, n):
     rng = np.random.default_rng(n)

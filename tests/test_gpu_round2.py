@@ -270,6 +270,49 @@ def test_msm_paths_forced_on_small_and_edge_cases(env):
     assert " passed" in out.stdout
 
 
+# ---------------------------------------------------------------------------------------------- combination tables (bit wires)
+@pytest.mark.parametrize("group,n,rows", [(1, 8, 3), (1, 300, 40), (1, 5000, 64), (2, 50, 4), (2, 700, 33)])
+def test_bit_wire_combination_table_kernels(oracle, group, n, rows):
+    """csrc/k_bitq.cu on the GPU: per-witness subset sums through the 255-entry tables of every group of 8 points against the
+    oracle's MSM on the same 0 / 1 scalars (infinity, equal points, an all-zero and an all-one witness, the exception flag)."""
+    from gnark_symmetric_crypto_b200 import _lib
+    from test_emu import _bitq_case
+    _bitq_case(_lib.load(), oracle, group, n, rows, 77 * group + n)
+
+
+def test_bit_wire_tables_leave_the_proofs_unchanged(G, oracle, pk_bytes, r1cs_bytes, monkeypatch):
+    """The wire-driven queries (A, B1, K, B2) through the combination tables: the context learns from its first witnesses which
+    wires are bits (here 40, normally 256), builds the tables, and from then on proves batches with one table point per group
+    of 8 wires. Same group elements, so the same proof bytes as the general path of the first batch; then the fallback: a
+    forced exception makes the context prove the batch again on the general path and switch the tables off."""
+    monkeypatch.setenv("G16_BITQ_MIN_ROWS", "40")
+    monkeypatch.setenv("G16_BITQ_MIN_BATCH", "8")
+    keys, nonces, ctrs, ins, rs = batch_inputs(40, seed=b"g16-b200-bitq")
+    ctx = G.Groth16Context(pk_bytes, r1cs_bytes)
+    e = np.zeros(16, dtype=np.uint64)
+    u64p = e.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_uint64))
+    p1, c1 = ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)             # general path; the classification is learned
+    assert ctx._L.g16_last_counters_ex(ctx._h, u64p) == 0 and (int(e[11]) & 0xFF, (int(e[11]) >> 8) & 1) == (0, 0)
+    p2, c2 = ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)             # tables built, used
+    assert ctx._L.g16_last_counters_ex(ctx._h, u64p) == 0 and (int(e[11]) & 0xFF, (int(e[11]) >> 8) & 1) == (1, 1)
+    assert (int(e[11]) >> 16) & 0xFFFFFF > 1000                               # groups of the A query: most of its ~22 k wires
+    assert p2 == p1 and c2 == c1
+    keys3, nonces3, ctrs3, ins3, rs3 = batch_inputs(24, seed=b"g16-b200-bitq-other")
+    p3, _ = ctx.prove_chacha_batch(keys3, nonces3, ctrs3, ins3, rs3)         # other witnesses through the same tables
+    ver = G.Groth16Verifier(open("tests/golden/vk.chacha20", "rb").read())
+    pubs = [oracle.chacha_assignment(keys3[i], nonces3[i], ctrs3[i], ins3[i])[0][1:1153] for i in range(24)]
+    assert ver.verify_batch(p3, pubs).all()
+    ver.close(); ctx.close()
+    monkeypatch.setenv("G16_BITQ_TEST_EXC", "1")
+    ctx = G.Groth16Context(pk_bytes, r1cs_bytes)
+    q1, _ = ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)
+    q2, _ = ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)             # exception -> proved again without the tables
+    assert ctx._L.g16_last_counters_ex(ctx._h, u64p) == 0 and int(e[11]) & 0xFF == 2
+    q3, _ = ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)
+    assert q1 == p1 and q2 == p1 and q3 == p1
+    ctx.close()
+
+
 # ---------------------------------------------------------------------------------------------- product-side Setup (8f rank 1)
 def test_setup_reproduces_oracle_keys_byte_for_byte(G, oracle):
     """g16_setup (QAP evaluation on the host, every key element a fixed-base product on the GPU) against the oracle's Setup
