@@ -151,6 +151,73 @@ msm_ba_inv_kernel(const uint32_t* __restrict__ total_slots, int shift, const Fp*
     }
 }
 
+// Two-level form of the same step for large levels (millions of thread totals): the binary-Euclid inversion is half of the
+// single kernel's issue slots there (one inversion per ~40 totals, every lane on its own divergent path), so the totals are
+// first folded into groups of G1 by products alone (fwd), the group totals go through the kernel above (one inversion per
+// ~G1 * 4 totals), and a backward walk turns the group inverses into the inverses of the thread totals (bwd). Same values.
+template <int T, int M, int G1>
+__global__ void __launch_bounds__(128)
+msm_ba_inv_fwd_kernel(const uint32_t* __restrict__ total_slots, int shift, const Fp* __restrict__ tot, Fp* __restrict__ totpre,
+                      Fp* __restrict__ gtot) {
+    const size_t npairs = ((size_t)(*total_slots) >> shift) >> 1;
+    const size_t ntot = ((npairs + (size_t)T * M - 1) / ((size_t)T * M)) * T;
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t g0 = g * G1;
+    if (g0 >= ntot) return;
+    const size_t n = ntot - g0 < (size_t)G1 ? ntot - g0 : (size_t)G1;
+    Fp c = Fp::one();
+#pragma unroll 1
+    for (size_t i = 0; i < n; i++) {
+        c = c * tot[g0 + i];
+        totpre[g0 + i] = c;
+    }
+    gtot[g] = c;
+}
+// the kernel above over the group totals: group g owns thread totals [g G1, (g+1) G1)
+template <int T, int M, int G1, int GMIN, int GMAX>
+__global__ void __launch_bounds__(128)
+msm_ba_inv_mid_kernel(const uint32_t* __restrict__ total_slots, int shift, const Fp* __restrict__ gtot, Fp* __restrict__ gpre,
+                      Fp* __restrict__ ginv) {
+    const size_t npairs = ((size_t)(*total_slots) >> shift) >> 1;
+    const size_t ntot = ((npairs + (size_t)T * M - 1) / ((size_t)T * M)) * T;
+    const size_t ng = (ntot + G1 - 1) / G1;
+    const uint32_t G = ba_inv_group(ng, GMIN, GMAX);
+    const size_t g0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * G;
+    if (g0 >= ng) return;
+    const size_t n = ng - g0 < (size_t)G ? ng - g0 : (size_t)G;
+    Fp c = Fp::one();
+#pragma unroll 1
+    for (size_t i = 0; i < n; i++) {
+        c = c * gtot[g0 + i];
+        gpre[g0 + i] = c;
+    }
+    Fp R = c.inv();
+#pragma unroll 1
+    for (size_t i = n; i-- > 0;) {
+        const Fp cprev = i ? gpre[g0 + i - 1] : Fp::one();
+        ginv[g0 + i] = cprev * R;
+        R = R * gtot[g0 + i];
+    }
+}
+template <int T, int M, int G1>
+__global__ void __launch_bounds__(128)
+msm_ba_inv_bwd_kernel(const uint32_t* __restrict__ total_slots, int shift, const Fp* __restrict__ tot, const Fp* __restrict__ totpre,
+                      const Fp* __restrict__ ginv, Fp* __restrict__ totinv) {
+    const size_t npairs = ((size_t)(*total_slots) >> shift) >> 1;
+    const size_t ntot = ((npairs + (size_t)T * M - 1) / ((size_t)T * M)) * T;
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t g0 = g * G1;
+    if (g0 >= ntot) return;
+    const size_t n = ntot - g0 < (size_t)G1 ? ntot - g0 : (size_t)G1;
+    Fp R = ginv[g];   // 1 / (product of the group's totals)
+#pragma unroll 1
+    for (size_t i = n; i-- > 0;) {
+        const Fp cprev = i ? totpre[g0 + i - 1] : Fp::one();
+        totinv[g0 + i] = cprev * R;
+        R = R * tot[g0 + i];
+    }
+}
+
 template <bool LEVEL0, int T, int M>
 __global__ void __launch_bounds__(T, 640 / T)
 msm_ba_add_kernel(const G1Affine* __restrict__ src, const uint32_t* __restrict__ refs, const uint32_t* __restrict__ total_slots,

@@ -249,11 +249,11 @@ def test_verifier_rejects_noncanonical_coordinates(G, oracle, kat):
 @pytest.mark.parametrize("env", [
     {"G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "1"},
     {"G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "2"},
-    {"G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "3"},
+    {"G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "3", "G16_BA_INV2_MIN": "1"},
     {"G16_MSM_ROWSORT": "2"},
     {"G16_MSM_ROWSORT": "2", "G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "3"},
     {"G16_MSM_ROWSORT": "0", "G16_MSM_BA": "0"},
-], ids=["batch_affine_k1", "batch_affine_k2", "batch_affine_k3", "rowsort", "rowsort_batch_affine_k3", "round1_paths"])
+], ids=["batch_affine_k1", "batch_affine_k2", "batch_affine_k3_two_level_inversion", "rowsort", "rowsort_batch_affine_k3", "round1_paths"])
 def test_msm_paths_forced_on_small_and_edge_cases(env):
     """The batch-affine pairwise levels (csrc/msm_ba.cuh; gnark's own bucket-addition algorithm, multiexp_affine.go:35-176)
     normally start at 2^21 entries and the per-row shared-memory sort at 32 rows. Here they are forced onto the existing small
