@@ -12,6 +12,6 @@ d=json.loads([l for l in open("gpurun_out/r2_bench_${N}gpu.json") if l.startswit
 print("value", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "n_gpus", d["n_gpus"])
 print("strong", d["strong_1024"]); print("split", d["msm_split"]); print("lib_multi", d["library_multi_gpu"])
 PY
-for callers in 1024 4096 8192; do
+for callers in ${CALLERS:-1024 4096 8192}; do
   G16_DEVICES=all G16_BATCH_MAX=1024 gnark_symmetric_crypto_b200/lib/serve_load gnark_symmetric_crypto_b200/lib/libg16b200.so tests/golden/pk.chacha20 tests/golden/r1cs.chacha20 $callers 6 | tee -a gpurun_out/r2_serve_load_${N}gpu.jsonl
 done
