@@ -672,8 +672,10 @@ def run_gpu(args):
                                  "/ accumulate-stage time (CUDA events on the launching stream, sum over launches, same schedule and inputs as "
                                  "the timed region, taken in the steps that follow it). The stage executes fewer products than the algorithmic "
                                  "count (executed_products_per_addition: batch-affine additions with a shared inversion, gnark's own "
-                                 "multiexp_affine.go algorithm), so frac measures time against the SURVEY work definition, and "
-                                 "executed_frac_of_modmul_peak how busy the multiplier is with what is actually run. "
+                                 "multiexp_affine.go algorithm, 1 of the 5 products of an addition a dedicated squaring), so frac measures time "
+                                 "against the SURVEY work definition and CAN EXCEED 1 (the stage does the algorithmic work in less multiplier "
+                                 "time than the XYZZ formula needs), while executed_frac_of_modmul_peak says how busy the multiplier is with "
+                                 "what is actually run. "
                                  "peak = mad.lo.u32 rate measured in this run (not in MEASURED_PEAKS.json); HBM is not the bound "
                                  "(SURVEY finding 8)",
                          "imad_wide_peak": imad["imad_wide_per_s"] / 1e12, "modmul_per_s": imad["modmul_per_s"],

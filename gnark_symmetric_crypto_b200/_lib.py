@@ -63,7 +63,7 @@ EXPORTS = {
     "g16_group_op": (C.c_int, [C.c_int, C.c_int, u64p, u64p, u64p, C.c_size_t]),
     "g16_decompress": (C.c_int, [C.c_int, u8p, u64p, C.c_size_t]),
     "g16_msm": (C.c_int, [C.c_int, u64p, u64p, C.c_int, C.c_size_t, C.c_int, u64p, f32p]),
-    "g16_bitq_sum": (C.c_int, [C.c_int, u64p, C.c_size_t, u64p, C.c_size_t, u64p, C.POINTER(C.c_uint32)]),
+    "g16_bitq_sum": (C.c_int, [C.c_int, u64p, C.c_size_t, C.c_size_t, u64p, C.c_size_t, u64p, C.POINTER(C.c_uint32)]),
     "g16_msm_plan_create": (C.c_int, [C.c_int, u64p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "g16_msm_plan_set_scalars": (C.c_int, [C.c_void_p, u64p, C.c_int]),
     "g16_msm_plan_precompute": (C.c_int, [C.c_void_p, C.c_int]),

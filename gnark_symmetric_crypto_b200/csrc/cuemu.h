@@ -54,6 +54,7 @@ static inline T atomicAdd(T* p, T v) {
     return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
 static inline uint32_t atomicOr(uint32_t* p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+static inline uint32_t atomicAnd(uint32_t* p, uint32_t v) { return __atomic_fetch_and(p, v, __ATOMIC_RELAXED); }
 static inline int atomicMax(int* p, int v) {
     int old = *p;
     while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}

@@ -839,32 +839,36 @@ int g16_msm(int group, const uint64_t* points, const uint64_t* scalars, int scal
 }
 
 // Stage-level view of the combination-table path (k_bitq.cu) for the parity tests: per-witness subset sums of `n` points.
-// wires: [n][rows] Montgomery Fr, wire-major like the prover's witness array (wire i pairs with point i); every value must be
-// 0 or 1, anything else raises *exception_out (the sums are then meaningless, as in the prover, which falls back). out: `rows`
-// affine points. Groups of 8 consecutive points, 255 subset sums each, one table point per group and witness.
-int g16_bitq_sum(int group, const uint64_t* points, size_t n, const uint64_t* wires, size_t rows, uint64_t* out, uint32_t* exception_out) {
+// wires: [n][rows] Montgomery Fr, wire-major like the prover's witness array (wire i pairs with point i). The first n_binary
+// wires must hold 0 or 1 (binary groups of 8 consecutive points, 255 subset sums each), the others 0, 1 or -1 (ternary groups of
+// 5, 242 signed combinations); anything else raises *exception_out (the sums are then meaningless, as in the prover, which
+// falls back). out: `rows` affine points, one table point per group and witness.
+int g16_bitq_sum(int group, const uint64_t* points, size_t n, size_t n_binary, const uint64_t* wires, size_t rows, uint64_t* out,
+                 uint32_t* exception_out) {
     return guarded([&] {
         REQUIRE(points && wires && out, "NULL argument");
         REQUIRE(group == 1 || group == 2, "group must be 1 (G1) or 2 (G2)");
-        REQUIRE(n > 0 && n <= (1u << 22) && rows > 0 && rows <= (1u << 20), "size out of range");
+        REQUIRE(n > 0 && n <= (1u << 22) && rows > 0 && rows <= (1u << 20) && n_binary <= n, "size out of range");
         require_device();
         cudaStream_t st = nullptr;
-        const uint32_t groups = (uint32_t)((n + BITQ_K - 1) / BITQ_K);
+        const uint32_t groups_bin = (uint32_t)((n_binary + BITQ_K - 1) / BITQ_K);
+        const uint32_t groups = groups_bin + (uint32_t)((n - n_binary + BITQ_T - 1) / BITQ_T);
         std::vector<uint32_t> ident((size_t)groups * BITQ_K, BITQ_NONE);
-        for (size_t i = 0; i < n; i++) ident[i] = (uint32_t)i;
+        for (size_t i = 0; i < n_binary; i++) ident[i] = (uint32_t)i;
+        for (size_t i = n_binary; i < n; i++) ident[((size_t)groups_bin + (i - n_binary) / BITQ_T) * BITQ_K + (i - n_binary) % BITQ_T] = (uint32_t)i;
         DevBuf<uint32_t> d_ident, d_exc(1);
         DevBuf<Fr> d_w;
         DevBuf<uint2> d_entries((size_t)rows * groups);
         d_ident.upload(ident.data(), ident.size(), st);
         d_w.upload(reinterpret_cast<const Fr*>(wires), n * rows, st);
         d_exc.zero(st);
-        bitq_entries(d_w.p, rows, (uint32_t)rows, d_ident.p, groups, d_entries.p, d_exc.p, st);
+        bitq_entries(d_w.p, rows, (uint32_t)rows, d_ident.p, groups, groups_bin, d_entries.p, d_exc.p, st);
         if (group == 1) {
             DevBuf<G1Affine> pts, table((size_t)groups << BITQ_K), aff(rows);
             DevBuf<G1XYZZ> sums(rows);
             MsmWorkspace<G1> ws;
             pts.upload(reinterpret_cast<const G1Affine*>(points), n, st);
-            bitq_build_g1(pts.p, d_ident.p, groups, table.p, st);
+            bitq_build_g1(pts.p, d_ident.p, groups, groups_bin, table.p, st);
             msm_sum_rows_g1(ws, table.p, d_entries.p, (uint32_t)(rows * groups), (uint32_t)rows, sums.p, st);
             xyzz_to_affine_g1(sums.p, (uint32_t)rows, aff.p, st);
             aff.download(reinterpret_cast<G1Affine*>(out), rows, st);
@@ -874,7 +878,7 @@ int g16_bitq_sum(int group, const uint64_t* points, size_t n, const uint64_t* wi
             DevBuf<G2XYZZ> sums(rows);
             MsmWorkspace<G2> ws;
             pts.upload(reinterpret_cast<const G2Affine*>(points), n, st);
-            bitq_build_g2(pts.p, d_ident.p, groups, table.p, st);
+            bitq_build_g2(pts.p, d_ident.p, groups, groups_bin, table.p, st);
             msm_sum_rows_g2(ws, table.p, d_entries.p, (uint32_t)(rows * groups), (uint32_t)rows, sums.p, st);
             xyzz_to_affine_g2(sums.p, (uint32_t)rows, aff.p, st);
             aff.download(reinterpret_cast<G2Affine*>(out), rows, st);

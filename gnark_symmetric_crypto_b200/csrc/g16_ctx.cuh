@@ -24,8 +24,8 @@ struct PrecompQuery {
 // the 255 subset sums of every group, and the remaining points as a general sub-query over gathered window tables.
 struct BitQuery {
     bool on = false;
-    uint32_t groups = 0;
-    DevBuf<uint32_t> grp_wires;     // 8 wire ids per group (BITQ_NONE pads the last one)
+    uint32_t groups = 0, groups_bin = 0;   // groups [0, groups_bin): 8 wires in {0, 1}; the others: 5 wires in {0, 1, -1}
+    DevBuf<uint32_t> grp_wires;     // 8 slots of wire ids per group (BITQ_NONE pads)
     DevBuf<G1Affine> table1;        // [groups][256] subset sums on G1
     DevBuf<G2Affine> table2;        // the same on G2 (B query only)
     PrecompQuery rest;              // points that are not bits: general path (map = their wires, table = gathered windows)
@@ -109,9 +109,9 @@ struct Ctx {
     bool bitq_built = false;
     size_t bitq_rows_seen = 0;
     uint32_t bitq_min_rows = 256, bitq_min_batch = 32;
-    std::vector<uint8_t> bit_mask;                 // host: wire -> 1 while every witness seen so far held 0 or 1
+    std::vector<uint32_t> bit_mask;                // host, per wire: bit 0 while every witness seen so far held 0 / 1, bit 1 while 0 / 1 / -1
     std::vector<uint32_t> h_mapA, h_mapB, h_mapK;
-    DevBuf<uint8_t> d_bit_flags;
+    DevBuf<uint32_t> d_bit_flags;
     DevBuf<uint32_t> d_bitq_exc;
     DevBuf<uint2> bitq_entries;
     DevBuf<G1XYZZ> bitq_tmp1;
@@ -592,21 +592,30 @@ static void run_query_g1(MsmWorkspace<G1>& ws, cudaStream_t st, const PrecompQue
 static void bitq_build_one(Ctx& cx, BitQuery& bq, const PrecompQuery& q, const std::vector<uint32_t>& map, const G1Affine* pts1,
                            const G2Affine* pts2, const G2Affine* tab2, int c2, cudaStream_t st) {
     auto nwin = [](int c) { return (254 + c - 1) / c; };
-    std::vector<uint32_t> bitpts, rest;
-    for (uint32_t i = 0; i < map.size(); i++) (cx.bit_mask[map[i]] ? bitpts : rest).push_back(i);
-    bq.on = bitpts.size() >= BITQ_K && 2 * bitpts.size() >= map.size();   // worth it only when most of the query is bits
+    std::vector<uint32_t> bitpts, tripts, rest;
+    for (uint32_t i = 0; i < map.size(); i++) {
+        const uint32_t m = cx.bit_mask[map[i]];
+        ((m & 1u) ? bitpts : ((m & 2u) ? tripts : rest)).push_back(i);
+    }
+    // worth it only when most of the query is bits / trits (AES: bytes and field elements, the general path stays)
+    bq.on = bitpts.size() + tripts.size() >= BITQ_K && 2 * (bitpts.size() + tripts.size()) >= map.size();
     if (!bq.on) return;
-    bq.groups = (uint32_t)((bitpts.size() + BITQ_K - 1) / BITQ_K);
+    bq.groups_bin = (uint32_t)((bitpts.size() + BITQ_K - 1) / BITQ_K);
+    bq.groups = bq.groups_bin + (uint32_t)((tripts.size() + BITQ_T - 1) / BITQ_T);
     std::vector<uint32_t> gw((size_t)bq.groups * BITQ_K, BITQ_NONE), gp((size_t)bq.groups * BITQ_K, BITQ_NONE);
     for (size_t k = 0; k < bitpts.size(); k++) { gp[k] = bitpts[k]; gw[k] = map[bitpts[k]]; }
+    for (size_t k = 0; k < tripts.size(); k++) {   // five used slots of the eight of a ternary group
+        const size_t slot = ((size_t)bq.groups_bin + k / BITQ_T) * BITQ_K + k % BITQ_T;
+        gp[slot] = tripts[k]; gw[slot] = map[tripts[k]];
+    }
     DevBuf<uint32_t> d_gp, d_rest;
     d_gp.upload(gp.data(), gp.size(), st);
     bq.grp_wires.upload(gw.data(), gw.size(), st);
     bq.table1.alloc((size_t)bq.groups << BITQ_K);
-    bitq_build_g1(pts1, d_gp.p, bq.groups, bq.table1.p, st);
+    bitq_build_g1(pts1, d_gp.p, bq.groups, bq.groups_bin, bq.table1.p, st);
     if (pts2) {
         bq.table2.alloc((size_t)bq.groups << BITQ_K);
-        bitq_build_g2(pts2, d_gp.p, bq.groups, bq.table2.p, st);
+        bitq_build_g2(pts2, d_gp.p, bq.groups, bq.groups_bin, bq.table2.p, st);
     }
     bq.rest.n = (uint32_t)rest.size();
     bq.rest.c = q.c;
@@ -641,7 +650,7 @@ static void run_query_bitq_g1(Ctx& cx, cudaStream_t st, const BitQuery& bq, cons
     else G16_CUDA(cudaMemsetAsync(out, 0, (size_t)rows * sizeof(G1XYZZ), st));
     cx.bitq_entries.ensure((size_t)rows * bq.groups);
     cx.bitq_tmp1.ensure(rows);
-    if (fresh_entries) bitq_entries(w, n, rows, bq.grp_wires.p, bq.groups, cx.bitq_entries.p, cx.d_bitq_exc.p, st);
+    if (fresh_entries) bitq_entries(w, n, rows, bq.grp_wires.p, bq.groups, bq.groups_bin, cx.bitq_entries.p, cx.d_bitq_exc.p, st);
     msm_sum_rows_g1(cx.ws1b, bq.table1.p, cx.bitq_entries.p, rows * bq.groups, rows, cx.bitq_tmp1.p, st);
     xyzz_add_g1(out, cx.bitq_tmp1.p, rows, st);
 }
@@ -673,6 +682,10 @@ static size_t ctx_solve(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaStream_
 // the wire-driven queries of one sub-batch (A, B1, K on G1, B on G2, the commitment PoK): short, latency-bound kernels
 static void ctx_wire_queries(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaStream_t st2, bool eval_z = false) {
     const Fr* w = cx.W.p + sb;   // column offset into the wire-major array
+    // The side stream's general-path queries meet almost only 0 / +-1 scalars: their live entries are a small fraction of the
+    // upper bound the batch-affine decision is taken on, so the levels would be launches over mostly idle grids (measured: 9
+    // launches, ~1 ms per sub-batch for the C-evaluation query alone).
+    cx.ws1b.no_ba = cx.n_commit == 0;
     if (eval_z)   // C-evaluation half of the Z query: almost every scalar is 0 or +-1
         run_query_g1(cx.ws1b, st2, cx.qQc, cx.Cev.p + sb * cx.n_dom, cx.n_dom, 1, false, rows, cx.resZc.p + sb, nullptr);
     const bool bitq = cx.bitq_state == 1 && cx.bitq_built && n >= cx.bitq_min_batch;
@@ -774,7 +787,7 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
         }
         if (bitq_profiling) {   // which wires held only 0 / 1 in this batch (read back below, folded into cx.bit_mask)
             cx.d_bit_flags.ensure(cx.nb_wires);
-            G16_CUDA(cudaMemsetAsync(cx.d_bit_flags.p, 1, cx.nb_wires, st2));
+            G16_CUDA(cudaMemsetAsync(cx.d_bit_flags.p, 3, cx.nb_wires * sizeof(uint32_t), st2));   // every byte 3: the low two bits are what counts
             bitq_profile(cx.W.p, n, cx.nb_wires, (uint32_t)n, cx.d_bit_flags.p, st2);
         }
         for (size_t sb = 0; sb < n; sb += cx.sub_batch) {
@@ -846,11 +859,11 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     G16_CUDA(cudaStreamSynchronize(st2));
     G16_CUDA(cudaStreamSynchronize(cx.stream3));
     if (bitq_profiling && !piped && !(status & 7u)) {
-        std::vector<uint8_t> f(cx.nb_wires);
+        std::vector<uint32_t> f(cx.nb_wires);
         cx.d_bit_flags.download(f.data(), cx.nb_wires, st);
         G16_CUDA(cudaStreamSynchronize(st));
-        if (cx.bit_mask.empty()) cx.bit_mask.assign(cx.nb_wires, 1);
-        for (uint32_t w = 0; w < cx.nb_wires; w++) cx.bit_mask[w] &= f[w];
+        if (cx.bit_mask.empty()) cx.bit_mask.assign(cx.nb_wires, 3u);
+        for (uint32_t w = 0; w < cx.nb_wires; w++) cx.bit_mask[w] &= f[w] & 3u;
         cx.bitq_rows_seen += n;
     }
     if (bitq_live) {
@@ -865,6 +878,7 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
             return ctx_run_batch(cx, n, kind);
         }
     }
+    cx.counters[12] = (uint64_t)cx.bqA.rest.n | ((uint64_t)cx.bqB.rest.n << 20) | ((uint64_t)cx.bqK.rest.n << 40);   // points left on the general path
     cx.counters[11] = (uint64_t)cx.bitq_state | ((uint64_t)(bitq_live ? 1 : 0) << 8) | ((uint64_t)cx.bqA.groups << 16) | ((uint64_t)cx.bqK.groups << 40);
     cx.counters[6] = cx.ws1.log_sum(st) + cx.ws1c.log_sum(cx.stream3);   // G1 mixed additions of the Z query (lanes)
     cx.counters[0] = cx.counters[6] + cx.ws1b.log_sum(st2);               // ... of all G1 queries

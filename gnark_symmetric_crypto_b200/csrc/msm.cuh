@@ -700,7 +700,7 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
         static const int ba_k = [] { const char* v = getenv("G16_MSM_BA_K"); return v && *v ? atoi(v) : 0; }();
         static const long ba_min = [] { const char* v = getenv("G16_MSM_BA_MIN"); return v && *v ? atol(v) : (1l << 21); }();
         const double run = (double)max_entries / (double)nbuckets;
-        if (ba_on && (long)max_entries >= ba_min) K = ba_k > 0 ? (ba_k > MSM_BA_MAX_LEVELS ? MSM_BA_MAX_LEVELS : ba_k) : (run >= 24.0 ? 3 : (run >= 8.0 ? 2 : 0));
+        if (ba_on && !ws.no_ba && (long)max_entries >= ba_min) K = ba_k > 0 ? (ba_k > MSM_BA_MAX_LEVELS ? MSM_BA_MAX_LEVELS : ba_k) : (run >= 24.0 ? 3 : (run >= 8.0 ? 2 : 0));
     }
     const uint32_t pad_mask = (1u << K) - 1u;
     // sorted slots: every non-empty bucket is padded by at most 2^K - 1 null slots

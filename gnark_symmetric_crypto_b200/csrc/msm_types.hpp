@@ -36,6 +36,7 @@ struct MsmWorkspace {
     DevBuf<uint32_t> entry_log;
     size_t log_n = 0;
     int last_K = 0;   // batch-affine levels of the last run (0 = XYZZ accumulation only)
+    bool no_ba = false;   // set by the caller for queries whose live entries are far below the upper bound (mostly 0 / +-1 scalars)
     void log_reset() { log_n = 0; }
     uint64_t log_sum(cudaStream_t st, int word = 0) {   // synchronises the stream; word 0 = entries, 1 = slots
         if (!log_n) return 0;
@@ -97,17 +98,20 @@ void msm_sum_rows_g2(MsmWorkspace<G2>& ws, const G2Affine* bases, const uint2* e
                      G2XYZZ* out, cudaStream_t stream);
 
 // ---- combination tables for wire-driven queries whose scalars are bits (k_bitq.cu)
-static const int BITQ_K = 8;                       // wires per group: 255 non-empty subset sums per group
-static const uint32_t BITQ_NONE = 0xFFFFFFFFu;     // padding of the last group
-// flags[w] = 0 unless wire w holds 0 or 1 (Montgomery) in every one of `rows` witnesses (flags must be preset to 1)
-void bitq_profile(const Fr* W, size_t wire_stride, uint32_t nb_wires, uint32_t rows, uint8_t* flags, cudaStream_t stream);
-// table[g * 256 + idx] = Sum_{j : idx bit j} pts[grp_pts[8 g + j]]  (affine; entry 0 unused)
-void bitq_build_g1(const G1Affine* pts, const uint32_t* grp_pts, uint32_t groups, G1Affine* table, cudaStream_t stream);
-void bitq_build_g2(const G2Affine* pts, const uint32_t* grp_pts, uint32_t groups, G2Affine* table, cudaStream_t stream);
-// entries[row * groups + g] = (row, table reference of the 8-bit pattern of group g in witness `row`), MSM_INVALID for the
-// empty pattern; *exception is set when a wire of a group holds something else than 0 or 1
-void bitq_entries(const Fr* W, size_t wire_stride, uint32_t rows, const uint32_t* grp_wires, uint32_t groups, uint2* entries,
-                  uint32_t* exception, cudaStream_t stream);
+static const int BITQ_K = 8;                       // wires per binary group: 255 non-empty subset sums; every group owns 2^8 table slots
+static const int BITQ_T = 5, BITQ_T_ENTRIES = 243; // wires per ternary group ({0, 1, -1}): 3^5 signed combinations (index in base 3, 2 = -1)
+static const uint32_t BITQ_NONE = 0xFFFFFFFFu;     // padding of the last group of a kind
+// flags[w]: bit 0 stays set while wire w only holds 0 / 1 (Montgomery), bit 1 while it only holds 0 / 1 / -1, over the `rows`
+// witnesses (flags: one word per wire, preset to 3)
+void bitq_profile(const Fr* W, size_t wire_stride, uint32_t nb_wires, uint32_t rows, uint32_t* flags, cudaStream_t stream);
+// groups [0, groups_bin) are binary (8 points), the others ternary (5 points); 8 slots of grp_pts / grp_wires per group.
+// table[g * 256 + idx] = the combination `idx` of the group's points (affine; entry 0 unused)
+void bitq_build_g1(const G1Affine* pts, const uint32_t* grp_pts, uint32_t groups, uint32_t groups_bin, G1Affine* table, cudaStream_t stream);
+void bitq_build_g2(const G2Affine* pts, const uint32_t* grp_pts, uint32_t groups, uint32_t groups_bin, G2Affine* table, cudaStream_t stream);
+// entries[row * groups + g] = (row, table reference of the pattern of group g in witness `row`), MSM_INVALID for the empty
+// pattern; *exception is set when a wire of a group holds something its kind of group does not allow
+void bitq_entries(const Fr* W, size_t wire_stride, uint32_t rows, const uint32_t* grp_wires, uint32_t groups, uint32_t groups_bin,
+                  uint2* entries, uint32_t* exception, cudaStream_t stream);
 // out[w * n_sub + j] = table[w * n + sub[j]]  (window tables of the points that stay on the general path)
 void bitq_gather_g1(const G1Affine* table, uint32_t n, int nwin, const uint32_t* sub, uint32_t n_sub, G1Affine* out, cudaStream_t stream);
 void bitq_gather_g2(const G2Affine* table, uint32_t n, int nwin, const uint32_t* sub, uint32_t n_sub, G2Affine* out, cudaStream_t stream);

@@ -178,9 +178,10 @@ int g16_msm(int group, const uint64_t* points, const uint64_t* scalars, int scal
             uint64_t* out, float ms[4]);
 /* device-resident variant for benchmarking: upload once, run many times */
 /* Stage-level view of the combination-table form of the wire-driven queries (csrc/k_bitq.cu; gnark prove.go:197-260 MultiExp over
- * pk.G1.A / G1.B / G1.K / G2.B for wires that only hold 0 or 1): out[row] = Sum_i wires[i][row] * points[i], wires wire-major
- * [n][rows] Montgomery Fr, every value 0 or 1 (otherwise *exception_out = 1 and the sums are meaningless). Parity tests only. */
-int g16_bitq_sum(int group, const uint64_t* points, size_t n, const uint64_t* wires, size_t rows, uint64_t* out,
+ * pk.G1.A / G1.B / G1.K / G2.B for wires that only hold 0, 1 or -1): out[row] = Sum_i wires[i][row] * points[i], wires wire-major
+ * [n][rows] Montgomery Fr; the first n_binary wires hold 0 / 1 (groups of 8), the others 0 / 1 / -1 (groups of 5); any other
+ * value sets *exception_out = 1 and the sums are meaningless. Parity tests only. */
+int g16_bitq_sum(int group, const uint64_t* points, size_t n, size_t n_binary, const uint64_t* wires, size_t rows, uint64_t* out,
                  uint32_t* exception_out);
 
 typedef struct g16_msm_plan g16_msm_plan;

@@ -130,33 +130,47 @@ def test_msm_edge_cases(emu, oracle):
 
 
 def _bitq_case(L, oracle, group, n, rows, seed):
-    """Combination-table sums (csrc/k_bitq.cu) against the oracle's MSM on the same 0 / 1 scalars."""
+    """Combination-table sums (csrc/k_bitq.cu) against the oracle's MSM on the same scalars: the first ~60 % of the wires hold
+    0 / 1 (binary groups of 8 points), the others 0 / 1 / -1 (ternary groups of 5)."""
     rng = np.random.default_rng(seed)
     pts = (oracle.g1_fixed_base if group == 1 else oracle.g2_fixed_base)(oracle.rand_field(rng, 1, n))
+    nb = n if n < 3 else (3 * n) // 5
     if n > 20:
         pts[3] = pts[2]      # equal points inside one group: a subset sum that is a doubling
         pts[9] = 0           # the point at infinity as a table operand
-    bits = rng.integers(0, 2, size=(n, rows))
-    bits[:, 0] = 0           # a witness without any set bit: infinity
+        pts[n - 1] = pts[n - 2]   # ... and inside a ternary group: P - P = infinity, P + P a doubling
+    vals = rng.integers(0, 2, size=(n, rows))
+    vals[nb:] = rng.integers(-1, 2, size=(n - nb, rows))
+    vals[:, 0] = 0           # a witness without any non-zero wire: infinity
     if rows > 1:
-        bits[:, 1] = 1       # every bit set
+        vals[:, 1] = 1       # every wire 1
+    if rows > 2:
+        vals[nb:, 2] = -1    # every trit -1
     one = oracle.to_mont(1, oracle.ints_to_limbs([1]))[0]
+    mone = oracle.to_mont(1, oracle.ints_to_limbs([oracle.R_MOD - 1]))[0]
     wires = np.zeros((n, rows, 4), dtype=np.uint64)
-    wires[bits == 1] = one
+    wires[vals == 1] = one
+    wires[vals == -1] = mone
     w = 8 if group == 1 else 16
     out = np.zeros((rows, w), dtype=np.uint64)
     exc = C.c_uint32(7)
-    ok(L, L.g16_bitq_sum(group, p64(pts), n, p64(wires), rows, p64(out), C.byref(exc)))
+    ok(L, L.g16_bitq_sum(group, p64(pts), n, nb, p64(wires), rows, p64(out), C.byref(exc)))
     assert exc.value == 0
     msm = oracle.g1_msm if group == 1 else oracle.g2_msm
+    minus1 = oracle.ints_to_limbs([oracle.R_MOD - 1])[0]
     for r in range(rows):
-        sc = np.zeros((n, 4), dtype=np.uint64); sc[:, 0] = bits[:, r]
+        sc = np.zeros((n, 4), dtype=np.uint64); sc[:, 0] = (vals[:, r] == 1)
+        sc[vals[:, r] == -1] = minus1
         assert np.array_equal(out[r], msm(pts, sc)), (group, r)
     assert not out[0].any()
-    # a wire that is not a bit is reported, never silently used
-    wires[n // 2, rows - 1] = oracle.to_mont(1, oracle.ints_to_limbs([2]))[0]
-    ok(L, L.g16_bitq_sum(group, p64(pts), n, p64(wires), rows, p64(out), C.byref(exc)))
+    # a wire that holds something its group does not allow is reported, never silently used
+    bad = wires.copy(); bad[n // 2, rows - 1] = oracle.to_mont(1, oracle.ints_to_limbs([2]))[0]
+    ok(L, L.g16_bitq_sum(group, p64(pts), n, nb, p64(bad), rows, p64(out), C.byref(exc)))
     assert exc.value == 1
+    if nb > 0:
+        bad = wires.copy(); bad[0, rows - 1] = mone      # -1 on a wire classified as a bit
+        ok(L, L.g16_bitq_sum(group, p64(pts), n, nb, p64(bad), rows, p64(out), C.byref(exc)))
+        assert exc.value == 1
 
 
 @pytest.mark.parametrize("group,n,rows", [(1, 1, 1), (1, 8, 3), (1, 77, 5), (1, 300, 40), (2, 50, 4)])
