@@ -794,9 +794,14 @@ unsigned char InitAlgorithm(unsigned char algorithmID, GoSlice_g16 provingKey, G
                 for (auto& b : nonces) b = (uint8_t)next();
                 for (auto& b : inputs) b = (uint8_t)next();
                 for (auto& c : counters) c = (uint32_t)next();
-                if (g16_prove_chacha_batch(ctx, n, keys.data(), nonces.data(), counters.data(), inputs.data(), nullptr,
-                                           proofs.data(), cts.data()))
-                    printf("warm-up batch failed: %s\n", g16_last_error());
+                // twice: the first batch is proved on the general path while the wires are classified, the second one builds the
+                // combination tables and runs through them, so the first caller meets neither the build nor a cold kernel
+                for (int pass = 0; pass < 2; pass++)
+                    if (g16_prove_chacha_batch(ctx, n, keys.data(), nonces.data(), counters.data(), inputs.data(), nullptr,
+                                               proofs.data(), cts.data())) {
+                        printf("warm-up batch failed: %s\n", g16_last_error());
+                        break;
+                    }
             }
         }
 #endif
