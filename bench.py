@@ -38,7 +38,7 @@ BATCH = 1024
 METRIC = "ChaCha20-V3 Groth16 proofs/sec"
 UNIT = "proofs/s"
 IMAD_PER_MADD_G1 = 2640      # 10 modmul x 264 IMAD
-BA_ADD_L0_TRAFFIC = 20.21e9   # dram__bytes_read.sum + dram__bytes_write.sum of msm_ba_add_kernel level 0 (profiles/ncu_msm_ba_add_r02.txt)
+BA_ADD_L0_TRAFFIC = 20.19e9   # dram__bytes_read.sum + dram__bytes_write.sum of msm_ba_add_kernel level 0 (profiles/ncu_msm_ba_add_r02_final.txt)
 WORKLOAD = "batched ChaCha20-V3 Groth16 BN254 proofs, 1024 synthetic key/nonce/counter/input requests per GPU (BASELINE config 4)"
 R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617   # BN254 group order
 
@@ -661,9 +661,9 @@ def run_gpu(args):
                          "achieved": achieved, "peak": peak,
                          "unit": "TIMAD/s", "frac": (achieved / peak) if achieved else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (msm_ba_add_kernel, level 0 of the Z query of
-                         # a 512-proof sub-batch) from the ncu --set full capture in profiles/ncu_msm_ba_add_r02.txt
+                         # a 512-proof sub-batch) from the ncu --set full capture in profiles/ncu_msm_ba_add_r02_final.txt
                          "traffic": BA_ADD_L0_TRAFFIC if (z_levels == 3 and sched["sub_batch"] == 512 and BATCH == 1024) else None,
-                         "traffic_unit": "bytes per launch (profiles/ncu_msm_ba_add_r02.txt)",
+                         "traffic_unit": "bytes per launch (profiles/ncu_msm_ba_add_r02_final.txt)",
                          "executed_products_per_addition": products_per_addition,
                          "algorithmic_products_per_addition": 10,
                          "executed_modmul_per_s": (executed_products / (acc_ms / 1e3)) if acc_ms else None,

@@ -70,6 +70,23 @@ struct DevBuf {
 
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
+// streaming multiprocessors of the current device (148 on B200): grid sizing heuristics scale with it instead of naming it
+static inline size_t sm_count() {
+#if defined(G16_EMU)
+    return 148;
+#else
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return (size_t)cached[dev];
+#endif
+}
+
 // CUDA-event stage timer: mark(stage) opens an interval attributed to `stage`; finish() (after the stream has been
 // synchronised) adds every interval to its stage. Events are pooled and reused.
 enum Stage { ST_SOLVE = 0, ST_H = 1, ST_MSM_SORT = 2, ST_MSM_ACC = 3, ST_MSM_REDUCE = 4, ST_ASSEMBLE = 5, ST_COUNT = 6 };

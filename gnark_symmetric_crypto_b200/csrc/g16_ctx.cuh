@@ -117,6 +117,7 @@ struct Ctx {
     DevBuf<G1XYZZ> bitq_tmp1;
     DevBuf<G2XYZZ> bitq_tmp2;
     BitQuery bqA, bqB, bqK;
+    int bitq_relearned = 0;                        // exceptions met so far (each one re-opens the learning phase; > 3: state 2)
     bool bitq_test_exception = false;              // G16_BITQ_TEST_EXC=1: pretend one exception (tests of the fallback)
 
     ~Ctx() {
@@ -872,9 +873,14 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
         G16_CUDA(cudaStreamSynchronize(st));
         if (cx.bitq_test_exception) { exc = 1; cx.bitq_test_exception = false; }
         if (exc) {
-            // a wire classified as a bit held something else: the table sums of this batch are wrong. Prove it again on the
-            // general path and stop using the tables (the classification was learned, not proved).
-            cx.bitq_state = 2;
+            // a wire classified as a bit (trit) held something else: the table sums of this batch are wrong. Prove it again on
+            // the general path. The classification was learned, not proved, so learn on: the mask keeps what it knows (it is
+            // only ever narrowed), the next bitq_min_rows witnesses narrow it further and the tables are rebuilt from it. After
+            // three such rounds the tables are switched off for good.
+            cx.bqA = BitQuery(); cx.bqB = BitQuery(); cx.bqK = BitQuery();
+            cx.bitq_built = false;
+            cx.bitq_rows_seen = 0;
+            cx.bitq_state = ++cx.bitq_relearned > 3 ? 2 : 0;
             return ctx_run_batch(cx, n, kind);
         }
     }

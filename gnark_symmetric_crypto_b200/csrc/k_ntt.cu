@@ -255,7 +255,7 @@ void imad_peak_measure(double* imad_per_s, double* imad_wide_per_s, double* modm
     cudaEvent_t e0, e1;
     G16_CUDA(cudaEventCreate(&e0));
     G16_CUDA(cudaEventCreate(&e1));
-    const int blocks = 148 * 8, threads = 256, iters = 2000;
+    const int blocks = (int)sm_count() * 8, threads = 256, iters = 2000;
     auto time_it = [&](auto launch) {
         launch();   // warm-up
         G16_CUDA(cudaDeviceSynchronize());

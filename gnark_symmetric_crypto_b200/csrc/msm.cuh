@@ -661,7 +661,7 @@ template <class C>
 void msm_sum_rows(MsmWorkspace<C>& ws, const typename C::A* bases, const uint2* entries, uint32_t n_entries, uint32_t rows,
                   typename C::X* out, cudaStream_t stream) {
     typedef typename C::X X;
-    size_t l = (size_t)n_entries / ((size_t)148 * 512 * 4);
+    size_t l = (size_t)n_entries / (sm_count() * 512 * 4);
     const int L = l < 8 ? 8 : (l > 64 ? 64 : (int)l);
     const size_t max_chunks = ((size_t)n_entries + L - 1) / L;
     const size_t n_l0 = 2 * max_chunks, n_l1 = 2 * ((n_l0 + MSM_MERGE_C - 1) / MSM_MERGE_C);
@@ -714,7 +714,7 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     int L = chunk_len;
     if (L <= 0) {
         // enough chunks to fill the machine a few times over, but not shorter than 8 / longer than 64 entries
-        size_t want_threads = 148 * 512 * 4;
+        size_t want_threads = sm_count() * 512 * 4;
         size_t l = acc_entries / want_threads;
         static const int lmax = [] { const char* v = getenv("G16_MSM_LMAX"); return v && *v ? atoi(v) : 64; }();
         L = l < 8 ? 8 : (l > (size_t)lmax ? lmax : (int)l);
@@ -828,7 +828,7 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     // A single MSM re-decides the arity at every level (its upper levels are small problems: 2^22 points, fixed base, reduce
     // 3.8 -> 2.7 ms); a batch keeps arity 32 below a wide first level (measured: 16.6 vs 17.4 ms per 1024 proofs).
     const bool tree_dynamic = sh.rows == 1;
-    int log_g = ((size_t)segs * ((n_in + MSM_TREE_G - 1) / MSM_TREE_G) < (size_t)148 * 256) ? MSM_TREE_LOG_G_SMALL : MSM_TREE_LOG_G;
+    int log_g = ((size_t)segs * ((n_in + MSM_TREE_G - 1) / MSM_TREE_G) < sm_count() * 256) ? MSM_TREE_LOG_G_SMALL : MSM_TREE_LOG_G;
     // small problems: block-parallel nodes of arity MSM_TREE_TB (log-depth) instead of thread-serial nodes of arity 4
     static const int tree_block = [] { const char* v = getenv("G16_MSM_TREE_BLOCK"); return v && *v ? atoi(v) : 1; }();
     static const int tree_block_max = [] { const char* v = getenv("G16_MSM_TREE_BLOCK_MAX"); return v && *v ? atoi(v) : 96; }();
@@ -839,7 +839,7 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     int level = 1, log_span = 0, pp = 0;
     while (true) {
         if (tree_dynamic)   // re-decide per level: the upper levels of a wide tree are small problems too
-            log_g = ((size_t)segs * ((n_in + MSM_TREE_G - 1) / MSM_TREE_G) < (size_t)148 * 256) ? MSM_TREE_LOG_G_SMALL : MSM_TREE_LOG_G;
+            log_g = ((size_t)segs * ((n_in + MSM_TREE_G - 1) / MSM_TREE_G) < sm_count() * 256) ? MSM_TREE_LOG_G_SMALL : MSM_TREE_LOG_G;
         // only while the level is a handful of blocks: a block node does ~4x the additions of a serial one (measured on B200:
         // 2^20 points, 128+ blocks: reduce 1.65 -> 2.77 ms; a single request, 64 blocks: 1.04 -> 0.64 ms)
         const bool block_level = (use_block || (tree_dynamic && tree_block)) && log_g == MSM_TREE_LOG_G_SMALL &&

@@ -284,7 +284,7 @@ def test_bit_wire_tables_leave_the_proofs_unchanged(G, oracle, pk_bytes, r1cs_by
     """The wire-driven queries (A, B1, K, B2) through the combination tables: the context learns from its first witnesses which
     wires are bits (here 40, normally 256), builds the tables, and from then on proves batches with one table point per group
     of 8 wires. Same group elements, so the same proof bytes as the general path of the first batch; then the fallback: a
-    forced exception makes the context prove the batch again on the general path and switch the tables off."""
+    forced exception makes the context prove the batch again on the general path and learn the classification anew."""
     monkeypatch.setenv("G16_BITQ_MIN_ROWS", "40")
     monkeypatch.setenv("G16_BITQ_MIN_BATCH", "8")
     keys, nonces, ctrs, ins, rs = batch_inputs(40, seed=b"g16-b200-bitq")
@@ -307,9 +307,10 @@ def test_bit_wire_tables_leave_the_proofs_unchanged(G, oracle, pk_bytes, r1cs_by
     monkeypatch.setenv("G16_BITQ_TEST_EXC", "1")
     ctx = G.Groth16Context(pk_bytes, r1cs_bytes)
     q1, _ = ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)
-    q2, _ = ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)             # exception -> proved again without the tables
-    assert ctx._L.g16_last_counters_ex(ctx._h, u64p) == 0 and int(e[11]) & 0xFF == 2
-    q3, _ = ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)
+    q2, _ = ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)             # exception -> proved again without the tables, learning re-opened
+    assert ctx._L.g16_last_counters_ex(ctx._h, u64p) == 0 and (int(e[11]) & 0xFF, (int(e[11]) >> 8) & 1) == (0, 0)
+    q3, _ = ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)             # tables rebuilt from the narrowed classification, used again
+    assert ctx._L.g16_last_counters_ex(ctx._h, u64p) == 0 and (int(e[11]) & 0xFF, (int(e[11]) >> 8) & 1) == (1, 1)
     assert q1 == p1 and q2 == p1 and q3 == p1
     ctx.close()
 
