@@ -312,7 +312,7 @@ def run_gpu(args):
     # ---------------- per-kernel view: stage timers exist only in the single-stream schedule (the default). When the
     # pipelined schedule was benchmarked (G16_PIPELINE=1) the same step is replayed on one stream for the roofline.
     stages = {}
-    madds = acc_launches = z_slots = z_levels = z_buckets = 0
+    madds = acc_launches = z_slots = z_levels = z_buckets = z_xyzz = 0
     if rank == 0:
         ctx.set_schedule(False, 0 if not sched["pipelined"] else 512)
         ctx.run()
@@ -323,7 +323,7 @@ def run_gpu(args):
                 stages[kk] = stages.get(kk, 0.0) + v
             c2 = ctx.counters()
             madds += c2["g1_madds_main_stream"]; acc_launches += c2["g1_acc_launches"]
-            z_slots += c2.get("z_sorted_slots", 0); z_levels = c2.get("z_batch_affine_levels", 0); z_buckets += c2.get("z_buckets", 0)
+            z_slots += c2.get("z_sorted_slots", 0); z_levels = c2.get("z_batch_affine_levels", 0); z_buckets += c2.get("z_buckets", 0); z_xyzz += c2.get("z_xyzz_entries", 0)
         ctx.fetch(proofs, cts)
         assert np.array_equal(proofs, ref_proofs), "pipelined and single-stream schedules disagree"
         ctx.set_schedule(sched["pipelined"], sched["sub_batch"])
@@ -610,7 +610,9 @@ def run_gpu(args):
         # mixed addition (10 products, the first point of every bucket is a copy). Without it every entry is one XYZZ addition.
         if z_levels and madds:
             pairs = sum(z_slots >> (l + 1) for l in range(z_levels))
-            executed_products = pairs * (6 + 3 / 32) + max((z_slots >> z_levels) - z_buckets, 0) * 10
+            # z_xyzz: entries of the XYZZ accumulation (group sums + the direct leftovers that skip the levels)
+            xyzz = z_xyzz if z_xyzz else (z_slots >> z_levels)
+            executed_products = pairs * (6 + 3 / 32) + max(xyzz - z_buckets, 0) * 10
         else:
             executed_products = madds * 10
         products_per_addition = executed_products / madds if madds else None

@@ -98,7 +98,7 @@ struct Ctx {
     size_t launches = 0;
     uint64_t counters[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t sub_batch = 512;
-    bool split_solve = false;          // G16_SPLIT_SOLVE=1: later sub-batches are solved on the side stream (ctx_run_batch)
+    int split_solve = 0;               // G16_SPLIT_SOLVE: 1 = later sub-batches solved on the side stream behind the first one's transforms, 2 = all sub-batches solved concurrently (ctx_run_batch)
     bool tables_ready = false;
     SolverGraphCache* solver_graphs = nullptr;
     // combination tables of the wire-driven queries (A, B1, K, B2). Which wires are bits is learned from the first
@@ -263,7 +263,7 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     cx->eval_z = env_int("G16_EVAL_Z", -1);
     cx->eval_z_min = (uint32_t)env_int("G16_EVAL_Z_MIN", 128);
     if (cx->sub_batch == 0) cx->sub_batch = 1;
-    cx->split_solve = env_int("G16_SPLIT_SOLVE", 0) != 0;
+    cx->split_solve = env_int("G16_SPLIT_SOLVE", -1);   // -1: decided once the circuit is known (below)
     cx->bitq_state = env_int("G16_BITQ", 1) ? 0 : 2;
     cx->bitq_min_rows = (uint32_t)env_int("G16_BITQ_MIN_ROWS", 256);
     cx->bitq_min_batch = (uint32_t)env_int("G16_BITQ_MIN_BATCH", 32);
@@ -284,6 +284,9 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     cx->n_constraints = (uint32_t)cs.n_constraints;
     cx->n_instr = (uint32_t)cs.n_instr(); cx->nlevels = (uint32_t)cs.levels.size();
     cx->n_commit = (uint32_t)cs.commitments.size();
+    // concurrent solves of the sub-batches (135.0 -> 134.4 ms per 1024 ChaCha proofs); circuits with a commitment keep the
+    // single chain (their solve includes a Pedersen MSM per sub-batch)
+    if (cx->split_solve < 0) cx->split_solve = cx->n_commit ? 0 : 2;
 
     // ---- decompress the key on the GPU (~89k Fp + 12.5k Fp2 square roots)
     DevBuf<uint32_t> err(1);
@@ -769,12 +772,28 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
         // queries run on a side stream and fill the SM slots that the long H / Z kernels leave idle.
         // G16_SPLIT_SOLVE=1: only the first sub-batch is solved on the main stream; the later ones are solved on the side
         // stream while the main stream already runs the transforms and the Z query of the one before (the solver is a chain
-        // of ~160 short level kernels: latency, not throughput). MEASURED ON B200 AND NOT THE DEFAULT: the solve interval
+        // of ~160 short level kernels: latency, not throughput). MEASURED ON B200 AND NOT ADOPTED: the solve interval
         // shrinks (6.85 -> 4.38 ms per 1024 proofs) but the side stream's wire queries start later and the same SM time is
         // taken out of the accumulate / reduce intervals instead: 145.6 vs 145.3 ms per step.
-        const bool split_solve = n > cx.sub_batch && cx.split_solve;
-        const uint32_t rows0 = split_solve ? (uint32_t)cx.sub_batch : (uint32_t)n;
-        own += ctx_solve(cx, n, 0, rows0, st, cx.ws1b);
+        // G16_SPLIT_SOLVE=2 (the default without a commitment): the sub-batches are solved CONCURRENTLY, the first on the main
+        // stream and the others on the side stream, and the main stream goes on when all of them are done: two chains of short
+        // level kernels fill each other's launch gaps and tails (solve 6.83 -> 6.26 ms per 1024 proofs).
+        const bool split_solve = n > cx.sub_batch && cx.split_solve == 1;
+        const bool par_solve = n > cx.sub_batch && cx.split_solve == 2;
+        const uint32_t rows0 = (split_solve || par_solve) ? (uint32_t)cx.sub_batch : (uint32_t)n;
+        if (par_solve) {
+            G16_CUDA(cudaEventRecord(cx.ev_fork, st));   // witness assignment done
+            G16_CUDA(cudaStreamWaitEvent(st2, cx.ev_fork, 0));
+            size_t k = 0;
+            for (size_t sb = cx.sub_batch; sb < n; sb += cx.sub_batch, k++) {
+                uint32_t rows = (uint32_t)((n - sb) < cx.sub_batch ? (n - sb) : cx.sub_batch);
+                own += ctx_solve(cx, n, sb, rows, st2, cx.ws1b);
+            }
+            if (cx.ev_solved.empty()) { cudaEvent_t e; G16_CUDA(cudaEventCreate(&e)); cx.ev_solved.push_back(e); }
+            G16_CUDA(cudaEventRecord(cx.ev_solved[0], st2));
+        }
+        own += ctx_solve(cx, n, 0, rows0, st, par_solve ? cx.ws1c : cx.ws1b);
+        if (par_solve) G16_CUDA(cudaStreamWaitEvent(st, cx.ev_solved[0], 0));
         G16_CUDA(cudaEventRecord(cx.ev_fork, st));
         G16_CUDA(cudaStreamWaitEvent(st2, cx.ev_fork, 0));
         if (split_solve) {
@@ -894,6 +913,7 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     cx.counters[4] = cx.launches;
     cx.counters[5] = n;
     cx.counters[8] = cx.ws1.log_sum(st, 1) + cx.ws1c.log_sum(cx.stream3, 1);   // sorted slots of the Z query (entries + batch-affine padding)
+    cx.counters[13] = cx.ws1.log_sum(st, 2) + cx.ws1c.log_sum(cx.stream3, 2);   // entries of the XYZZ accumulation of the Z query (group sums + direct leftovers)
     cx.counters[9] = (uint64_t)cx.ws1.last_K;                                   // batch-affine levels of the Z query
     cx.counters[10] = (uint64_t)cx.nZ_buckets_total(n);
     cx.counters[7] = (uint64_t)cx.sub_batch | ((uint64_t)(piped ? 1 : 0) << 32) | ((uint64_t)(eval_z ? 1 : 0) << 33);

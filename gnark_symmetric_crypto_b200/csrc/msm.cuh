@@ -59,9 +59,28 @@ FD int recode_digit(const Recoded& r, int w, int c, int& carry) {
 // (refs[pos]), and the first slot of every group of 2^ba_shift writes the group's key (bucket id, group index) to `entries`.
 // scalar of (row r, point i) = scalars[r*row_stride + e*elem_stride], e = map ? map[i] : i. Consecutive threads walk the
 // unit-stride dimension (points for row-major h vectors, rows for the wire-major witness array).
+static const uint32_t MSM_REF_TABLE = 0x80000000u;   // entry reference into the base table (a direct leftover), not a level sum
+// Pass 2 of the batch-affine path places every entry through a 64-bit cursor per bucket (built by scan_tiles):
+// cursor word = slot offset of the bucket's run (high 32 bits) | direct leftovers of the bucket (bits 29..31) | entries placed
+// so far (bits 0..28). The first `lc` entries of a bucket skip the batch-affine levels: they go straight into the accumulate
+// list as references into the base table; the others fill the run, whose length is a multiple of 2^ba_shift.
+FD void msm_ba_place(unsigned long long word, uint32_t b, uint32_t ref_neg, int ba_shift, const uint32_t* __restrict__ loff,
+                     uint2* __restrict__ entries, uint32_t* __restrict__ refs) {
+    const uint32_t soff = (uint32_t)(word >> 32), low = (uint32_t)word;
+    const uint32_t lc = low >> 29, j = low & 0x1FFFFFFFu;
+    const uint32_t ebase = (soff >> ba_shift) + loff[b];   // first accumulate entry of this bucket
+    if (j < lc) {
+        entries[ebase + j] = make_uint2(b, MSM_REF_TABLE | ref_neg);
+    } else {
+        const uint32_t k = j - lc, pos = soff + k;
+        refs[pos] = ref_neg;
+        if ((k & ((1u << ba_shift) - 1u)) == 0) entries[ebase + lc + (k >> ba_shift)] = make_uint2(b, (pos >> ba_shift) << 1);
+    }
+}
 static __global__ void msm_digits_kernel(MsmShape sh, const Fr* __restrict__ scalars, size_t row_stride, size_t elem_stride,
                                   const uint32_t* __restrict__ map, int is_mont, int pass, uint32_t* __restrict__ counts,
-                                  uint2* __restrict__ entries, uint32_t* __restrict__ refs = nullptr, int ba_shift = 0) {
+                                  uint2* __restrict__ entries, uint32_t* __restrict__ refs = nullptr, int ba_shift = 0,
+                                  unsigned long long* __restrict__ cursor64 = nullptr) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)sh.n * sh.rows) return;
     uint32_t row, i;
@@ -94,8 +113,12 @@ static __global__ void msm_digits_kernel(MsmShape sh, const Fr* __restrict__ sca
         if (pass == 0) {
             atomicAdd(&counts[b], 1u);
         } else {
-            uint32_t pos = atomicAdd(&counts[b], 1u);   // counts holds the running write cursor (= exclusive scan)
             uint32_t ref = sh.precomp ? (uint32_t)w * sh.n + i : i;
+            if (pass == 2 && cursor64) {   // counts holds the leftover offsets of the buckets here
+                msm_ba_place(atomicAdd(&cursor64[b], 1ull), b, (ref << 1) | neg, ba_shift, counts, entries, refs);
+                continue;
+            }
+            uint32_t pos = atomicAdd(&counts[b], 1u);   // counts holds the running write cursor (= exclusive scan)
             if (pass == 1) {
                 entries[pos] = make_uint2(b, (ref << 1) | neg);
             } else {
@@ -236,34 +259,82 @@ msm_rowscan_kernel(const uint32_t* __restrict__ row_tot, uint32_t rows, uint32_t
 // three-kernel scan: tile sums -> scan of tile sums (single block) -> rescan tiles. Tile = 256 threads x 8 items.
 #define SCAN_T 256
 #define SCAN_I 8
+// Padded run length and direct leftovers of a bucket with v entries on the batch-affine path (pad_mask = 2^K - 1): the run holds
+// the multiple of 2^K below v, plus one more full group when the remainder exceeds pad_t; a remainder of at most pad_t entries
+// skips the levels instead and is added in the XYZZ accumulation directly. A group of 2^K slots that holds one or two entries
+// costs as much as a full one in the levels (0.80 ns per group of 8 against 0.17 ns per direct entry, measured per sub-batch of
+// the Z query), so pad_t = 5 for K = 3 and 2 for K = 2. pad_t = 0 is the plain padding (per-row sort, small-case tests).
+FD uint32_t ba_padded(uint32_t v, uint32_t pad_mask, uint32_t pad_t) {
+    const uint32_t m = v & pad_mask;
+    return (v & ~pad_mask) + (m > pad_t ? pad_mask + 1u : 0u);
+}
+FD uint32_t ba_leftover(uint32_t v, uint32_t pad_mask, uint32_t pad_t) {
+    const uint32_t m = v & pad_mask;
+    return m <= pad_t ? m : 0u;
+}
 // pad_mask = 2^K - 1 rounds every count up to a multiple of 2^K before it is summed (batch-affine path: padded runs);
 // raw_sums (optional) receives the unpadded tile sums, i.e. the number of real entries.
 static __global__ void scan_tile_sums(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ tile_sums, uint32_t pad_mask = 0,
-                                      uint32_t* __restrict__ raw_sums = nullptr) {
+                                      uint32_t* __restrict__ raw_sums = nullptr, uint32_t pad_t = 0, uint32_t* __restrict__ left_sums = nullptr) {
     __shared__ uint32_t sm[SCAN_T];
     __shared__ uint32_t sr[SCAN_T];
+    __shared__ uint32_t sl[SCAN_T];
     size_t base = (size_t)blockIdx.x * SCAN_T * SCAN_I;
-    uint32_t s = 0, r = 0;
+    uint32_t s = 0, r = 0, l = 0;
     for (int k = 0; k < SCAN_I; k++) {
         size_t idx = base + (size_t)k * SCAN_T + threadIdx.x;
-        if (idx < n) { uint32_t v = in[idx]; r += v; s += (v + pad_mask) & ~pad_mask; }
+        if (idx < n) { uint32_t v = in[idx]; r += v; s += ba_padded(v, pad_mask, pad_t); l += ba_leftover(v, pad_mask, pad_t); }
     }
     sm[threadIdx.x] = s;
     sr[threadIdx.x] = r;
+    sl[threadIdx.x] = l;
     __syncthreads();
     for (int off = SCAN_T / 2; off > 0; off >>= 1) {
-        if ((int)threadIdx.x < off) { sm[threadIdx.x] += sm[threadIdx.x + off]; sr[threadIdx.x] += sr[threadIdx.x + off]; }
+        if ((int)threadIdx.x < off) {
+            sm[threadIdx.x] += sm[threadIdx.x + off]; sr[threadIdx.x] += sr[threadIdx.x + off]; sl[threadIdx.x] += sl[threadIdx.x + off];
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { tile_sums[blockIdx.x] = sm[0]; if (raw_sums) raw_sums[blockIdx.x] = sr[0]; }
+    if (threadIdx.x == 0) {
+        tile_sums[blockIdx.x] = sm[0];
+        if (raw_sums) raw_sums[blockIdx.x] = sr[0];
+        if (left_sums) left_sums[blockIdx.x] = sl[0];
+    }
 }
 // single block: in-place exclusive scan of `m` tile sums; writes total[0] = the grand total (sorted slots),
 // total[1] = the sum of raw_sums (real entries; = total[0] without padding), total[2] = total[0] >> ba_shift
 static __global__ void scan_of_sums(uint32_t* __restrict__ tile_sums, size_t m, uint32_t* __restrict__ total,
-                                    const uint32_t* __restrict__ raw_sums = nullptr, int ba_shift = 0) {
+                                    const uint32_t* __restrict__ raw_sums = nullptr, int ba_shift = 0, uint32_t* __restrict__ left_sums = nullptr) {
     __shared__ uint32_t sm[SCAN_T];
     __shared__ uint32_t carry;
     __shared__ uint32_t raw[SCAN_T];
+    __shared__ uint32_t left_total;
+    if (threadIdx.x == 0) left_total = 0;
+    if (left_sums) {   // exclusive scan of the leftover tile sums (same loop as below, kept apart for clarity: m is small)
+        __shared__ uint32_t lcarry;
+        if (threadIdx.x == 0) lcarry = 0;
+        __syncthreads();
+        for (size_t base = 0; base < m; base += SCAN_T) {
+            size_t idx = base + threadIdx.x;
+            uint32_t v = idx < m ? left_sums[idx] : 0;
+            sm[threadIdx.x] = v;
+            __syncthreads();
+            for (int off = 1; off < SCAN_T; off <<= 1) {
+                uint32_t add = (int)threadIdx.x >= off ? sm[threadIdx.x - off] : 0;
+                __syncthreads();
+                sm[threadIdx.x] += add;
+                __syncthreads();
+            }
+            uint32_t incl = sm[threadIdx.x];
+            uint32_t c0 = lcarry;
+            if (idx < m) left_sums[idx] = c0 + incl - v;
+            __syncthreads();
+            if (threadIdx.x == SCAN_T - 1) lcarry = c0 + incl;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) left_total = lcarry;
+        __syncthreads();
+    }
     {
         uint32_t r = 0;
         if (raw_sums) for (size_t i = threadIdx.x; i < m; i += SCAN_T) r += raw_sums[i];
@@ -294,32 +365,51 @@ static __global__ void scan_of_sums(uint32_t* __restrict__ tile_sums, size_t m, 
         for (int i = 0; i < SCAN_T; i++) r += raw[i];
         total[0] = carry;
         total[1] = raw_sums ? r : carry;
-        total[2] = carry >> ba_shift;
+        total[2] = (carry >> ba_shift) + left_total;   // what the XYZZ accumulation walks: one entry per group + the direct leftovers
     }
 }
 // each tile: exclusive scan of its SCAN_T*SCAN_I items (thread-contiguous layout) + tile offset ; out may alias in
+// With cursor64 (batch-affine path): out[b] receives the exclusive scan of the LEFTOVER counts instead, and cursor64[b] the
+// placement word of the bucket (slot offset << 32 | leftovers << 29 | 0 entries placed), see msm_ba_place.
 static __global__ void scan_tiles(const uint32_t* __restrict__ in, size_t n, const uint32_t* __restrict__ tile_offs,
-                           uint32_t* __restrict__ out, uint32_t pad_mask = 0) {
+                           uint32_t* __restrict__ out, uint32_t pad_mask = 0, uint32_t pad_t = 0,
+                           const uint32_t* __restrict__ left_offs = nullptr, unsigned long long* __restrict__ cursor64 = nullptr) {
     __shared__ uint32_t sm[SCAN_T];
+    __shared__ uint32_t sl[SCAN_T];
     size_t base = (size_t)blockIdx.x * SCAN_T * SCAN_I + (size_t)threadIdx.x * SCAN_I;
-    uint32_t v[SCAN_I];
-    uint32_t s = 0;
+    uint32_t v[SCAN_I], lv[SCAN_I];
+    uint32_t s = 0, l = 0;
     for (int k = 0; k < SCAN_I; k++) {
-        v[k] = (base + k < n) ? ((in[base + k] + pad_mask) & ~pad_mask) : 0;
+        const uint32_t c = (base + k < n) ? in[base + k] : 0;
+        v[k] = ba_padded(c, pad_mask, pad_t);
+        lv[k] = ba_leftover(c, pad_mask, pad_t);
         s += v[k];
+        l += lv[k];
     }
     sm[threadIdx.x] = s;
+    sl[threadIdx.x] = l;
     __syncthreads();
     for (int off = 1; off < SCAN_T; off <<= 1) {
         uint32_t add = (int)threadIdx.x >= off ? sm[threadIdx.x - off] : 0;
+        uint32_t addl = (int)threadIdx.x >= off ? sl[threadIdx.x - off] : 0;
         __syncthreads();
         sm[threadIdx.x] += add;
+        sl[threadIdx.x] += addl;
         __syncthreads();
     }
     uint32_t run = tile_offs[blockIdx.x] + sm[threadIdx.x] - s;
+    uint32_t lrun = (left_offs ? left_offs[blockIdx.x] : 0u) + sl[threadIdx.x] - l;
     for (int k = 0; k < SCAN_I; k++) {
-        if (base + k < n) out[base + k] = run;
+        if (base + k < n) {
+            if (cursor64) {
+                cursor64[base + k] = ((unsigned long long)run << 32) | ((unsigned long long)lv[k] << 29);
+                out[base + k] = lrun;
+            } else {
+                out[base + k] = run;
+            }
+        }
         run += v[k];
+        lrun += lv[k];
     }
 }
 // NOTE scan_tile_sums reads items tile-strided while scan_tiles reads thread-contiguous: both cover the same tile
@@ -346,7 +436,8 @@ template <class C>
 __global__ void __launch_bounds__(128, 4)
 msm_accumulate_kernel(const typename C::A* __restrict__ bases, const uint2* __restrict__ entries,
                       const uint32_t* __restrict__ total_entries, int L, typename C::X* __restrict__ bucket_sums,
-                      typename C::X* __restrict__ part_val, uint32_t* __restrict__ part_key) {
+                      typename C::X* __restrict__ part_val, uint32_t* __restrict__ part_key,
+                      const typename C::A* __restrict__ table = nullptr) {
     typedef typename C::X X;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t M = *total_entries;
@@ -365,7 +456,9 @@ msm_accumulate_kernel(const typename C::A* __restrict__ bases, const uint2* __re
             cur = e.x;
         }
         if (e.y == MSM_INVALID) continue;   // a slot without a point (combination-table queries: an all-zero group of wires)
-        typename C::A p = load_point<C>(bases, e.y >> 1);
+        // with `table` (batch-affine path): MSM_REF_TABLE marks a direct leftover, a reference into the base table
+        const bool tab = table != nullptr && (e.y & MSM_REF_TABLE);
+        typename C::A p = load_point<C>(tab ? table : bases, (tab ? (e.y & ~MSM_REF_TABLE) : e.y) >> 1);
         acc.madd(p, (e.y & 1u) != 0);
     }
     if (first) {
@@ -674,7 +767,7 @@ void msm_sum_rows(MsmWorkspace<C>& ws, const typename C::A* bases, const uint2* 
     G16_LAUNCH(msm_set_u32_kernel, 1, 1, 0, stream, false, ws.total.p + 3, n_entries);
     auto k = msm_accumulate_kernel<C>;
     G16_LAUNCH(k, div_up(max_chunks, 128), 128, 0, stream, false, bases, entries, (const uint32_t*)(ws.total.p + 3), L, out,
-               ws.part_val[0].p, ws.part_key[0].p);
+               ws.part_val[0].p, ws.part_key[0].p, (const typename C::A*)nullptr);
     ws.launches += 2;
     msm_merge_partials<C>(ws, ws.total.p + 3, L, n_l0, out, stream);
     G16_CHECK_LAUNCH();
@@ -703,6 +796,18 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
         if (ba_on && !ws.no_ba && (long)max_entries >= ba_min) K = ba_k > 0 ? (ba_k > MSM_BA_MAX_LEVELS ? MSM_BA_MAX_LEVELS : ba_k) : (run >= 24.0 ? 3 : (run >= 8.0 ? 2 : 0));
     }
     const uint32_t pad_mask = (1u << K) - 1u;
+    // per-row sort in shared memory: batches over fixed-base tables with <= 2^14 buckets per row (G16_MSM_ROWSORT: 0 (default)
+    // never, 1 from 32 rows on, 2 whenever the shape allows — the switch the small-case tests use)
+    static const int rowsort_mode = [] { const char* v = getenv("G16_MSM_ROWSORT"); return v && *v ? atoi(v) : 0; }();
+    const size_t rowsort_smem = (size_t)sh.nbk * sizeof(uint32_t);
+    const bool rowsort = sh.precomp && rowsort_smem <= 65536 && rowsort_mode > 0 && (rowsort_mode > 1 || sh.rows >= 32);
+    // direct leftovers (ba_padded / ba_leftover): a remainder of at most pad_t entries of a bucket skips the levels.
+    // G16_MSM_BA_LEFT=0 restores the plain padding, 1 (default) uses the measured thresholds; the placement word keeps 29 bits
+    // for the entries of one bucket.
+    static const int ba_left = [] { const char* v = getenv("G16_MSM_BA_LEFT"); return v && *v ? atoi(v) : 1; }();
+    uint32_t pad_t = (K >= 2 && ba_left && !rowsort && (size_t)sh.n * sh.nwin < (1u << 29)) ? (K == 3 ? 5u : 2u) : 0u;
+    if (pad_t && ba_left >= 2) pad_t = (uint32_t)ba_left < pad_mask ? (uint32_t)ba_left : pad_mask;   // G16_MSM_BA_LEFT=2..7: explicit threshold (tuning)
+    const bool cursor64 = K > 0 && !rowsort && (size_t)sh.n * sh.nwin < (1u << 29);
     // sorted slots: every non-empty bucket is padded by at most 2^K - 1 null slots
     size_t max_slots = max_entries;
     if (K) {
@@ -710,7 +815,10 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
         max_slots = a < b ? a : b;
         if (max_slots >= 0xFFFFFFF0ull) throw std::runtime_error("msm: problem too large for 32-bit slot positions");
     }
-    const size_t acc_entries = max_slots >> K;   // what the XYZZ accumulation walks: entries, or one group sum per 2^K slots
+    // what the XYZZ accumulation walks: entries, or one group sum per 2^K slots plus at most pad_t direct leftovers per bucket
+    size_t max_left = (size_t)pad_t * nbuckets;
+    if (max_left > max_entries) max_left = max_entries;
+    const size_t acc_entries = (max_slots >> K) + max_left;
     int L = chunk_len;
     if (L <= 0) {
         // enough chunks to fill the machine a few times over, but not shorter than 8 / longer than 64 entries
@@ -723,7 +831,8 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     const size_t ntiles = (nbuckets + SCAN_T * SCAN_I - 1) / (SCAN_T * SCAN_I);
 
     ws.counts.ensure(nbuckets);
-    ws.tile_sums.ensure(2 * ntiles + 3 * (size_t)sh.rows);   // padded tile sums, then the raw ones (or the per-row totals / bases)
+    ws.tile_sums.ensure(3 * ntiles + 3 * (size_t)sh.rows);   // padded tile sums, the raw ones, the leftover ones (or the per-row totals / bases)
+    if (cursor64) ws.cursor64.ensure(nbuckets);
     ws.total.ensure(8);
     ws.entries.ensure(acc_entries);
     ws.buckets.ensure(nbuckets);
@@ -743,11 +852,6 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     if (tm) tm->mark(ST_MSM_SORT, stream);
     G16_CUDA(cudaMemsetAsync(ws.buckets.p, 0, nbuckets * sizeof(X), stream));
     const size_t nthreads = (size_t)sh.n * sh.rows;
-    // per-row sort in shared memory: batches over fixed-base tables with <= 2^14 buckets per row (G16_MSM_ROWSORT: 0 (default)
-    // never, 1 from 32 rows on, 2 whenever the shape allows — the switch the small-case tests use)
-    static const int rowsort_mode = [] { const char* v = getenv("G16_MSM_ROWSORT"); return v && *v ? atoi(v) : 0; }();
-    const size_t rowsort_smem = (size_t)sh.nbk * sizeof(uint32_t);
-    const bool rowsort = sh.precomp && rowsort_smem <= 65536 && rowsort_mode > 0 && (rowsort_mode > 1 || sh.rows >= 32);
     uint32_t* row_tot = ws.tile_sums.p;                  // 2 words per row
     uint32_t* row_base = ws.tile_sums.p + 2 * (size_t)sh.rows;
     if (rowsort) {
@@ -770,9 +874,12 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
         G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, elem_stride, map, is_mont, 0,
                    ws.counts.p, ws.entries.p);
         uint32_t* raw_sums = ws.tile_sums.p + ntiles;
-        G16_LAUNCH(scan_tile_sums, (unsigned)ntiles, SCAN_T, 0, stream, true, ws.counts.p, nbuckets, ws.tile_sums.p, pad_mask, raw_sums);
-        G16_LAUNCH(scan_of_sums, 1, SCAN_T, 0, stream, true, ws.tile_sums.p, ntiles, ws.total.p, (const uint32_t*)raw_sums, K);
-        G16_LAUNCH(scan_tiles, (unsigned)ntiles, SCAN_T, 0, stream, true, ws.counts.p, nbuckets, ws.tile_sums.p, ws.counts.p, pad_mask);
+        uint32_t* left_sums = cursor64 ? ws.tile_sums.p + 2 * ntiles : nullptr;
+        G16_LAUNCH(scan_tile_sums, (unsigned)ntiles, SCAN_T, 0, stream, true, ws.counts.p, nbuckets, ws.tile_sums.p, pad_mask, raw_sums, pad_t, left_sums);
+        G16_LAUNCH(scan_of_sums, 1, SCAN_T, 0, stream, true, ws.tile_sums.p, ntiles, ws.total.p, (const uint32_t*)raw_sums, K, left_sums);
+        // batch-affine path: counts <- leftover offsets, cursor64 <- placement words; otherwise counts <- write cursors
+        G16_LAUNCH(scan_tiles, (unsigned)ntiles, SCAN_T, 0, stream, true, ws.counts.p, nbuckets, ws.tile_sums.p, ws.counts.p, pad_mask, pad_t,
+                   (const uint32_t*)left_sums, cursor64 ? ws.cursor64.p : (unsigned long long*)nullptr);
     }
     // the XYZZ accumulation (and the merge levels after it) walk ws.entries with the live length at `acc_total`
     const uint32_t* acc_total = ws.total.p + (K ? 2 : 0);
@@ -787,7 +894,7 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
         if (tm) tm->mark(ST_MSM_ACC, stream);
         auto k = msm_accumulate_kernel<C>;
         G16_LAUNCH(k, div_up(max_chunks, 128), 128, 0, stream, false, bases, ws.entries.p, acc_total, L, ws.buckets.p,
-                   ws.part_val[0].p, ws.part_key[0].p);
+                   ws.part_val[0].p, ws.part_key[0].p, (const typename C::A*)nullptr);
         ws.launches += 6;
     } else {
         G16_CUDA(cudaMemsetAsync(ws.ba_refs.p, 0xFF, max_slots * sizeof(uint32_t), stream));   // padding slots stay null references
@@ -796,7 +903,7 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
                        ws.counts.p, row_tot, (const uint32_t*)row_base, ws.entries.p, ws.ba_refs.p, K);
         else
             G16_LAUNCH(msm_digits_kernel, div_up(nthreads, 256), 256, 0, stream, false, sh, scalars, row_stride, elem_stride, map, is_mont, 2,
-                       ws.counts.p, ws.entries.p, ws.ba_refs.p, K);
+                       ws.counts.p, ws.entries.p, ws.ba_refs.p, K, cursor64 ? ws.cursor64.p : (unsigned long long*)nullptr);
         G16_CHECK_LAUNCH();
         if (tm) tm->mark(ST_MSM_ACC, stream);
         if (getenv("G16_MSM_BA_TRACE")) fprintf(stderr, "[msm] batch-affine K=%d rows=%u n=%u c=%d max_slots=%zu\n", K, sh.rows, sh.n, sh.c, max_slots);
@@ -804,20 +911,21 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
         // one group sum per 2^K slots is left: the sorted-run accumulation over (bucket, group) keys finishes the buckets
         auto k = msm_accumulate_kernel<C>;
         G16_LAUNCH(k, div_up(max_chunks, 128), 128, 0, stream, false, (const typename C::A*)ws.ba_lvl[K - 1].p, ws.entries.p, acc_total, L,
-                   ws.buckets.p, ws.part_val[0].p, ws.part_key[0].p);
+                   ws.buckets.p, ws.part_val[0].p, ws.part_key[0].p, bases);
         ws.launches += 6 + 3 * K;
     }
     if (tm) tm->mark(ST_MSM_REDUCE, stream);
     msm_merge_partials<C>(ws, acc_total, L, n_l0, ws.buckets.p, stream);
     G16_CHECK_LAUNCH();
-    if (ws.entry_log.n < 2 * (ws.log_n + 1)) {   // grow the log (rare; keeps old values)
-        DevBuf<uint32_t> bigger((ws.log_n + 1) * 4 + 64);
-        if (ws.log_n) G16_CUDA(cudaMemcpyAsync(bigger.p, ws.entry_log.p, ws.log_n * 8, cudaMemcpyDeviceToDevice, stream));
+    if (ws.entry_log.n < 3 * (ws.log_n + 1)) {   // grow the log (rare; keeps old values)
+        DevBuf<uint32_t> bigger((ws.log_n + 1) * 6 + 96);
+        if (ws.log_n) G16_CUDA(cudaMemcpyAsync(bigger.p, ws.entry_log.p, ws.log_n * 12, cudaMemcpyDeviceToDevice, stream));
         G16_CUDA(cudaStreamSynchronize(stream));
         ws.entry_log = std::move(bigger);
     }
-    G16_CUDA(cudaMemcpyAsync(ws.entry_log.p + 2 * ws.log_n, ws.total.p + 1, 4, cudaMemcpyDeviceToDevice, stream));      // entries = additions
-    G16_CUDA(cudaMemcpyAsync(ws.entry_log.p + 2 * ws.log_n + 1, ws.total.p, 4, cudaMemcpyDeviceToDevice, stream));     // sorted slots
+    G16_CUDA(cudaMemcpyAsync(ws.entry_log.p + 3 * ws.log_n, ws.total.p + 1, 4, cudaMemcpyDeviceToDevice, stream));      // entries = additions
+    G16_CUDA(cudaMemcpyAsync(ws.entry_log.p + 3 * ws.log_n + 1, ws.total.p, 4, cudaMemcpyDeviceToDevice, stream));     // sorted slots
+    G16_CUDA(cudaMemcpyAsync(ws.entry_log.p + 3 * ws.log_n + 2, ws.total.p + (K ? 2 : 1), 4, cudaMemcpyDeviceToDevice, stream));   // XYZZ accumulation entries
     ws.log_n++;
     ws.last_K = K;
     // reduction tree. Arity 32 minimises the work (2 + 3/32 additions per bucket) and is used whenever its first level

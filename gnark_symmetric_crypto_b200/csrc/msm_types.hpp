@@ -28,23 +28,25 @@ struct MsmWorkspace {
     DevBuf<X> buckets, part_val[2], lvlR[2], lvlV[2], result;
     // batch-affine path (G1, msm_ba.cuh): padded point references, one level buffer per pairwise level, running products
     DevBuf<uint32_t> ba_refs;
+    DevBuf<unsigned long long> cursor64;   // placement word per bucket (msm.cuh msm_ba_place)
     DevBuf<typename C::A> ba_lvl[3];
     DevBuf<typename C::F> ba_scratch;
     size_t launches = 0;
-    // per run since log_reset(): two words — the number of entries (= bucket additions, the algorithmic work) and the number of
-    // sorted slots (entries + the padding of the batch-affine path; equal without it)
+    // per run since log_reset(): three words — the number of entries (= bucket additions, the algorithmic work), the number of
+    // sorted slots (entries in runs + the padding of the batch-affine path; equal to the entries without it) and the number of
+    // entries the XYZZ accumulation walks (group sums + direct leftovers; the entries without the batch-affine path)
     DevBuf<uint32_t> entry_log;
     size_t log_n = 0;
     int last_K = 0;   // batch-affine levels of the last run (0 = XYZZ accumulation only)
     bool no_ba = false;   // set by the caller for queries whose live entries are far below the upper bound (mostly 0 / +-1 scalars)
     void log_reset() { log_n = 0; }
-    uint64_t log_sum(cudaStream_t st, int word = 0) {   // synchronises the stream; word 0 = entries, 1 = slots
+    uint64_t log_sum(cudaStream_t st, int word = 0) {   // synchronises the stream; word 0 = entries, 1 = slots, 2 = XYZZ entries
         if (!log_n) return 0;
-        std::vector<uint32_t> h(2 * log_n);
-        entry_log.download(h.data(), 2 * log_n, st);
+        std::vector<uint32_t> h(3 * log_n);
+        entry_log.download(h.data(), 3 * log_n, st);
         G16_CUDA(cudaStreamSynchronize(st));
         uint64_t s = 0;
-        for (size_t i = 0; i < log_n; i++) s += h[2 * i + word];
+        for (size_t i = 0; i < log_n; i++) s += h[3 * i + word];
         return s;
     }
 };

@@ -333,6 +333,9 @@ class Groth16Context:
         out["z_sorted_slots"] = int(e[8])     # Z-query entries + batch-affine padding
         out["z_batch_affine_levels"] = int(e[9])
         out["z_buckets"] = int(e[10])
+        out["z_xyzz_entries"] = int(e[13])    # what the XYZZ accumulation of the Z query walks: group sums + direct leftovers
+        out["bitq_state"] = int(e[11]) & 0xFF  # combination tables of the wire queries: 0 learning, 1 in use, 2 off
+        out["bitq_live"] = bool((int(e[11]) >> 8) & 1)
         return out
 
     # ---- stage-level
