@@ -38,7 +38,7 @@ BATCH = 1024
 METRIC = "ChaCha20-V3 Groth16 proofs/sec"
 UNIT = "proofs/s"
 IMAD_PER_MADD_G1 = 2640      # 10 modmul x 264 IMAD
-BA_ADD_L0_TRAFFIC = 20.19e9   # dram__bytes_read.sum + dram__bytes_write.sum of msm_ba_add_kernel level 0 (profiles/ncu_msm_ba_add_r02_final.txt)
+BA_ADD_L0_TRAFFIC = 17.39e9   # dram__bytes_read.sum + dram__bytes_write.sum of msm_ba_add_kernel level 0 (profiles/ncu_msm_ba_add_r02_final.txt)
 WORKLOAD = "batched ChaCha20-V3 Groth16 BN254 proofs, 1024 synthetic key/nonce/counter/input requests per GPU (BASELINE config 4)"
 R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617   # BN254 group order
 

@@ -98,6 +98,8 @@ struct Ctx {
     size_t launches = 0;
     uint64_t counters[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t sub_batch = 512;
+    size_t solve_chains = 2;           // G16_SOLVE_CHAINS: concurrent solver chains of mode 2 (2 = one per sub-batch on the two streams)
+    std::vector<cudaStream_t> solve_streams;
     int split_solve = 0;               // G16_SPLIT_SOLVE: 1 = later sub-batches solved on the side stream behind the first one's transforms, 2 = all sub-batches solved concurrently (ctx_run_batch)
     bool tables_ready = false;
     SolverGraphCache* solver_graphs = nullptr;
@@ -128,6 +130,7 @@ struct Ctx {
         if (ev_t0) cudaEventDestroy(ev_t0);
         if (ev_t1) cudaEventDestroy(ev_t1);
         for (auto e : ev_solved) cudaEventDestroy(e);
+        for (auto s : solve_streams) cudaStreamDestroy(s);
         if (stream3) cudaStreamDestroy(stream3);
         if (stream2) cudaStreamDestroy(stream2);
         if (stream) cudaStreamDestroy(stream);
@@ -263,6 +266,8 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     cx->eval_z = env_int("G16_EVAL_Z", -1);
     cx->eval_z_min = (uint32_t)env_int("G16_EVAL_Z_MIN", 128);
     if (cx->sub_batch == 0) cx->sub_batch = 1;
+    cx->solve_chains = (size_t)env_int("G16_SOLVE_CHAINS", 2);
+    if (cx->solve_chains < 2 || cx->solve_chains > 16) cx->solve_chains = 2;
     cx->split_solve = env_int("G16_SPLIT_SOLVE", -1);   // -1: decided once the circuit is known (below)
     cx->bitq_state = env_int("G16_BITQ", 1) ? 0 : 2;
     cx->bitq_min_rows = (uint32_t)env_int("G16_BITQ_MIN_ROWS", 256);
@@ -781,6 +786,25 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
         const bool split_solve = n > cx.sub_batch && cx.split_solve == 1;
         const bool par_solve = n > cx.sub_batch && cx.split_solve == 2;
         const uint32_t rows0 = (split_solve || par_solve) ? (uint32_t)cx.sub_batch : (uint32_t)n;
+        if (par_solve && cx.solve_chains > 2 && !cx.n_commit) {
+            // more than two chains (G16_SOLVE_CHAINS): the rows are cut into equal parts, one stream each
+            const size_t P = cx.solve_chains;
+            const size_t part = ((n + P - 1) / P + 31) / 32 * 32;
+            while (cx.solve_streams.size() + 3 < P) { cudaStream_t s; G16_CUDA(cudaStreamCreate(&s)); cx.solve_streams.push_back(s); }
+            G16_CUDA(cudaEventRecord(cx.ev_fork, st));   // witness assignment done
+            size_t k = 0;
+            for (size_t c = 1; c * part < n; c++, k++) {
+                cudaStream_t s = c == 1 ? st2 : (c == 2 ? cx.stream3 : cx.solve_streams[c - 3]);
+                const size_t sb = c * part;
+                const uint32_t rows = (uint32_t)((n - sb) < part ? (n - sb) : part);
+                G16_CUDA(cudaStreamWaitEvent(s, cx.ev_fork, 0));
+                own += ctx_solve(cx, n, sb, rows, s, cx.ws1b);
+                if (cx.ev_solved.size() <= k) { cudaEvent_t e; G16_CUDA(cudaEventCreate(&e)); cx.ev_solved.push_back(e); }
+                G16_CUDA(cudaEventRecord(cx.ev_solved[k], s));
+            }
+            own += ctx_solve(cx, n, 0, (uint32_t)(part < n ? part : n), st, cx.ws1c);
+            for (size_t i = 0; i < k; i++) G16_CUDA(cudaStreamWaitEvent(st, cx.ev_solved[i], 0));
+        } else {
         if (par_solve) {
             G16_CUDA(cudaEventRecord(cx.ev_fork, st));   // witness assignment done
             G16_CUDA(cudaStreamWaitEvent(st2, cx.ev_fork, 0));
@@ -794,6 +818,7 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
         }
         own += ctx_solve(cx, n, 0, rows0, st, par_solve ? cx.ws1c : cx.ws1b);
         if (par_solve) G16_CUDA(cudaStreamWaitEvent(st, cx.ev_solved[0], 0));
+        }
         G16_CUDA(cudaEventRecord(cx.ev_fork, st));
         G16_CUDA(cudaStreamWaitEvent(st2, cx.ev_fork, 0));
         if (split_solve) {

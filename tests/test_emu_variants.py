@@ -14,8 +14,9 @@ ROOT = Path(__file__).resolve().parent.parent
 @pytest.mark.parametrize("env", [
     {"G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "1", "G16_MSM_TREE_BLOCK": "0"},
     {"G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "3", "G16_BA_INV2_MIN": "1"},
+    {"G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "2", "G16_MSM_BA_LEFT": "3"},
     {"G16_MSM_ROWSORT": "2", "G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "2"},
-], ids=["batch_affine_k1_serial_tree", "batch_affine_k3_two_level_inversion", "rowsort_batch_affine_k2"])
+], ids=["batch_affine_k1_serial_tree", "batch_affine_k3_two_level_inversion", "batch_affine_k2_leftovers_3", "rowsort_batch_affine_k2"])
 def test_msm_variants_on_emulation(emu, env):
     out = subprocess.run([sys.executable, "-m", "pytest", "tests/test_emu.py", "-q", "-x", "-k", "msm", "-p", "no:cacheprovider"],
                          capture_output=True, text=True, env=dict(os.environ, **env), cwd=str(ROOT), timeout=1200)

@@ -250,16 +250,19 @@ def test_verifier_rejects_noncanonical_coordinates(G, oracle, kat):
     {"G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "1"},
     {"G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "2"},
     {"G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "3", "G16_BA_INV2_MIN": "1"},
+    {"G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "3", "G16_MSM_BA_LEFT": "0"},
     {"G16_MSM_ROWSORT": "2"},
     {"G16_MSM_ROWSORT": "2", "G16_MSM_BA_MIN": "1", "G16_MSM_BA_K": "3"},
     {"G16_MSM_ROWSORT": "0", "G16_MSM_BA": "0"},
-], ids=["batch_affine_k1", "batch_affine_k2", "batch_affine_k3_two_level_inversion", "rowsort", "rowsort_batch_affine_k3", "round1_paths"])
+], ids=["batch_affine_k1", "batch_affine_k2", "batch_affine_k3_two_level_inversion", "batch_affine_k3_plain_padding", "rowsort", "rowsort_batch_affine_k3", "round1_paths"])
 def test_msm_paths_forced_on_small_and_edge_cases(env):
     """The batch-affine pairwise levels (csrc/msm_ba.cuh; gnark's own bucket-addition algorithm, multiexp_affine.go:35-176)
     normally start at 2^21 entries and the per-row shared-memory sort at 32 rows. Here they are forced onto the existing small
     MSM parity tests — sizes 1 to 2^16 against the oracle, zeros, +-1 runs, duplicate points (the doubling branch), P + (-P),
     points at infinity, fixed-base tables, the KAT proof and a 37-request batch — in a child process (the switches are read
-    once per process). The last variant switches both off: the round-1 paths stay correct."""
+    once per process). By default a bucket's remainder of <= 5 (K = 3) or <= 2 (K = 2) entries skips the levels (direct
+    leftovers, 64-bit placement cursor); one variant restores the plain padding. The last variant switches both off: the round-1
+    paths stay correct."""
     import subprocess
     import sys
     out = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu.py", "tests/test_gpu_round2.py", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
