@@ -30,6 +30,11 @@
 namespace g16 {
 
 static const uint32_t BA_NULL = 0xFFFFFFFFu;   // reference of a padding slot
+// G16_BA_PREFETCH=1: the addition kernel requests the references and the running product of its next pair one iteration ahead.
+// MEASURED ON B200 AND NOT THE DEFAULT: 92 instead of 88 registers, step 130.15 vs 129.73 ms — the kernel is not waiting on those loads.
+#ifndef G16_BA_PREFETCH
+#define G16_BA_PREFETCH 0
+#endif
 enum { BA_ADD = 0, BA_DBL = 1, BA_INF = 2, BA_COPYP = 3, BA_COPYQ = 4 };
 
 FD Fp ba_load_fp(const Fp* p) {
@@ -228,15 +233,45 @@ msm_ba_add_kernel(const G1Affine* __restrict__ src, const uint32_t* __restrict__
     int m = (int)((npairs - q0 + T - 1) / T);   // this thread's pairs: j < m
     if (m > M) m = M;
     Fp R = totinv[(size_t)blockIdx.x * T + threadIdx.x];   // 1 / (d_0 ... d_(m-1))
+#if G16_BA_PREFETCH
+    // the references of pair j - 1 and its running product are requested while pair j is computed: at level 0 the points are
+    // two dependent loads away (reference, then table point), and the loop is not unrolled
+    uint32_t nr1 = 0, nr2 = 0;
+    Fp ncprev = Fp::one();
+    {
+        const size_t q = q0 + (size_t)(m - 1) * T;
+        if (LEVEL0) { nr1 = refs[2 * q]; nr2 = refs[2 * q + 1]; }
+        if (m > 1) ncprev = ba_load_fp(&pre[q - T]);
+    }
+#endif
 #pragma unroll 1
     for (int j = m - 1; j >= 0; j--) {
         const size_t q = q0 + (size_t)j * T;
+#if G16_BA_PREFETCH
+        const Fp cprev = ncprev;
+        uint32_t r1 = nr1, r2 = nr2;
+        if (j > 0) {
+            const size_t qn = q - T;
+            if (LEVEL0) { nr1 = refs[2 * qn]; nr2 = refs[2 * qn + 1]; }
+            ncprev = j > 1 ? ba_load_fp(&pre[qn - T]) : Fp::one();
+        }
+        const Fp inv = cprev * R;    // 1 / d_j
+        Fp x1, x2, d;
+        if (LEVEL0) {
+            x1 = r1 == BA_NULL ? Fp::zero() : ba_load_fp(&src[r1 >> 1].x);
+            x2 = r2 == BA_NULL ? Fp::zero() : ba_load_fp(&src[r2 >> 1].x);
+        } else {
+            x1 = ba_load_fp(&src[2 * q].x);
+            x2 = ba_load_fp(&src[2 * q + 1].x);
+        }
+#else
         const Fp cprev = j ? pre[q - T] : Fp::one();
         const Fp inv = cprev * R;    // 1 / d_j
         Fp x1, x2, d;
         uint32_t r1, r2;
         ba_load_x<LEVEL0>(src, refs, 2 * q, x1, r1);
         ba_load_x<LEVEL0>(src, refs, 2 * q + 1, x2, r2);
+#endif
         const Fp y1 = ba_load_y<LEVEL0>(src, 2 * q, r1), y2 = ba_load_y<LEVEL0>(src, 2 * q + 1, r2);
         const int kind = ba_classify(x1, y1, x2, y2, d);
         R = R * d;
