@@ -32,6 +32,11 @@ namespace g16 {
 static const uint32_t BA_NULL = 0xFFFFFFFFu;   // reference of a padding slot
 // G16_BA_PREFETCH=1: the addition kernel requests the references and the running product of its next pair one iteration ahead.
 // MEASURED ON B200 AND NOT THE DEFAULT: 92 instead of 88 registers, step 130.15 vs 129.73 ms — the kernel is not waiting on those loads.
+#ifndef G16_BA_ADD_THREADS
+#define G16_BA_ADD_THREADS 768   // resident threads per SM the addition kernel is compiled for: 768 (80 registers, 28 bytes of
+                                 // spills) against 640 (88 registers): accumulate stage 69.9 vs 70.4 ms per 1024 proofs; 64 pairs per
+                                 // thread instead of 32: 70.7 ms (profiles/sweep_r02_add_occupancy.jsonl)
+#endif
 #ifndef G16_BA_PREFETCH
 #define G16_BA_PREFETCH 0
 #endif
@@ -224,7 +229,7 @@ msm_ba_inv_bwd_kernel(const uint32_t* __restrict__ total_slots, int shift, const
 }
 
 template <bool LEVEL0, int T, int M>
-__global__ void __launch_bounds__(T, 640 / T)
+__global__ void __launch_bounds__(T, G16_BA_ADD_THREADS / T)
 msm_ba_add_kernel(const G1Affine* __restrict__ src, const uint32_t* __restrict__ refs, const uint32_t* __restrict__ total_slots,
                   int shift, const Fp* __restrict__ pre, const Fp* __restrict__ totinv, G1Affine* __restrict__ out) {
     const size_t npairs = ((size_t)(*total_slots) >> shift) >> 1;
