@@ -359,13 +359,18 @@ def run_gpu(args):
         prs = [ref_proofs[j * ctx.proof_bytes:(j + 1) * ctx.proof_bytes].tobytes() for j in range(n)]
         okv = np.zeros(n, dtype=np.uint8)
         ms_v = ctypes.c_float(0)
-        rc = L.g16_verify_batch(ver._h, n, ref_proofs.ctypes.data_as(u8p), pub.ctypes.data_as(ctypes.c_void_p), 1,
-                                okv.ctypes.data_as(u8p), ctypes.byref(ms_v))
-        if rc:
-            raise RuntimeError(L.g16_last_error().decode())
-        assert int(okv.sum()) == n and len(set(prs)) == n, "a proof of the measured batch was rejected by the verifier"
-        verified = {"proofs": n, "accepted": int(okv.sum()), "device_ms": float(ms_v.value), "key": "vk.chacha20 (the reference's)",
-                    "path": "g16_verify_batch (GPU pairing check, one verdict per proof)"}
+        first_ms = None
+        for attempt in range(2):   # the first call on a fresh verifier context also pays for its device buffers (cudaMalloc inside the interval)
+            rc = L.g16_verify_batch(ver._h, n, ref_proofs.ctypes.data_as(u8p), pub.ctypes.data_as(ctypes.c_void_p), 1,
+                                    okv.ctypes.data_as(u8p), ctypes.byref(ms_v))
+            if rc:
+                raise RuntimeError(L.g16_last_error().decode())
+            assert int(okv.sum()) == n and len(set(prs)) == n, "a proof of the measured batch was rejected by the verifier"
+            if attempt == 0:
+                first_ms = float(ms_v.value)
+        verified = {"proofs": n, "accepted": int(okv.sum()), "device_ms": float(ms_v.value), "first_call_ms": first_ms,
+                    "key": "vk.chacha20 (the reference's)",
+                    "path": "g16_verify_batch (GPU pairing check, one verdict per proof); device_ms is the second call, first_call_ms includes the buffer allocations"}
         ver.close()
     barrier()
 
