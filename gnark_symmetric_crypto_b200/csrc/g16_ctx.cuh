@@ -90,6 +90,8 @@ struct Ctx {
     cudaStream_t stream3 = nullptr;   // lane 1 of the pipelined schedule
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     std::vector<cudaEvent_t> ev_solved;   // one per sub-batch: witness complete
+    std::vector<cudaEvent_t> ev_hdone;    // pipelined schedule: transforms of sub-batch k done
+    bool pipeline_stagger = true;         // G16_PIPE_STAGGER
     int pipeline = 0;                 // 1: sub-batches alternate between two lanes (streams); 0: one main stream, stage timers
     DevBuf<G1XYZZ> resA, resB1, resK, resZ;
     DevBuf<G2XYZZ> resB2;
@@ -130,6 +132,7 @@ struct Ctx {
         if (ev_t0) cudaEventDestroy(ev_t0);
         if (ev_t1) cudaEventDestroy(ev_t1);
         for (auto e : ev_solved) cudaEventDestroy(e);
+        for (auto e : ev_hdone) cudaEventDestroy(e);
         for (auto s : solve_streams) cudaStreamDestroy(s);
         if (stream3) cudaStreamDestroy(stream3);
         if (stream2) cudaStreamDestroy(stream2);
@@ -258,14 +261,18 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     G16_CUDA(cudaEventCreate(&cx->ev_t0));
     G16_CUDA(cudaEventCreate(&cx->ev_t1));
     cudaStream_t st = cx->stream;
-    // Measured on B200 (1024 ChaCha proofs): single stream 189.9 ms; two lanes 191.3 / 198.6 / 214.9 ms at sub-batch
-    // 512 / 256 / 128. The bucket-accumulation and NTT kernels fill every SM's register file, so kernels of the other
-    // lane only time-slice with them; the pipelined schedule stays available (G16_PIPELINE=1) but is not the default.
-    cx->pipeline = env_int("G16_PIPELINE", 0);
+    // Round 1, measured on B200 (1024 ChaCha proofs): single stream 189.9 ms; two lanes 191.3 / 198.6 / 214.9 ms at sub-batch
+    // 512 / 256 / 128 — the bucket-accumulation and NTT kernels filled every SM's register file, so kernels of the other
+    // lane only time-sliced with them. End of round 2 (evaluation-basis Z query in both lanes, lighter kernels): two lanes
+    // 125.9 ms against 128.9 ms on one main stream (sub-batch 384 / 342 / 256: 129.2 / 129.1 / 131.2), so circuits without a
+    // commitment now default to the two lanes (G16_PIPELINE=0 / 1 forces; the stage timers only exist on the single stream,
+    // g16_set_schedule switches per context).
+    cx->pipeline = env_int("G16_PIPELINE", -1);
     cx->sub_batch = (uint32_t)env_int("G16_SUBBATCH", 512);
     cx->eval_z = env_int("G16_EVAL_Z", -1);
     cx->eval_z_min = (uint32_t)env_int("G16_EVAL_Z_MIN", 128);
     if (cx->sub_batch == 0) cx->sub_batch = 1;
+    cx->pipeline_stagger = env_int("G16_PIPE_STAGGER", 1) != 0;
     cx->solve_chains = (size_t)env_int("G16_SOLVE_CHAINS", 2);
     if (cx->solve_chains < 2 || cx->solve_chains > 16) cx->solve_chains = 2;
     cx->split_solve = env_int("G16_SPLIT_SOLVE", -1);   // -1: decided once the circuit is known (below)
@@ -292,6 +299,7 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     // concurrent solves of the sub-batches (135.0 -> 134.4 ms per 1024 ChaCha proofs); circuits with a commitment keep the
     // single chain (their solve includes a Pedersen MSM per sub-batch)
     if (cx->split_solve < 0) cx->split_solve = cx->n_commit ? 0 : 2;
+    if (cx->pipeline < 0) cx->pipeline = cx->n_commit ? 0 : 1;
 
     // ---- decompress the key on the GPU (~89k Fp + 12.5k Fp2 square roots)
     DevBuf<uint32_t> err(1);
@@ -744,7 +752,7 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     // evaluation-basis Z query (no commitment circuits only: their C evaluations are mostly full-width)
     // Not for the commitment (AES) circuits: their C evaluations are largely full-width, measured 1 112 vs 1 090 proofs/s.
     // Not when the caller asked for the coefficients of H (g16_prove_witness_detail).
-    const bool eval_z = !cx.n_commit && !cx.pipeline && !cx.want_h && (cx.eval_z > 0 || (cx.eval_z < 0 && n >= cx.eval_z_min));
+    const bool eval_z = !cx.n_commit && !cx.want_h && (cx.eval_z > 0 || (cx.eval_z < 0 && n >= cx.eval_z_min));
     if (eval_z) ctx_build_eval_tables(cx);
     StageTimer& tm = cx.timer;
     tm.reset();
@@ -868,10 +876,21 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
             if (cx.ev_solved.size() <= k) { cudaEvent_t e; G16_CUDA(cudaEventCreate(&e)); cx.ev_solved.push_back(e); }
             G16_CUDA(cudaEventRecord(cx.ev_solved[k], s));
             G16_CUDA(cudaStreamWaitEvent(st2, cx.ev_solved[k], 0));
-            ctx_wire_queries(cx, n, sb, rows, st2);
+            ctx_wire_queries(cx, n, sb, rows, st2, eval_z);
             Fr* a = cx.Aev.p + sb * cx.n_dom;
-            compute_h_run(cx.dom, a, cx.Bev.p + sb * cx.n_dom, cx.Cev.p + sb * cx.n_dom, cx.n_dom, rows, s);
-            run_query_g1(wz, s, cx.qZ, a, cx.n_dom, 1, false, rows, cx.resZ.p + sb, nullptr);
+            // stagger the lanes: the transforms of this sub-batch start when those of the one before are done, so that they
+            // run beside its digit sort (L2 atomics, no multiplier) and this sub-batch's sort beside its bucket additions
+            if (k > 0 && cx.pipeline_stagger) G16_CUDA(cudaStreamWaitEvent(s, cx.ev_hdone[k - 1], 0));
+            if (eval_z) compute_d_run(cx.dom, a, cx.Bev.p + sb * cx.n_dom, cx.n_dom, rows, s);
+            else compute_h_run(cx.dom, a, cx.Bev.p + sb * cx.n_dom, cx.Cev.p + sb * cx.n_dom, cx.n_dom, rows, s);
+            if (cx.ev_hdone.size() <= k) { cudaEvent_t e; G16_CUDA(cudaEventCreate(&e)); cx.ev_hdone.push_back(e); }
+            G16_CUDA(cudaEventRecord(cx.ev_hdone[k], s));
+            run_query_g1(wz, s, eval_z ? cx.qQd : cx.qZ, a, cx.n_dom, 1, false, rows, cx.resZ.p + sb, nullptr);
+        }
+        if (bitq_profiling) {   // the side stream has waited for every sub-batch's witness by now
+            cx.d_bit_flags.ensure(cx.nb_wires);
+            G16_CUDA(cudaMemsetAsync(cx.d_bit_flags.p, 3, cx.nb_wires * sizeof(uint32_t), st2));
+            bitq_profile(cx.W.p, n, cx.nb_wires, (uint32_t)n, cx.d_bit_flags.p, st2);
         }
         G16_CUDA(cudaEventRecord(cx.ev_join3, lane[1]));
         G16_CUDA(cudaStreamWaitEvent(st, cx.ev_join3, 0));
@@ -903,7 +922,7 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     cx.stage_ms[7] = (float)cx.launches;
     G16_CUDA(cudaStreamSynchronize(st2));
     G16_CUDA(cudaStreamSynchronize(cx.stream3));
-    if (bitq_profiling && !piped && !(status & 7u)) {
+    if (bitq_profiling && !(status & 7u)) {
         std::vector<uint32_t> f(cx.nb_wires);
         cx.d_bit_flags.download(f.data(), cx.nb_wires, st);
         G16_CUDA(cudaStreamSynchronize(st));

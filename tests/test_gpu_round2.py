@@ -318,6 +318,29 @@ def test_bit_wire_tables_leave_the_proofs_unchanged(G, oracle, pk_bytes, r1cs_by
     ctx.close()
 
 
+def test_two_lane_schedule_matches_the_single_stream(G, pk_bytes, r1cs_bytes, monkeypatch):
+    """Circuits without a commitment default to the two-lane schedule for batches above one sub-batch (sub-batch k runs its chain
+    solve -> transforms -> Z query on lane k % 2). Forced here with sub-batches of 16: 40 requests = three sub-batches over two
+    lanes, compared byte for byte with the single main stream (g16_set_schedule), with the combination tables learned in
+    between (the classification is also taken in the two-lane path)."""
+    monkeypatch.setenv("G16_SUBBATCH", "16")
+    monkeypatch.setenv("G16_BITQ_MIN_ROWS", "40")
+    monkeypatch.setenv("G16_BITQ_MIN_BATCH", "8")
+    keys, nonces, ctrs, ins, rs = batch_inputs(40, seed=b"g16-b200-lanes")
+    ctx = G.Groth16Context(pk_bytes, r1cs_bytes)
+    p1, c1 = ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)
+    cn = ctx.counters()
+    assert cn["pipelined"] and cn["sub_batch"] == 16 and cn["bitq_state"] == 0
+    p2, _ = ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)             # two lanes + combination tables
+    cn = ctx.counters()
+    assert cn["pipelined"] and cn["bitq_live"]
+    ctx.set_schedule(False, 16)
+    p3, c3 = ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)
+    assert not ctx.counters()["pipelined"]
+    assert p1 == p2 == p3 and c1 == c3
+    ctx.close()
+
+
 # ---------------------------------------------------------------------------------------------- product-side Setup (8f rank 1)
 def test_setup_reproduces_oracle_keys_byte_for_byte(G, oracle):
     """g16_setup (QAP evaluation on the host, every key element a fixed-base product on the GPU) against the oracle's Setup
