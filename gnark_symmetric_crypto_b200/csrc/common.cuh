@@ -53,8 +53,8 @@ struct DevBuf {
     }
     void alloc(size_t count) {
         release();
+        if (count) G16_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));   // on failure the buffer stays empty (n = 0)
         n = count;
-        if (count) G16_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
     }
     void ensure(size_t count) { if (count > n) alloc(count); }
     void upload(const T* h, size_t count, cudaStream_t s = 0) {

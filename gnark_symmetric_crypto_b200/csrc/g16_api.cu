@@ -332,7 +332,19 @@ static int batch_run_one(g16_ctx* ctx, float* ms) {
         Ctx& c = *ctx->cx;
         REQUIRE(c.staged > 0 && c.staged_kind != 0, "no staged request batch");
         G16_CUDA(cudaSetDevice(c.device));
-        float t = ctx_run_batch(c, c.staged, c.staged_kind);
+        float t;
+        try {
+            t = ctx_run_batch(c, c.staged, c.staged_kind);
+        } catch (const CudaError& e) {
+            // the second lane's scratch (another ~28 GB for a 512-proof sub-batch) did not fit next to whatever else lives on this
+            // GPU: give it back and prove the batch on the single main stream from now on
+            if (!c.pipeline || !strstr(e.what(), "out of memory")) throw;
+            cudaGetLastError();
+            cudaDeviceSynchronize();
+            c.ws1c = MsmWorkspace<G1>();
+            c.pipeline = 0;
+            t = ctx_run_batch(c, c.staged, c.staged_kind);
+        }
         if (ms) *ms = t;
     });
 }

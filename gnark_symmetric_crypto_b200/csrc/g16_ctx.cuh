@@ -92,6 +92,7 @@ struct Ctx {
     std::vector<cudaEvent_t> ev_solved;   // one per sub-batch: witness complete
     std::vector<cudaEvent_t> ev_hdone;    // pipelined schedule: transforms of sub-batch k done
     bool pipeline_stagger = true;         // G16_PIPE_STAGGER
+    bool test_lane_oom = false;           // G16_TEST_LANE_OOM
     int pipeline = 0;                 // 1: sub-batches alternate between two lanes (streams); 0: one main stream, stage timers
     DevBuf<G1XYZZ> resA, resB1, resK, resZ;
     DevBuf<G2XYZZ> resB2;
@@ -273,6 +274,7 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     cx->eval_z_min = (uint32_t)env_int("G16_EVAL_Z_MIN", 128);
     if (cx->sub_batch == 0) cx->sub_batch = 1;
     cx->pipeline_stagger = env_int("G16_PIPE_STAGGER", 1) != 0;
+    cx->test_lane_oom = env_int("G16_TEST_LANE_OOM", 0) != 0;
     cx->solve_chains = (size_t)env_int("G16_SOLVE_CHAINS", 2);
     if (cx->solve_chains < 2 || cx->solve_chains > 16) cx->solve_chains = 2;
     cx->split_solve = env_int("G16_SPLIT_SOLVE", -1);   // -1: decided once the circuit is known (below)
@@ -871,6 +873,10 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
         // phases of one sub-batch (solver levels, bucket sort, reduction trees) overlap the integer-multiply-bound phases
         // (NTT, bucket accumulation) of the other lane; the wire-driven queries follow on the side stream as soon as the
         // sub-batch's witness is complete. Stage timers are meaningless here: only the total is measured.
+        if (cx.test_lane_oom) {   // G16_TEST_LANE_OOM=1: what an allocation failure of the second lane's scratch looks like (tests of the fallback)
+            cx.test_lane_oom = false;
+            throw CudaError("cudaMalloc: out of memory (G16_TEST_LANE_OOM)");
+        }
         cudaStream_t lane[2] = {st, cx.stream3};
         MsmWorkspace<G1>* wsz[2] = {&cx.ws1, &cx.ws1c};
         G16_CUDA(cudaEventRecord(cx.ev_fork, st));

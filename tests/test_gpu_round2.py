@@ -339,6 +339,14 @@ def test_two_lane_schedule_matches_the_single_stream(G, pk_bytes, r1cs_bytes, mo
     assert not ctx.counters()["pipelined"]
     assert p1 == p2 == p3 and c1 == c3
     ctx.close()
+    # the second lane's scratch does not fit (simulated): the batch is proved on the single stream, which stays the schedule
+    monkeypatch.setenv("G16_TEST_LANE_OOM", "1")
+    ctx = G.Groth16Context(pk_bytes, r1cs_bytes)
+    p4, _ = ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)
+    assert p4 == p1 and not ctx.counters()["pipelined"]
+    p5, _ = ctx.prove_chacha_batch(keys, nonces, ctrs, ins, rs)
+    assert p5 == p1 and not ctx.counters()["pipelined"]
+    ctx.close()
 
 
 # ---------------------------------------------------------------------------------------------- product-side Setup (8f rank 1)
