@@ -703,11 +703,11 @@ int g16_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64
 }
 int g16_group_op(int group, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
     return guarded([&] {
-        REQUIRE(a && out && (group == 1 || group == 2) && op >= 0 && op <= 3, "bad argument");
+        REQUIRE(a && out && (group == 1 || group == 2) && op >= 0 && op <= (group == 1 ? 5 : 3), "bad argument");
         REQUIRE(b || op == 2, "op needs b");
         require_device();
         size_t pw = group == 1 ? 8 : 16;
-        size_t bw = (op == 0 || op == 3) ? pw : 4;
+        size_t bw = (op == 0 || op >= 3) ? pw : 4;
         DevBuf<uint64_t> da, db, dout(pw * n);
         da.upload(a, pw * n);
         if (b) db.upload(b, bw * n);

@@ -1,5 +1,6 @@
 // Hot translation unit: G1 half of the proof assembly (assemble.cuh) with the Montgomery product inlined.
 #include "assemble.cuh"
+#include <cstdlib>
 
 namespace g16 {
 
@@ -11,8 +12,18 @@ void launch_fixed_base_table_g1(const G1Affine& base, G1Affine* tab, cudaStream_
 size_t launch_assemble(const AssemblyKeys& keys, AssemblyScratch& sc, bool with_commitment, uint32_t n, const G1XYZZ* mA,
                        const G1XYZZ* mB1, const G1XYZZ* mK, const G1XYZZ* mZ, const Fr* rs, uint8_t* out, size_t out_stride,
                        cudaStream_t st) {
-    sc.Ar.ensure(n); sc.Bs1.ensure(n); sc.nrsd.ensure(n); sc.win_tab.ensure((size_t)n * 4 * 15);
+    sc.Ar.ensure(n); sc.Bs1.ensure(n); sc.nrsd.ensure(n); sc.win_tab.ensure((size_t)n * 4 * 16);   // 15 window multiples + the half-product
     G16_LAUNCH(assemble_phase1_kernel, dim3(n, 3), FB_WINDOWS, 0, st, true, keys, n, mA, mB1, rs, sc.Ar.p, sc.Bs1.p, sc.nrsd.p);
+    // G16_ASSEMBLE_TEAM=0: the one-kernel form (a thread per half-product)
+    static const int team = [] { const char* v = getenv("G16_ASSEMBLE_TEAM"); return v && *v ? atoi(v) : 1; }();
+    if (team) {
+        G16_LAUNCH(assemble_mul_team_kernel, dim3(div_up(n, 32), 4), 128, 0, st, true, n, (const G1XYZZ*)sc.Ar.p, (const G1XYZZ*)sc.Bs1.p, rs,
+                   sc.win_tab.p);
+        G16_LAUNCH(assemble_finish_kernel, div_up(n, 32), dim3(32, 2), 0, st, false, n, with_commitment ? 1 : 0, mK, mZ, (const G1XYZZ*)sc.Ar.p,
+                   (const G1XYZZ*)sc.nrsd.p, (const G1XYZZ*)sc.win_tab.p, out, out_stride);
+        G16_CHECK_LAUNCH();
+        return 3;
+    }
     G16_LAUNCH(assemble_phase2_kernel, div_up(n, 32), dim3(32, 5), 0, st, true, n, with_commitment ? 1 : 0, mK, mZ,
                (const G1XYZZ*)sc.Ar.p, (const G1XYZZ*)sc.Bs1.p, (const G1XYZZ*)sc.nrsd.p, rs, sc.win_tab.p, out, out_stride);
     G16_CHECK_LAUNCH();

@@ -2,6 +2,7 @@
 // the stage-level field / group test kernels. The Montgomery product stays out of line here (see field.cuh FD_MUL).
 #include "prover_kernels.cuh"
 #include "msm_types.hpp"
+#include "team.cuh"
 
 namespace g16 {
 
@@ -54,12 +55,41 @@ __global__ void group_op_kernel(int op, const typename C::A* __restrict__ a, con
     out[i] = acc.to_affine();
 }
 
+// the four-warp forms of team.cuh (G1): op 4: a + b with b made projective as in op 3 ; op 5: 4a + 2b (two team doublings of a,
+// one of b, one team addition: both operands projective). Block = one team, lane = instance.
+__global__ void __launch_bounds__(128)
+group_op_team_kernel(int op, const G1Affine* __restrict__ a, const G1Affine* __restrict__ b, G1Affine* __restrict__ out, size_t n) {
+    __shared__ Fp sm[TEAM4_SM_ELEMS];
+    __shared__ uint32_t flag;
+    Team4 T{sm, &flag, (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31), 0};
+    if (threadIdx.x == 0) flag = 0u;
+    __syncthreads();
+    const size_t i = (size_t)blockIdx.x * 32 + T.lane;
+    const bool live = i < n;
+    G1XYZZ acc = live ? G1XYZZ::from_affine(a[i]) : G1XYZZ::inf();
+    G1XYZZ o = live ? G1XYZZ::from_affine(b[i]) : G1XYZZ::inf();
+    if (op == 4) {
+        if (!o.is_inf()) {
+            Fp two = Fp::one().dbl(), four = two.dbl(), eight = four.dbl();
+            o.X = o.X * four; o.Y = o.Y * eight; o.ZZ = four; o.ZZZ = eight;
+        }
+        acc = team_add(T, acc, o, false);
+    } else {
+        acc = team_dbl(T, team_dbl(T, acc));
+        o = team_dbl(T, o);
+        acc = team_add(T, acc, o, false);
+    }
+    if (live && T.w == 0) out[i] = acc.to_affine();
+}
+
 void launch_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, cudaStream_t st) {
     G16_LAUNCH(field_op_kernel, div_up(n, 128), 128, 0, st, false, field, op, a, b, out, n);
     G16_CHECK_LAUNCH();
 }
 void launch_group_op(int group, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, cudaStream_t st) {
-    if (group == 1) {
+    if (group == 1 && op >= 4) {
+        G16_LAUNCH(group_op_team_kernel, div_up(n, 32), 128, 0, st, true, op, (const G1Affine*)a, (const G1Affine*)b, (G1Affine*)out, n);
+    } else if (group == 1) {
         auto k = group_op_kernel<G1>;
         G16_LAUNCH(k, div_up(n, 64), 64, 0, st, false, op, (const G1Affine*)a, b, (G1Affine*)out, n);
     } else {

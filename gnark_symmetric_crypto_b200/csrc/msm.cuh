@@ -17,6 +17,7 @@
 // Points are read with 128-bit loads (64 B / 128 B affine points are 16-byte aligned).
 #pragma once
 #include "msm_types.hpp"
+#include "team.cuh"
 #include <cstdlib>
 #include <type_traits>
 
@@ -687,6 +688,40 @@ __global__ void msm_combine_kernel(const typename C::X* __restrict__ S, uint32_t
     out[row] = acc;
 }
 
+// The same Horner pass for G1 by a team of four warps (team.cuh): block = 128 threads = one team, lane l = row 32 b + l. The
+// ~254 doublings are one dependent chain whatever the size of the MSM; a thread alone needs 3.95 us per doubling and 6.3 us
+// per addition, the team 2.5 and 3.9 (B200, scripts/proto/dbl_chain.cu): 2^16 points, combine 1.04 -> 0.65 ms.
+static __global__ void __launch_bounds__(128)
+msm_combine_team_kernel(const G1XYZZ* __restrict__ S, uint32_t rows, int nwin, int c, G1XYZZ* __restrict__ out) {
+    __shared__ Fp sm[TEAM4_SM_ELEMS];
+    __shared__ uint32_t flag;
+    Team4 T{sm, &flag, (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31), 0};
+    if (threadIdx.x == 0) flag = 0u;
+    __syncthreads();
+    const uint32_t row = blockIdx.x * 32 + T.lane;
+    const bool live = row < rows;   // dead lanes carry the point at infinity through the same barriers
+    G1XYZZ acc = G1XYZZ::inf();
+    for (int w = nwin - 1; w >= 0; w--) {
+        if (w != nwin - 1)
+            for (int k = 0; k < c; k++) acc = team_dbl(T, acc);
+        const G1XYZZ s = live ? S[(size_t)row * nwin + w] : G1XYZZ::inf();
+        acc = team_add(T, acc, s, false);
+    }
+    if (live && T.w == 0) out[row] = acc;
+}
+template <class C>
+static void msm_combine_launch(const typename C::X* S, uint32_t rows, int nwin, int c, typename C::X* out, cudaStream_t stream) {
+    if constexpr (std::is_same<C, G1>::value) {
+        static const int team = [] { const char* v = getenv("G16_MSM_COMBINE_TEAM"); return v && *v ? atoi(v) : 1; }();
+        if (team) {
+            G16_LAUNCH(msm_combine_team_kernel, div_up(rows, 32), 128, 0, stream, true, S, rows, nwin, c, out);
+            return;
+        }
+    }
+    auto k = msm_combine_kernel<C>;
+    G16_LAUNCH(k, div_up(rows, 64), 64, 0, stream, false, S, rows, nwin, c, out);
+}
+
 template <class C>
 __global__ void xyzz_to_affine_kernel(const typename C::X* __restrict__ in, uint32_t n, typename C::A* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -992,8 +1027,7 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     if (sh.precomp) {
         G16_CUDA(cudaMemcpyAsync(ws.result.p, inV, (size_t)sh.rows * sizeof(X), cudaMemcpyDeviceToDevice, stream));
     } else {
-        auto k = msm_combine_kernel<C>;
-        G16_LAUNCH(k, div_up(sh.rows, 64), 64, 0, stream, false, inV, sh.rows, sh.nwin, sh.c, ws.result.p);
+        msm_combine_launch<C>(inV, sh.rows, sh.nwin, sh.c, ws.result.p, stream);
         ws.launches++;
     }
     G16_CHECK_LAUNCH();

@@ -376,7 +376,7 @@ def field_op(field: int, op: str, a: np.ndarray, b: np.ndarray | None = None) ->
 
 
 def group_op(group: int, op: str, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:
-    code = {"add": 0, "mul": 1, "dbl": 2, "add_xyzz": 3}[op]
+    code = {"add": 0, "mul": 1, "dbl": 2, "add_xyzz": 3, "add_team": 4, "dbl_add_team": 5}[op]
     w = 8 if group == 1 else 16
     a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, w)
     out = np.empty_like(a)

@@ -132,7 +132,8 @@ int g16_last_counters_ex(const g16_ctx* ctx, uint64_t out[16]);
 /* field: 0 = Fp, 1 = Fr. op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 sqr(a), 5 neg(a), 6 to_mont(a), 7 from_mont(a) */
 int g16_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 /* group: 1 = G1, 2 = G2. op 0: out = a + b (affine in/out) ; op 1: out = k * a, k = canonical scalar limbs in b (4 u64)
- * ; op 2: out = 2a */
+ * ; op 2: out = 2a ; op 3: a + b through the general (projective) addition ; G1 only, the four-warp forms the serial tails of
+ * the MSM and of the proof assembly use (csrc/team.cuh): op 4: a + b ; op 5: 4a + 2b */
 int g16_group_op(int group, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 /* decompression of gnark-crypto compressed points (32 / 64 bytes each) -> affine Montgomery */
 int g16_decompress(int group, const uint8_t* in, uint64_t* out, size_t n);

@@ -57,6 +57,15 @@ def test_group_ops_and_special_cases(emu, oracle):
         ok(emu, emu.g16_group_op(1, op, p64(P), p64(Q), p64(out), 12))
         assert np.array_equal(out, ref), op
     assert not ref[1].any()
+    ok(emu, emu.g16_group_op(1, 4, p64(P), p64(Q), p64(out), 12))          # the four-warp addition (team.cuh)
+    assert np.array_equal(out, ref)
+    # 4a + 2b with both operands projective: b = 2a (equal points, different representations), b = -2a (infinity), infinities
+    Q5 = Q.copy(); P5 = P.copy()
+    Q5[0] = oracle.g1_add(P[0], P[0])
+    Q5[1] = oracle.g1_add(P[1], P[1]); Q5[1][4:8] = oracle.f_op(0, "neg", Q5[1][4:8].reshape(1, 4))[0]
+    ref5 = np.array([oracle.g1_add(oracle.g1_mul(P5[i], 4), oracle.g1_mul(Q5[i], 2)) for i in range(12)])
+    ok(emu, emu.g16_group_op(1, 5, p64(P5), p64(Q5), p64(out), 12))
+    assert np.array_equal(out, ref5) and not ref5[1].any()
     sc = oracle.rand_field(rng, 1, 12)
     ok(emu, emu.g16_group_op(1, 1, p64(P), p64(sc), p64(out), 12))
     assert np.array_equal(out, np.array([oracle.g1_mul(P[i], oracle.limbs_to_ints(sc[i:i + 1])[0]) for i in range(12)]))

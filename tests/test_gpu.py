@@ -44,8 +44,14 @@ def test_group_ops(G, oracle):
     P = oracle.g1_fixed_base(oracle.rand_field(rng, 1, n)); Q = oracle.g1_fixed_base(oracle.rand_field(rng, 1, n))
     Q[0] = P[0]; Q[1] = P[1]; Q[1][4:8] = oracle.f_op(0, "neg", P[1][4:8].reshape(1, 4))[0]; Q[2] = 0; P[3] = 0
     ref = np.array([oracle.g1_add(P[i], Q[i]) for i in range(n)])
-    for op in ("add", "add_xyzz"):
+    for op in ("add", "add_xyzz", "add_team"):
         assert np.array_equal(G.group_op(1, op, P, Q), ref), op
+    # four-warp forms with both operands projective (csrc/team.cuh): 4a + 2b with b = 2a, b = -2a, infinities
+    Q5 = Q.copy()
+    Q5[0] = oracle.g1_add(P[0], P[0])
+    Q5[1] = oracle.g1_add(P[1], P[1]); Q5[1][4:8] = oracle.f_op(0, "neg", Q5[1][4:8].reshape(1, 4))[0]
+    ref5 = np.array([oracle.g1_add(oracle.g1_mul(P[i], 4), oracle.g1_mul(Q5[i], 2)) for i in range(n)])
+    assert np.array_equal(G.group_op(1, "dbl_add_team", P, Q5), ref5) and not ref5[1].any()
     sc = oracle.rand_field(rng, 1, n)
     ref = np.array([oracle.g1_mul(P[i], oracle.limbs_to_ints(sc[i:i + 1])[0]) for i in range(n)])
     assert np.array_equal(G.group_op(1, "mul", P, sc), ref)
