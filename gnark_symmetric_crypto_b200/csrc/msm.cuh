@@ -629,31 +629,29 @@ msm_tree_block_kernel(const typename C::X* __restrict__ in_R, const typename C::
     const X run = sm[0];                      // sum of all children
     __syncthreads();
     if (!LEVEL1 && t == 0) sm[0] = X::inf();  // upper levels: child k has weight k, so S_0 does not count
+    // upper levels also sum the children's own weighted sums: that tree runs in the second half of the shared memory, on the
+    // upper half of the block, at the same time as the tree over the suffix sums (different warps, different partitions)
+    X* smV = sm + TB;
+    if (!LEVEL1) {
+        const X* V = in_V + (size_t)seg * n_in + lo;
+        smV[t] = t < g ? V[t] : X::inf();
+    }
     __syncthreads();
-    for (uint32_t s2 = TB / 2; s2 >= 1; s2 >>= 1) {   // tree sum of the suffix sums
+    for (uint32_t s2 = TB / 2; s2 >= 1; s2 >>= 1) {   // tree sums
+        const bool doS = t < s2, doV = !LEVEL1 && t >= TB / 2 && t < TB / 2 + s2;
+        const uint32_t u = t - TB / 2;
         X a;
-        if (t < s2) { a = sm[t]; a.add(sm[t + s2]); }
+        if (doS) { a = sm[t]; a.add(sm[t + s2]); }
+        else if (doV) { a = smV[u]; a.add(smV[u + s2]); }
         __syncthreads();
-        if (t < s2) sm[t] = a;
+        if (doS) sm[t] = a;
+        else if (doV) smV[u] = a;
         __syncthreads();
     }
     X tot = sm[0];
-    if (!LEVEL1) {
-        __syncthreads();
-        const X* V = in_V + (size_t)seg * n_in + lo;
-        sm[t] = t < g ? V[t] : X::inf();      // plus the children's own weighted sums
-        __syncthreads();
-        for (uint32_t s2 = TB / 2; s2 >= 1; s2 >>= 1) {
-            X a;
-            if (t < s2) { a = sm[t]; a.add(sm[t + s2]); }
-            __syncthreads();
-            if (t < s2) sm[t] = a;
-            __syncthreads();
-        }
-        if (t == 0) {
-            for (int d = 0; d < log_span_child; d++) tot = tot.dbl();
-            tot.add(sm[0]);
-        }
+    if (!LEVEL1 && t == 0) {
+        for (int d = 0; d < log_span_child; d++) tot = tot.dbl();
+        tot.add(smV[0]);
     }
     if (t == 0) {
         out_R[blockIdx.x] = run;
@@ -745,8 +743,11 @@ __global__ void msm_precompute_kernel(const typename C::A* __restrict__ pts, uin
     }
 }
 
-// arity of the block-parallel tree node: 256 children for G1 (32 KB of shared memory), 128 for G2 (32 KB)
-template <class C> struct MsmTreeBlock { static const int LOG_TB = 8, TB = 256; };
+// arity of the block-parallel tree node: 128 children (16 KB of shared memory for G1, 32 KB for G2). A node is a chain of
+// ~3 log2(TB) dependent additions in which every warp of the block takes part, and a warp alone on its scheduler partition runs
+// an addition in 6.3 us whatever its live lanes: with 256 threads two warps share each partition's multiplier and every step
+// takes twice as long (2^16 points, fixed base, ncu: 280 + 256 us for the two block levels of 256 children).
+template <class C> struct MsmTreeBlock { static const int LOG_TB = 7, TB = 128; };
 template <> struct MsmTreeBlock<G2> { static const int LOG_TB = 7, TB = 128; };
 
 // the batch-affine levels exist for G1 only (k_msm_ba.cu)
@@ -974,7 +975,9 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
     int log_g = ((size_t)segs * ((n_in + MSM_TREE_G - 1) / MSM_TREE_G) < sm_count() * 256) ? MSM_TREE_LOG_G_SMALL : MSM_TREE_LOG_G;
     // small problems: block-parallel nodes of arity MSM_TREE_TB (log-depth) instead of thread-serial nodes of arity 4
     static const int tree_block = [] { const char* v = getenv("G16_MSM_TREE_BLOCK"); return v && *v ? atoi(v) : 1; }();
-    static const int tree_block_max = [] { const char* v = getenv("G16_MSM_TREE_BLOCK_MAX"); return v && *v ? atoi(v) : 96; }();
+    // at most one block per SM (G1: 128 threads = one warp per partition); G2 keeps the measured 96
+    static const int tree_block_max_env = [] { const char* v = getenv("G16_MSM_TREE_BLOCK_MAX"); return v && *v ? atoi(v) : 0; }();
+    const int tree_block_max = tree_block_max_env > 0 ? tree_block_max_env : (std::is_same<C, G1>::value ? (int)sm_count() : 96);
     const bool use_block = tree_block && log_g == MSM_TREE_LOG_G_SMALL;
     const int TBK = MsmTreeBlock<C>::TB;
     const X* inR = ws.buckets.p;
@@ -992,7 +995,7 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
         ws.lvlR[pp].ensure((size_t)segs * n_out);
         ws.lvlV[pp].ensure((size_t)segs * n_out);
         if (block_level) {
-            const size_t smem = (size_t)TBK * sizeof(X);
+            const size_t smem = (size_t)2 * TBK * sizeof(X);   // suffix sums | the children's weighted sums
 #if !defined(G16_EMU)
             static bool attr_done = false;
             if (!attr_done && smem > 48 * 1024) {
