@@ -895,11 +895,13 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
         row_tot = ws.tile_sums.p;
         row_base = ws.tile_sums.p + 2 * (size_t)sh.rows;
 #if !defined(G16_EMU)
-        static bool attr_done = false;   // > 48 KB of dynamic shared memory needs the opt-in (once per process and kernel)
-        if (!attr_done) {
+        static bool attr_done[64] = {};   // > 48 KB of dynamic shared memory needs the opt-in (once per device and kernel)
+        int dev = 0;
+        G16_CUDA(cudaGetDevice(&dev));
+        if (!attr_done[dev & 63]) {
             G16_CUDA(cudaFuncSetAttribute(msm_rowsort_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
             G16_CUDA(cudaFuncSetAttribute(msm_rowsort_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-            attr_done = true;
+            attr_done[dev & 63] = true;
         }
 #endif
         G16_LAUNCH(msm_rowsort_kernel<0>, sh.rows, ROWSORT_T, rowsort_smem, stream, true, sh, scalars, row_stride, elem_stride, map, is_mont, pad_mask,
@@ -997,11 +999,15 @@ void msm_run(MsmWorkspace<C>& ws, const MsmShape& sh, const typename C::A* bases
         if (block_level) {
             const size_t smem = (size_t)2 * TBK * sizeof(X);   // suffix sums | the children's weighted sums
 #if !defined(G16_EMU)
-            static bool attr_done = false;
-            if (!attr_done && smem > 48 * 1024) {
+            // > 48 KB of dynamic shared memory (G2: 64 KB) needs the opt-in, and the attribute belongs to the DEVICE the call is
+            // made on: a process that drives several GPUs (g16_init_multi) sets it once on each
+            static bool attr_done[64] = {};
+            int dev = 0;
+            G16_CUDA(cudaGetDevice(&dev));
+            if (smem > 48 * 1024 && !attr_done[dev & 63]) {
                 G16_CUDA(cudaFuncSetAttribute(msm_tree_block_kernel<C, 1, MsmTreeBlock<C>::TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 G16_CUDA(cudaFuncSetAttribute(msm_tree_block_kernel<C, 0, MsmTreeBlock<C>::TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_done = true;
+                attr_done[dev & 63] = true;
             }
 #endif
             if (level == 1) {
