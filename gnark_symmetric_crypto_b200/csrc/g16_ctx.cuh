@@ -388,7 +388,10 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
 
     // ---- fixed-base tables (built now, or on the first prove when G16_LAZY_TABLES=1 — gnark's icicle backend also
     //      defers its device set-up to the first Prove)
-    cx->qZ.c = env_int("G16_C_Z", 15);
+    // Z query: c = 15 for the 2^15 domain of ChaCha (14 / 16 measured: 153.1 / 158.0 vs 150.5 ms per 1024 proofs); the 2^17
+    // domain of the AES circuits has four times the entries per bucket, so one window less pays for the larger tree
+    // (AES-128, 256 proofs: 171.5 -> 168.8 ms at c = 16, 188.0 at c = 14; profiles/sweep_r02g_aes_windows.jsonl)
+    cx->qZ.c = env_int("G16_C_Z", pk.nZ >= (1u << 16) ? 16 : 15);
     cx->qA.c = env_int("G16_C_A", 13);
     cx->qB.c = env_int("G16_C_B", 13);
     cx->qK.c = env_int("G16_C_K", 13);
@@ -572,7 +575,10 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
         cx->ped_basis = std::move(basis);
         cx->ped_basis_sigma = std::move(basis_sigma);
         cx->qPed.n = cx->qPedSigma.n = pk.ped[0].n_basis;
-        cx->qPed.c = cx->qPedSigma.c = env_int("G16_C_PED", 16);
+        // c = 11: the ~6 k committed wires of the AES circuits give ~30 k entries per proof, so a bucket set of 2^15 (c = 16, the
+        // value until late round 2) cost 9.4 ms of reduction tree per 256 proofs and query for 0.65 ms of accumulation
+        // (profiles/launches_r02g_aes128_batch256_summary.txt); sweep 10..16 in profiles/sweep_r02g_aes_pedersen_window.log
+        cx->qPed.c = cx->qPedSigma.c = env_int("G16_C_PED", 11);
         cx->qPed.map.upload(ci.private_committed.data(), ci.private_committed.size(), st);
         cx->qPedSigma.map.upload(ci.private_committed.data(), ci.private_committed.size(), st);
         G16_CUDA(cudaStreamSynchronize(st));
