@@ -104,8 +104,21 @@ static size_t launch_solver_levels(const SolverProgram& sp, const uint32_t* h_le
 #if !defined(G16_EMU)
         if (hi > split) {
             dim3 grid(div_up(hi - split, SOLVER_WARPS), batch);
-            G16_LAUNCH(solver_level_small_kernel, grid, dim3(32, SOLVER_WARPS), 0, st, false, sp, split, hi, batch, W, w_stride, A,
-                       B, C, status);
+            // small batches: programmatic stream serialisation, so that the launch of a level overlaps the level before it
+            // (G16_SOLVER_PDL=0: plain launches)
+            static const int pdl = [] { const char* v = getenv("G16_SOLVER_PDL"); return v && *v ? atoi(v) : 1; }();
+            if (small && pdl) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = grid; cfg.blockDim = dim3(32, SOLVER_WARPS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                G16_CUDA(cudaLaunchKernelEx(&cfg, solver_level_small_pdl_kernel, sp, split, hi, batch, W, w_stride, A, B, C, status));
+            } else {
+                G16_LAUNCH(solver_level_small_kernel, grid, dim3(32, SOLVER_WARPS), 0, st, false, sp, split, hi, batch, W, w_stride, A,
+                           B, C, status);
+            }
             launches++;
         }
         if (end > hi) {

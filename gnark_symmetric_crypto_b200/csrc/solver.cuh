@@ -358,6 +358,26 @@ solver_level_small_kernel(SolverProgram sp, uint32_t lo, uint32_t hi, uint32_t b
     if (inst >= batch || k >= hi) return;   // warp-uniform
     solve_item_warp(sp, sp.level_instr[k], inst, W, w_stride, A, B, C, status);
 }
+// The same kernel for launches with programmatic stream serialisation (the small-batch graph of k_solver.cu): the grid may be
+// scheduled while the level before it is still running — it says so to the level after it at once, fetches its instruction
+// (program data, written at init), and only then waits for the level before it to complete and flush its wires. A level of one
+// request is a few microseconds of work behind a few microseconds of launch latency; this hides the latter behind the former.
+__global__ void __launch_bounds__(32 * SOLVER_WARPS)
+solver_level_small_pdl_kernel(SolverProgram sp, uint32_t lo, uint32_t hi, uint32_t batch, Fr* W, size_t w_stride, Fr* A, Fr* B,
+                              Fr* C, uint32_t* status) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
+    const uint32_t inst = blockIdx.y;
+    const uint32_t k = lo + blockIdx.x * blockDim.y + threadIdx.y;
+    const bool live = inst < batch && k < hi;   // warp-uniform
+    const uint32_t ins = live ? sp.level_instr[k] : 0u;
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+    if (!live) return;
+    solve_item_warp(sp, ins, inst, W, w_stride, A, B, C, status);
+}
 // (Measured on B200 and not adopted: all levels in ONE cooperative launch, warps striding over the items of a level and
 // meeting in grid.sync(). One ChaCha proof: 3.3 ms against 1.5 ms for one launch per level — back-to-back launches overlap
 // the tail of a level with the head of the next, a grid-wide barrier cannot.)
