@@ -88,7 +88,9 @@ struct Ctx {
     MsmWorkspace<G2> ws2;    // B2 query, side stream
     cudaStream_t stream2 = nullptr;
     cudaStream_t stream3 = nullptr;   // lane 1 of the pipelined schedule
+    cudaStream_t stream4 = nullptr;   // the half-products of the assembly, as soon as the A and B1 queries of the batch are done
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_ab = nullptr, ev_prod = nullptr;   // A / B1 results complete (side stream) ; half-products done (stream4)
     std::vector<cudaEvent_t> ev_solved;   // one per sub-batch: witness complete
     std::vector<cudaEvent_t> ev_hdone;    // pipelined schedule: transforms of sub-batch k done
     bool pipeline_stagger = true;         // G16_PIPE_STAGGER
@@ -136,6 +138,9 @@ struct Ctx {
         for (auto e : ev_hdone) cudaEventDestroy(e);
         for (auto s : solve_streams) cudaStreamDestroy(s);
         if (stream3) cudaStreamDestroy(stream3);
+        if (stream4) cudaStreamDestroy(stream4);
+        if (ev_ab) cudaEventDestroy(ev_ab);
+        if (ev_prod) cudaEventDestroy(ev_prod);
         if (stream2) cudaStreamDestroy(stream2);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -258,7 +263,10 @@ static std::unique_ptr<Ctx> ctx_create(const uint8_t* pk_bytes, size_t pk_len, c
     G16_CUDA(cudaEventCreate(&cx->ev_fork));
     G16_CUDA(cudaEventCreate(&cx->ev_join));
     G16_CUDA(cudaStreamCreate(&cx->stream3));
+    G16_CUDA(cudaStreamCreate(&cx->stream4));
     G16_CUDA(cudaEventCreate(&cx->ev_join3));
+    G16_CUDA(cudaEventCreate(&cx->ev_ab));
+    G16_CUDA(cudaEventCreate(&cx->ev_prod));
     G16_CUDA(cudaEventCreate(&cx->ev_t0));
     G16_CUDA(cudaEventCreate(&cx->ev_t1));
     cudaStream_t st = cx->stream;
@@ -719,6 +727,7 @@ static void ctx_wire_queries(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaSt
     if (bitq && cx.bqB.on) {
         const BitQuery& bq = cx.bqB;
         run_query_bitq_g1(cx, st2, bq, w, n, rows, true, cx.resB1.p + sb);
+        if (sb + rows == n) G16_CUDA(cudaEventRecord(cx.ev_ab, st2));   // A and B1 of the whole batch are complete
         // the G2 element of the same wires: same entries, the G2 table
         G2XYZZ* out2 = cx.resB2.p + sb;
         if (bq.rest.n) {
@@ -733,6 +742,7 @@ static void ctx_wire_queries(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaSt
         xyzz_add_g2(out2, cx.bitq_tmp2.p, rows, st2);
     } else {
         run_query_g1(cx.ws1b, st2, cx.qB, w, 1, n, true, rows, cx.resB1.p + sb, nullptr);
+        if (sb + rows == n) G16_CUDA(cudaEventRecord(cx.ev_ab, st2));   // A and B1 of the whole batch are complete
         MsmShape sh = msm_make_shape(cx.nB2, rows, cx.cB2, 1);
         msm_run_g2(cx.ws2, sh, cx.tabB2.p, w, 1, n, cx.qB.map.p, 1, st2, nullptr);
         G16_CUDA(cudaMemcpyAsync(cx.resB2.p + sb, cx.ws2.result.p, (size_t)rows * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st2));
@@ -915,6 +925,15 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
         G16_CUDA(cudaEventRecord(cx.ev_join3, lane[1]));
         G16_CUDA(cudaStreamWaitEvent(st, cx.ev_join3, 0));
     }
+    // Ar, Bs1, -rs delta and the half-products s*Ar, r*Bs1 only need the A and B1 results: they run on their own stream beside
+    // the K / B2 queries and the Z query (G16_ASSEMBLE_EARLY=0: after the last MSM, on the main stream)
+    static const int asm_early = env_int("G16_ASSEMBLE_EARLY", 1);
+    const bool early = asm_early && assemble_team_enabled();
+    if (early) {
+        G16_CUDA(cudaStreamWaitEvent(cx.stream4, cx.ev_ab, 0));
+        own += launch_assemble_products(cx.keys, cx.asm_scratch, (uint32_t)n, cx.resA.p, cx.resB1.p, cx.d_rs.p, cx.stream4);
+        G16_CUDA(cudaEventRecord(cx.ev_prod, cx.stream4));
+    }
     // the G2 element only needs the G2 MSM: assembled on the side stream, off the critical path of the G1 chain
     launch_assemble_g2(cx.keys, (uint32_t)n, cx.resB2.p, cx.d_rs.p, cx.d_proofs.p, cx.proof_bytes(), st2);
     own += 1;
@@ -922,8 +941,13 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     G16_CUDA(cudaStreamWaitEvent(st, cx.ev_join, 0));
     tm.mark(ST_ASSEMBLE, st);
     if (eval_z) { xyzz_add_g1(cx.resZ.p, cx.resZc.p, (uint32_t)n, st); own += 1; }
-    own += launch_assemble(cx.keys, cx.asm_scratch, cx.n_commit != 0, (uint32_t)n, cx.resA.p, cx.resB1.p, cx.resK.p, cx.resZ.p,
-                           cx.d_rs.p, cx.d_proofs.p, cx.proof_bytes(), st);
+    if (early) {
+        G16_CUDA(cudaStreamWaitEvent(st, cx.ev_prod, 0));
+        own += launch_assemble_finish(cx.asm_scratch, cx.n_commit != 0, (uint32_t)n, cx.resK.p, cx.resZ.p, cx.d_proofs.p, cx.proof_bytes(), st);
+    } else {
+        own += launch_assemble(cx.keys, cx.asm_scratch, cx.n_commit != 0, (uint32_t)n, cx.resA.p, cx.resB1.p, cx.resK.p, cx.resZ.p,
+                               cx.d_rs.p, cx.d_proofs.p, cx.proof_bytes(), st);
+    }
     if (cx.n_commit) {
         launch_assemble_commitment(cx.commit_aff.p, cx.resPok.p, (uint32_t)n, cx.d_proofs.p, cx.proof_bytes(), st);
         own += 1;
@@ -942,6 +966,7 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     cx.stage_ms[7] = (float)cx.launches;
     G16_CUDA(cudaStreamSynchronize(st2));
     G16_CUDA(cudaStreamSynchronize(cx.stream3));
+    G16_CUDA(cudaStreamSynchronize(cx.stream4));
     if (bitq_profiling && !(status & 7u)) {
         std::vector<uint32_t> f(cx.nb_wires);
         cx.d_bit_flags.download(f.data(), cx.nb_wires, st);

@@ -82,6 +82,12 @@ void launch_fixed_base_table_g1(const G1Affine& base, G1Affine* tab, cudaStream_
 size_t launch_assemble(const AssemblyKeys& keys, AssemblyScratch& sc, bool with_commitment, uint32_t n, const G1XYZZ* mA,
                        const G1XYZZ* mB1, const G1XYZZ* mK, const G1XYZZ* mZ, const Fr* rs, uint8_t* out, size_t out_stride,
                        cudaStream_t st);
+// the same in two parts (team form, G16_ASSEMBLE_TEAM != 0): what only needs the A / B1 results, and the rest
+bool assemble_team_enabled();
+size_t launch_assemble_products(const AssemblyKeys& keys, AssemblyScratch& sc, uint32_t n, const G1XYZZ* mA, const G1XYZZ* mB1,
+                                const Fr* rs, cudaStream_t st);
+size_t launch_assemble_finish(AssemblyScratch& sc, bool with_commitment, uint32_t n, const G1XYZZ* mK, const G1XYZZ* mZ, uint8_t* out,
+                              size_t out_stride, cudaStream_t st);
 void launch_assemble_g2(const AssemblyKeys& keys, uint32_t n, const G2XYZZ* mB2, const Fr* rs, uint8_t* out, size_t out_stride,
                         cudaStream_t st);
 // AES-CTR witness (provers.go:172-227): key_len 16 or 32; W wire-major
