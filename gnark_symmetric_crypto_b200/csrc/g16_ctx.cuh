@@ -91,6 +91,10 @@ struct Ctx {
     cudaStream_t stream4 = nullptr;   // the half-products of the assembly, as soon as the A and B1 queries of the batch are done
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     cudaEvent_t ev_ab = nullptr, ev_prod = nullptr;   // A / B1 results complete (side stream) ; half-products done (stream4)
+    // small batches: the four wire-driven queries run side by side (ctx_wire_queries_fan) — B1, B2, K on streams of their own
+    cudaStream_t fan[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fan[4] = {nullptr, nullptr, nullptr, nullptr};
+    MsmWorkspace<G1> wsf[2];   // B1 and K queries of the fan (ws1b keeps A)
     std::vector<cudaEvent_t> ev_solved;   // one per sub-batch: witness complete
     std::vector<cudaEvent_t> ev_hdone;    // pipelined schedule: transforms of sub-batch k done
     bool pipeline_stagger = true;         // G16_PIPE_STAGGER
@@ -139,6 +143,8 @@ struct Ctx {
         for (auto s : solve_streams) cudaStreamDestroy(s);
         if (stream3) cudaStreamDestroy(stream3);
         if (stream4) cudaStreamDestroy(stream4);
+        for (auto& f : fan) if (f) cudaStreamDestroy(f);
+        for (auto& e : ev_fan) if (e) cudaEventDestroy(e);
         if (ev_ab) cudaEventDestroy(ev_ab);
         if (ev_prod) cudaEventDestroy(ev_prod);
         if (stream2) cudaStreamDestroy(stream2);
@@ -712,6 +718,39 @@ static size_t ctx_solve(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaStream_
     return launches;
 }
 
+// Small batches (G16_QUERY_FAN, <= 4 proofs): every wire-driven query is a chain of ~15 short, latency-bound launches (digits,
+// scans, accumulate, merge levels, tree), and one after the other on the side stream they took 1.8 ms for one request — 0.8 ms
+// longer than the transforms and the Z query on the main stream, which then waited for them. Here A stays on the side stream and
+// B1, B2 and K each get a stream and a workspace of their own; the side stream joins them again, and the half-products of the
+// assembly (stream4) are released as soon as A and B1 are there.
+static void ctx_wire_queries_fan(Ctx& cx, size_t n, uint32_t rows, cudaStream_t st2) {
+    const Fr* w = cx.W.p;
+    if (!cx.fan[0]) {
+        for (auto& f : cx.fan) G16_CUDA(cudaStreamCreate(&f));
+        for (auto& e : cx.ev_fan) G16_CUDA(cudaEventCreate(&e));
+    }
+    cx.ws1b.no_ba = cx.wsf[0].no_ba = cx.wsf[1].no_ba = cx.n_commit == 0;
+    G16_CUDA(cudaEventRecord(cx.ev_fan[0], st2));   // the witness is complete (the side stream has waited for the solver)
+    for (auto& f : cx.fan) G16_CUDA(cudaStreamWaitEvent(f, cx.ev_fan[0], 0));
+    run_query_g1(cx.ws1b, st2, cx.qA, w, 1, n, true, rows, cx.resA.p, nullptr);
+    run_query_g1(cx.wsf[0], cx.fan[0], cx.qB, w, 1, n, true, rows, cx.resB1.p, nullptr);
+    G16_CUDA(cudaEventRecord(cx.ev_fan[1], cx.fan[0]));
+    {
+        MsmShape sh = msm_make_shape(cx.nB2, rows, cx.cB2, 1);
+        msm_run_g2(cx.ws2, sh, cx.tabB2.p, w, 1, n, cx.qB.map.p, 1, cx.fan[1], nullptr);
+        G16_CUDA(cudaMemcpyAsync(cx.resB2.p, cx.ws2.result.p, (size_t)rows * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, cx.fan[1]));
+        G16_CUDA(cudaEventRecord(cx.ev_fan[2], cx.fan[1]));
+    }
+    run_query_g1(cx.wsf[1], cx.fan[2], cx.qK, w, 1, n, true, rows, cx.resK.p, nullptr);
+    G16_CUDA(cudaEventRecord(cx.ev_fan[3], cx.fan[2]));
+    G16_CUDA(cudaStreamWaitEvent(st2, cx.ev_fan[1], 0));
+    G16_CUDA(cudaEventRecord(cx.ev_ab, st2));   // A and B1 of the whole batch are complete
+    if (cx.n_commit)   // proof of knowledge of the commitment: same scalars over BasisExpSigma
+        run_query_g1(cx.ws1b, st2, cx.qPedSigma, w, 1, n, true, rows, cx.resPok.p, nullptr);
+    G16_CUDA(cudaStreamWaitEvent(st2, cx.ev_fan[2], 0));
+    G16_CUDA(cudaStreamWaitEvent(st2, cx.ev_fan[3], 0));
+}
+
 // the wire-driven queries of one sub-batch (A, B1, K on G1, B on G2, the commitment PoK): short, latency-bound kernels
 static void ctx_wire_queries(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaStream_t st2, bool eval_z = false) {
     const Fr* w = cx.W.p + sb;   // column offset into the wire-major array
@@ -722,6 +761,11 @@ static void ctx_wire_queries(Ctx& cx, size_t n, size_t sb, uint32_t rows, cudaSt
     if (eval_z)   // C-evaluation half of the Z query: almost every scalar is 0 or +-1
         run_query_g1(cx.ws1b, st2, cx.qQc, cx.Cev.p + sb * cx.n_dom, cx.n_dom, 1, false, rows, cx.resZc.p + sb, nullptr);
     const bool bitq = cx.bitq_state == 1 && cx.bitq_built && n >= cx.bitq_min_batch;
+    static const int fan_max = env_int("G16_QUERY_FAN", 4);   // measured: 1 / 2 proofs 3.49 / 3.72 -> 2.81 / 3.08 ms, 8 / 16 proofs 4.85 / 6.57 -> 4.95 / 6.60 ms
+    if (!eval_z && !bitq && sb == 0 && rows == n && (int)n <= fan_max) {
+        ctx_wire_queries_fan(cx, n, rows, st2);
+        return;
+    }
     if (bitq && cx.bqA.on) run_query_bitq_g1(cx, st2, cx.bqA, w, n, rows, true, cx.resA.p + sb);
     else run_query_g1(cx.ws1b, st2, cx.qA, w, 1, n, true, rows, cx.resA.p + sb, nullptr);
     if (bitq && cx.bqB.on) {
@@ -782,11 +826,13 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     if (eval_z) ctx_build_eval_tables(cx);
     StageTimer& tm = cx.timer;
     tm.reset();
-    size_t l0 = cx.ws1.launches + cx.ws1c.launches + cx.ws1b.launches + cx.ws2.launches + cx.dom.launches;
+    size_t l0 = cx.ws1.launches + cx.ws1c.launches + cx.ws1b.launches + cx.ws2.launches + cx.dom.launches + cx.wsf[0].launches + cx.wsf[1].launches;
     size_t own = 0;
     cx.ws1.log_reset();
     cx.ws1c.log_reset();
     cx.ws1b.log_reset();
+    cx.wsf[0].log_reset();
+    cx.wsf[1].log_reset();
     cx.ws2.log_reset();
     const bool piped = cx.pipeline && n > cx.sub_batch;
     tm.mark(piped ? ST_COUNT : ST_SOLVE, st);   // pipelined: one interval that only counts towards the total
@@ -962,7 +1008,7 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     float total = tm.finish(per);
     for (int i = 0; i < ST_COUNT; i++) cx.stage_ms[i] = per[i];
     cx.stage_ms[6] = total;
-    cx.launches = own + (cx.ws1.launches + cx.ws1c.launches + cx.ws1b.launches + cx.ws2.launches + cx.dom.launches - l0);
+    cx.launches = own + (cx.ws1.launches + cx.ws1c.launches + cx.ws1b.launches + cx.ws2.launches + cx.dom.launches + cx.wsf[0].launches + cx.wsf[1].launches - l0);
     cx.stage_ms[7] = (float)cx.launches;
     G16_CUDA(cudaStreamSynchronize(st2));
     G16_CUDA(cudaStreamSynchronize(cx.stream3));
@@ -995,7 +1041,7 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
     cx.counters[12] = (uint64_t)cx.bqA.rest.n | ((uint64_t)cx.bqB.rest.n << 20) | ((uint64_t)cx.bqK.rest.n << 40);   // points left on the general path
     cx.counters[11] = (uint64_t)cx.bitq_state | ((uint64_t)(bitq_live ? 1 : 0) << 8) | ((uint64_t)cx.bqA.groups << 16) | ((uint64_t)cx.bqK.groups << 40);
     cx.counters[6] = cx.ws1.log_sum(st) + cx.ws1c.log_sum(cx.stream3);   // G1 mixed additions of the Z query (lanes)
-    cx.counters[0] = cx.counters[6] + cx.ws1b.log_sum(st2);               // ... of all G1 queries
+    cx.counters[0] = cx.counters[6] + cx.ws1b.log_sum(st2) + cx.wsf[0].log_sum(cx.fan[0]) + cx.wsf[1].log_sum(cx.fan[2]);               // ... of all G1 queries
     cx.counters[1] = cx.ws2.log_sum(st2);   // G2 mixed additions
     cx.counters[2] = cx.ws1.log_n + cx.ws1c.log_n + cx.ws1b.log_n;   // G1 accumulate launches
     cx.counters[3] = cx.ws2.log_n;
