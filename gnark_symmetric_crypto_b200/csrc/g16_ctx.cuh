@@ -627,6 +627,16 @@ static void run_query_g1(MsmWorkspace<G1>& ws, cudaStream_t st, const PrecompQue
     G16_CUDA(cudaMemcpyAsync(out, ws.result.p, (size_t)rows * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
 }
 
+// The batch-affine levels in front of the Z query's accumulation pay from ~16 ChaCha proofs on: below 2^23 entries their
+// fixed latency (nine more launches, three rounds of inversions) is larger than the products they save, and since the
+// wire-driven queries of a small batch no longer hide it (ctx_wire_queries_fan) it is on the critical path — 4 proofs 4.18 ->
+// 3.40 ms, 8 proofs 4.89 -> 4.73 ms, 16 and more unchanged (profiles/sweep_r02j_query_fan.log). G16_Z_BA_MIN moves the threshold.
+static void z_query_ba_policy(MsmWorkspace<G1>& ws, const PrecompQuery& q, uint32_t rows) {
+    static const int zmin = env_int("G16_Z_BA_MIN", 1 << 23);
+    const size_t entries = (size_t)rows * q.n * (size_t)((254 + q.c - 1) / q.c);
+    ws.no_ba = entries < (size_t)zmin;
+}
+
 // ---- combination tables (k_bitq.cu)
 static void bitq_build_one(Ctx& cx, BitQuery& bq, const PrecompQuery& q, const std::vector<uint32_t>& map, const G1Affine* pts1,
                            const G2Affine* pts2, const G2Affine* tab2, int c2, cudaStream_t st) {
@@ -922,10 +932,12 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
             tm.mark(ST_H, st);
             if (eval_z) {
                 compute_d_run(cx.dom, a, cx.Bev.p + sb * cx.n_dom, cx.n_dom, rows, st);
+                z_query_ba_policy(cx.ws1, cx.qQd, rows);
                 run_query_g1(cx.ws1, st, cx.qQd, a, cx.n_dom, 1, false, rows, cx.resZ.p + sb, &tm);
             } else {
                 compute_h_run(cx.dom, a, cx.Bev.p + sb * cx.n_dom, cx.Cev.p + sb * cx.n_dom, cx.n_dom, rows, st);
                 // h (gnark order) pairs index-for-index with G1.Z; the other queries read wire values through their maps
+                z_query_ba_policy(cx.ws1, cx.qZ, rows);
                 run_query_g1(cx.ws1, st, cx.qZ, a, cx.n_dom, 1, false, rows, cx.resZ.p + sb, &tm);
             }
             ctx_wire_queries(cx, n, sb, rows, st2, eval_z);
@@ -961,6 +973,7 @@ static float ctx_run_batch(Ctx& cx, size_t n, int kind) {
             else compute_h_run(cx.dom, a, cx.Bev.p + sb * cx.n_dom, cx.Cev.p + sb * cx.n_dom, cx.n_dom, rows, s);
             if (cx.ev_hdone.size() <= k) { cudaEvent_t e; G16_CUDA(cudaEventCreate(&e)); cx.ev_hdone.push_back(e); }
             G16_CUDA(cudaEventRecord(cx.ev_hdone[k], s));
+            z_query_ba_policy(wz, eval_z ? cx.qQd : cx.qZ, rows);
             run_query_g1(wz, s, eval_z ? cx.qQd : cx.qZ, a, cx.n_dom, 1, false, rows, cx.resZ.p + sb, nullptr);
         }
         if (bitq_profiling) {   // the side stream has waited for every sub-batch's witness by now
